@@ -1,0 +1,177 @@
+"""ctypes binding of the CPU oracle (oracle/libranslice_oracle.so).  Test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "libranslice_oracle.so")
+
+PROPAGATION = {"macro_cell_urban_2GHz": (128.1, 37.6), "macro_cell_urban_900MHz": (120.9, 37.6),
+               "macro_cell_rural": (95.5, 34.1)}
+SCENARIOS = [(200, 5, 0), (150, 3, 2), (100, 1, 4), (70, 1, 1)]   # n_prbs, n_embb, n_mmtc
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [("n_prbs", C.c_int32), ("n_embb", C.c_int32), ("n_mmtc", C.c_int32),
+                ("slots_per_step", C.c_int32), ("penalty", C.c_double), ("prop_A", C.c_double),
+                ("prop_B", C.c_double)]
+
+
+class OrcTables(C.Structure):
+    _fields_ = [("trace", C.c_void_p), ("mcs_rate", C.c_void_p), ("mcs_snr", C.c_void_p),
+                ("mcs_order", C.c_void_p), ("mcs_mod", C.c_void_p)]
+
+
+F_RANDOM = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int)
+F_EXP = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_double)
+F_INT = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64)
+F_NORMAL = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double)
+F_RANDOM2 = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double))
+
+
+class OrcRng(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("random", F_RANDOM), ("exponential", F_EXP), ("integers", F_INT),
+                ("choice", F_INT), ("normal", F_NORMAL), ("random2", F_RANDOM2)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_ROOT, "oracle")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcTables), C.c_uint64]
+        L.orc_set_rng.argtypes = [C.c_void_p, C.POINTER(OrcRng)]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_n_variables.argtypes = [C.c_void_p]
+        L.orc_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_step.restype = C.c_uint32
+        L.orc_step.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orc_step_batch.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        L.orc_mcs_lut.argtypes = [C.POINTER(OrcTables), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int)]
+        L.orc_response.restype = C.c_double
+        L.orc_response.argtypes = [C.POINTER(OrcTables), C.c_int, C.c_void_p, C.c_int]
+        L.orc_macro_cell.restype = C.c_double
+        L.orc_macro_cell.argtypes = [C.c_double] * 5
+        L.orc_n_ues.argtypes = [C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def c_tables(tables):
+    t = OrcTables(_ptr(tables.trace), _ptr(tables.mcs_rate), _ptr(tables.mcs_snr), _ptr(tables.mcs_order),
+                  _ptr(tables.mcs_mod))
+    t._keep = tables
+    return t
+
+
+class NumpyRng:
+    """orc_rng vtable backed by a numpy Generator + the legacy global np.random (VBR stream),
+    i.e. exactly the reference's native RNG usage."""
+
+    def __init__(self, rng):
+        self.rng = rng
+        g = rng
+
+        def random(ctx, sl, st):
+            return float(g.random())
+
+        def exponential(ctx, sl, st, scale):
+            if st == 3:                                   # ORC_STREAM_VBR -> legacy global stream
+                return float(np.random.exponential(scale))
+            return float(g.exponential(scale))
+
+        def integers(ctx, sl, st, n):
+            return int(g.integers(n))
+
+        def choice(ctx, sl, st, n):
+            return int(g.choice(n))
+
+        def normal(ctx, sl, st, mu, sigma):
+            return float(g.normal(mu, sigma))
+
+        def random2(ctx, sl, st, out):
+            v = g.random(2)
+            out[0] = v[0]
+            out[1] = v[1]
+
+        self.struct = OrcRng(None, F_RANDOM(random), F_EXP(exponential), F_INT(integers), F_INT(choice),
+                             F_NORMAL(normal), F_RANDOM2(random2))
+
+
+class OracleEnv:
+    """One oracle environment (scenario index like scenario_creator.create_env)."""
+
+    def __init__(self, tables, scenario, seed, slots_per_step=50, penalty=100.0,
+                 propagation="macro_cell_urban_2GHz", numpy_rng=None):
+        n_prbs, n_embb, n_mmtc = SCENARIOS[scenario]
+        A, B = PROPAGATION[propagation]
+        self.cfg = OrcConfig(n_prbs, n_embb, n_mmtc, slots_per_step, penalty, A, B)
+        self.tbl = c_tables(tables)
+        self.S = n_embb + n_mmtc
+        self.V = 10 * n_embb + 3 * n_mmtc
+        self.n_prbs = n_prbs
+        self.h = lib().orc_create(C.byref(self.cfg), C.byref(self.tbl), C.c_uint64(seed))
+        self._rng = None
+        if numpy_rng is not None:
+            self._rng = NumpyRng(numpy_rng)
+            lib().orc_set_rng(self.h, C.byref(self._rng.struct))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        obs = np.zeros(self.V, np.float32)
+        lib().orc_reset(self.h, _ptr(obs))
+        return obs
+
+    def step(self, action):
+        a = np.ascontiguousarray(action, np.int64)
+        obs = np.zeros(self.V, np.float32)
+        rew = np.zeros(1, np.float64)
+        lab = np.zeros(self.S, np.int32)
+        vio = np.zeros(self.S, np.int32)
+        acc = np.zeros((self.S, 10), np.float64)
+        flags = lib().orc_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(lab), _ptr(vio), _ptr(acc))
+        return obs, float(rew[0]), lab, vio, acc, flags
+
+
+class OracleBatch:
+    """N independent oracle envs with Philox seeds base_seed + i, stepped by n_threads pthreads."""
+
+    def __init__(self, tables, scenario, n_envs, base_seed, n_threads=1, first_env=0, **kw):
+        self.envs = [OracleEnv(tables, scenario, base_seed + first_env + i, **kw) for i in range(n_envs)]
+        self.N, self.S, self.V = n_envs, self.envs[0].S, self.envs[0].V
+        self.n_threads = n_threads
+        self.handles = (C.c_void_p * n_envs)(*[e.h for e in self.envs])
+
+    def reset(self):
+        return np.stack([e.reset() for e in self.envs])
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.int64).reshape(self.N, self.S)
+        obs = np.zeros((self.N, self.V), np.float32)
+        rew = np.zeros(self.N, np.float64)
+        lab = np.zeros((self.N, self.S), np.int32)
+        vio = np.zeros((self.N, self.S), np.int32)
+        flags = np.zeros(self.N, np.uint32)
+        lib().orc_step_batch(self.handles, self.N, self.n_threads, _ptr(a), _ptr(obs), _ptr(rew), _ptr(lab),
+                             _ptr(vio), _ptr(flags))
+        return obs, rew, lab, vio, flags
