@@ -1,0 +1,109 @@
+/*
+ * ranslice_b200.h -- C ABI of the B200-native batched RAN-slicing env (libranslice_b200.so).
+ *
+ * Drop-in boundary for the reference's gym env step path.  The reference has no FFI (it is
+ * pure Python); each entry point below names the reference interface it replaces, N
+ * independent environments at a time.  Binding shown in INTEGRATION.md (ctypes).
+ *
+ * Conventions: plain C, opaque handle, caller-owned buffers, return 0 on success and a negative
+ * RS_E_* code on failure (rs_last_error() gives the message); no exceptions cross the boundary;
+ * one handle is used from one host thread at a time.  Arrays are row-major:
+ *   action [N][S] int32   PRBs per slice (eMBB slices first, then mMTC; scenario_creator.py:158-166)
+ *   obs    [N][V] float32 V = 10*n_embb + 3*n_mmtc            (node_b.py:40-44)
+ *   reward [N]    float32                                     (ran_slice.py:45-54)
+ *   labels [N][S] int32   +1 / -1                             (slice_l1.py:160-171)
+ *   violations [N][S] int32 0 / 1                             (slice_ran.py:307-319, 145-148)
+ *   flags  [N]    uint32  RS_FLAG_* bits (out-of-contract events; the reference prints or crashes)
+ */
+#ifndef RANSLICE_B200_H
+#define RANSLICE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+
+enum { RS_OK = 0, RS_E_ARG = -1, RS_E_CUDA = -2, RS_E_NOMEM = -3, RS_E_STATE = -4 };
+
+enum {
+    RS_FLAG_UE_CAP = 1u,        /* an arriving UE was dropped: max_ues live UEs in the slice            */
+    RS_FLAG_BURST_CAP = 2u,     /* a VBR burst was dropped: max_bursts active bursts in the UE          */
+    RS_FLAG_ACTION_CLAMP = 4u,  /* action < 0 or sum(action) > n_prbs: clamped (node_b.py:71-74 has no check) */
+    RS_FLAG_SAME_SLOT_DEP = 8u, /* holding time rounded to 1 slot: UE dropped (reference: KeyError, channel_models.py:194) */
+    RS_FLAG_MTC_QUEUE_CAP = 16u /* mMTC backlog exceeded mtc_queue_cap: arrival dropped                 */
+};
+
+/* scenario_creator.create_env(rng, n, slots_per_step, propagation_type, L1_level=True, penalty)
+ * (scenario_creator.py:100-183) flattened into a POD.  Traffic / SLA / normalisation constants
+ * (scenario_creator.py:55-96,115-134) are fixed inside the library exactly as in the reference. */
+typedef struct rs_config {
+    int32_t abi_version;    /* RS_ABI_VERSION */
+    int32_t device;         /* CUDA device ordinal */
+    int32_t n_envs;         /* N environments stepped in lockstep on this device */
+    int32_t n_prbs, n_embb, n_mmtc;   /* scenario_creator.py:26-50 */
+    int32_t slots_per_step; /* 50 */
+    int32_t max_ues;        /* live-UE cap per eMBB slice (<= 32); 0 -> default 16 */
+    int32_t max_bursts;     /* active-burst cap per VBR UE (<= 16); 0 -> default 8 */
+    int32_t mtc_queue_cap;  /* mMTC backlog cap per slice; 0 -> default 128 */
+    int32_t kernel_variant; /* 0 = default (fastest validated); see DESIGN.md */
+    int32_t reserved;
+    double penalty;         /* ran_slice.py:19 */
+    double prop_A, prop_B;  /* channel_models.py:117-124 */
+    uint64_t base_seed;     /* Philox key of env e is base_seed + first_env_id + e */
+    uint64_t first_env_id;  /* global id of local env 0 (multi-GPU sharding, results invariant to the split) */
+} rs_config;
+
+/* Host pointers; copied to the device by rs_create. */
+typedef struct rs_tables {
+    const double *trace;    /* [3][10001][100] time-major fading traces (channel_models.py:141-150), col 10000 = NaN */
+    const double *mcs_rate; /* [26] datasets/mcs_codeset.csv 'rate'  */
+    const double *mcs_snr;  /* [26] 'snr'   */
+    const int32_t *mcs_order; /* [26] 'order' */
+    const int32_t *mcs_mod;   /* [26] 0 qpsk, 1 16qam, 2 64qam */
+} rs_tables;
+
+typedef struct rs_handle rs_handle;
+
+/* create_env(...) -> env.   Allocates SoA state for N envs in HBM, uploads tables. */
+int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out);
+int rs_destroy(rs_handle *h);
+
+/* RanSlice.reset() (ran_slice.py:30-36 -> node_b.py:17-22).  obs (host, may be NULL) <- zeros. */
+int rs_reset(rs_handle *h, float *obs);
+
+/* RanSlice.step(action) (ran_slice.py:38-54) for all N envs; HOST buffers (any of the outputs may
+ * be NULL).  Copies action H2D, runs the step kernels, copies results D2H, synchronises. */
+int rs_step(rs_handle *h, const int32_t *action, float *obs, float *reward, int32_t *labels,
+            int32_t *violations, uint32_t *flags);
+
+/* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = legacy default). */
+int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d_reward,
+                   int32_t *d_labels, int32_t *d_violations, uint32_t *d_flags, void *stream);
+
+/* info['l1_info'] of one env (node_b.py:46-49): raw accumulators of the last step, [S][10]
+ * (eMBB order scenario_creator.py:80-82; mMTC: devices, avg_rep, delay, then zeros) and the
+ * PRBs in force per slice [S]. */
+int rs_get_info(rs_handle *h, int32_t env, double *acc, int32_t *n_prbs);
+
+/* live UEs per eMBB slice [N][n_embb] (host buffer); population diagnostics */
+int rs_get_n_ues(rs_handle *h, int32_t *n_ues);
+
+/* checkpoint / restore of the whole device state (state_dict-style dump) */
+int rs_state_size(rs_handle *h, size_t *bytes);
+int rs_get_state(rs_handle *h, void *blob, size_t bytes);
+int rs_set_state(rs_handle *h, const void *blob, size_t bytes);
+
+/* counters: kernels launched by this handle so far; algorithmic fading-trace elements touched in
+ * the last step summed over envs (B_trace of SURVEY 8d, 0 if the variant does not count) */
+int rs_get_counters(rs_handle *h, uint64_t *kernel_launches, uint64_t *trace_elems_last_step);
+
+int rs_n_variables(const rs_handle *h);
+const char *rs_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,149 @@
+"""BatchedRanSlice: N independent RAN-slicing envs advanced in lockstep on one B200.
+
+Mirrors ``RanSlice.reset()/step()`` (gym-ran_slice/gym_ran_slice/ran_slice.py:30-54) with a
+leading env axis.  Two call paths, both through the C ABI (include/ranslice_b200.h):
+
+* ``step(action)``          host numpy in / host numpy out (``rs_step``: H2D + kernels + D2H);
+* ``step_device(action)``   torch CUDA tensors in / out, asynchronous on torch's current stream
+                            (``rs_step_device``); no host round trip.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .scenario_creator import PROPAGATION, scenarios
+from .tables import load_tables
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class BatchedRanSlice:
+    def __init__(self, scenario=0, n_envs=1, base_seed=0, slots_per_step=50,
+                 propagation_type='macro_cell_urban_2GHz', penalty=100, device=0, first_env_id=0,
+                 max_ues=0, max_bursts=0, mtc_queue_cap=0, kernel_variant=0, tables=None):
+        sc = scenarios[scenario] if isinstance(scenario, int) else scenario
+        self.n_prbs, self.n_embb, self.n_mmtc = sc['n_prbs'], sc['n_embb'], sc['n_mmtc']
+        self.n_slices = self.n_embb + self.n_mmtc
+        self.n_variables = 10 * self.n_embb + 3 * self.n_mmtc
+        self.n_envs, self.device, self.penalty = n_envs, device, penalty
+        self.slots_per_step = slots_per_step
+        A, B = PROPAGATION[propagation_type]
+        L = _lib.lib()
+        t = tables or load_tables()
+        self._tables = t
+        self._cfg = _lib.RsConfig(_lib.RS_ABI_VERSION, device, n_envs, self.n_prbs, self.n_embb, self.n_mmtc,
+                                  slots_per_step, max_ues, max_bursts, mtc_queue_cap, kernel_variant, 0,
+                                  float(penalty), A, B, base_seed & (2 ** 64 - 1), first_env_id)
+        tb = _lib.RsTables(_p(t.trace), _p(t.mcs_rate), _p(t.mcs_snr), _p(t.mcs_order), _p(t.mcs_mod))
+        h = C.c_void_p()
+        _lib.check(L.rs_create(C.byref(self._cfg), C.byref(tb), C.byref(h)))
+        self._h = h
+        N, S, V = n_envs, self.n_slices, self.n_variables
+        self._pin = None
+        self._alloc_host(N, S, V)
+
+    # ---------------------------------------------------------------- host buffers (pinned when torch+CUDA)
+    def _alloc_host(self, N, S, V):
+        try:
+            import torch
+            pin = torch.cuda.is_available()
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=pin)
+            self._pin = dict(action=mk((N, S), torch.int32), obs=mk((N, V), torch.float32),
+                             reward=mk((N,), torch.float32), labels=mk((N, S), torch.int32),
+                             violations=mk((N, S), torch.int32), flags=mk((N,), torch.int32))
+            self._hb = {k: v.numpy() for k, v in self._pin.items()}
+            self._hb['flags'] = self._hb['flags'].view(np.uint32)
+        except ImportError:
+            self._hb = dict(action=np.empty((N, S), np.int32), obs=np.empty((N, V), np.float32),
+                            reward=np.empty(N, np.float32), labels=np.empty((N, S), np.int32),
+                            violations=np.empty((N, S), np.int32), flags=np.empty(N, np.uint32))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().rs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- gym-like API
+    def reset(self):
+        """-> float32 zeros [N, V] (ran_slice.py:30-36)."""
+        _lib.check(_lib.lib().rs_reset(self._h, _p(self._hb['obs'])))
+        return self._hb['obs'].copy()
+
+    def step(self, action):
+        """action int [N, S] -> (obs f32 [N,V], reward f32 [N], done False, info dict of arrays)."""
+        a = np.asarray(action)
+        if a.shape != (self.n_envs, self.n_slices):
+            raise ValueError("The action must contain as many elements as slices! expected %s got %s"
+                             % ((self.n_envs, self.n_slices), a.shape))     # node_b.py:66-68 prints; we raise
+        hb = self._hb
+        np.copyto(hb['action'], a, casting='unsafe')
+        _lib.check(_lib.lib().rs_step(self._h, _p(hb['action']), _p(hb['obs']), _p(hb['reward']), _p(hb['labels']),
+                                      _p(hb['violations']), _p(hb['flags'])))
+        info = {'SLA_labels': hb['labels'].copy(), 'violations': hb['violations'].copy(),
+                'total_violations': hb['violations'].sum(axis=1), 'flags': hb['flags'].copy()}
+        return hb['obs'].copy(), hb['reward'].copy(), False, info
+
+    def step_host_inplace(self, action_i32):
+        """Zero-copy variant for throughput loops: ``action_i32`` is int32 [N,S] (ideally pinned);
+        results land in the env's pinned host buffers (returned without copying)."""
+        hb = self._hb
+        _lib.check(_lib.lib().rs_step(self._h, _p(action_i32), _p(hb['obs']), _p(hb['reward']), _p(hb['labels']),
+                                      _p(hb['violations']), _p(hb['flags'])))
+        return hb
+
+    def step_device(self, action, out=None):
+        """torch int32 CUDA tensor [N,S] -> dict of CUDA tensors; async on the current torch stream."""
+        import torch
+        assert action.is_cuda and action.dtype == torch.int32 and action.is_contiguous()
+        assert tuple(action.shape) == (self.n_envs, self.n_slices)
+        if out is None:
+            dev = action.device
+            N, S, V = self.n_envs, self.n_slices, self.n_variables
+            out = dict(obs=torch.empty((N, V), dtype=torch.float32, device=dev),
+                       reward=torch.empty((N,), dtype=torch.float32, device=dev),
+                       labels=torch.empty((N, S), dtype=torch.int32, device=dev),
+                       violations=torch.empty((N, S), dtype=torch.int32, device=dev),
+                       flags=torch.empty((N,), dtype=torch.int32, device=dev))
+        stream = torch.cuda.current_stream(action.device).cuda_stream
+        _lib.check(_lib.lib().rs_step_device(
+            self._h, C.c_void_p(action.data_ptr()), C.c_void_p(out['obs'].data_ptr()),
+            C.c_void_p(out['reward'].data_ptr()), C.c_void_p(out['labels'].data_ptr()),
+            C.c_void_p(out['violations'].data_ptr()), C.c_void_p(out['flags'].data_ptr()), C.c_void_p(stream)))
+        return out
+
+    # ---------------------------------------------------------------- introspection
+    def get_info(self, env=0):
+        acc = np.zeros((self.n_slices, 10), np.float64)
+        prbs = np.zeros(self.n_slices, np.int32)
+        _lib.check(_lib.lib().rs_get_info(self._h, env, _p(acc), _p(prbs)))
+        return acc, prbs
+
+    def n_ues(self):
+        out = np.zeros((self.n_envs, max(self.n_embb, 1)), np.int32)
+        _lib.check(_lib.lib().rs_get_n_ues(self._h, _p(out)))
+        return out[:, :self.n_embb]
+
+    def counters(self):
+        k, t = C.c_uint64(), C.c_uint64()
+        _lib.check(_lib.lib().rs_get_counters(self._h, C.byref(k), C.byref(t)))
+        return int(k.value), int(t.value)
+
+    def get_state(self):
+        n = C.c_size_t()
+        _lib.check(_lib.lib().rs_state_size(self._h, C.byref(n)))
+        blob = np.empty(n.value, np.uint8)
+        _lib.check(_lib.lib().rs_get_state(self._h, _p(blob), n))
+        return blob
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _lib.check(_lib.lib().rs_set_state(self._h, _p(blob), C.c_size_t(blob.size)))

@@ -1,0 +1,153 @@
+// K2: mMTC slice step + end-of-period reduction (reward).
+//
+//   SliceL1mMTC.slot        slice_l1.py:87-125       FIFO of queued devices with repetition counters
+//   SliceRANmMTC.slot/reset slice_ran.py:91-121      1000 periodic devices, deterministic inter-arrival
+//   RanSlice.step reward    ran_slice.py:45-54
+//
+// The reference decrements 1000 countdowns per slot (slice_ran.py:107); here every device stores the
+// ABSOLUTE slot of its next arrival, so one step scans the 1000 words once (coalesced across units)
+// and only arriving devices are rewritten.  All arithmetic is integer except the per-slot means.
+#include <cuda_runtime.h>
+
+#include "philox.cuh"
+#include "ranslice_state.cuh"
+
+namespace rs {
+
+__device__ __constant__ int c_REP_SET[7] = {2, 4, 8, 16, 32, 64, 128};                     // scenario_creator.py:88
+__device__ __constant__ int c_PERIOD_SET[8] = {1000, 50000, 10000, 15000, 20000, 25000, 50000, 100000};  // :89 (50000 twice)
+
+constexpr int MTC_MAX_ARR = 96;   // arrivals buffered per unit per step (mean 8.2, Poisson-like)
+
+// SliceRANmMTC.reset (slice_ran.py:91-101) + SliceL1mMTC.reset (slice_l1.py:29-39)
+__global__ void __launch_bounds__(128) mmtc_reset_kernel(const __grid_constant__ StepParams p,
+                                                         const __grid_constant__ MmtcState st) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= st.U) return;
+    const int env = u / p.n_mmtc, m = u - env * p.n_mmtc;
+    const uint64_t seed = p.seed0 + (uint64_t)env;
+    PhiloxStream r{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(p.n_embb + m), STREAM_MTC, st.ctr[u]};
+    for (int i = 0; i < N_MTC_DEV; ++i) {
+        const uint32_t rep_ix = r.integers(7);
+        const uint32_t per_ix = r.integers(8);
+        const uint32_t t = 1u + r.integers((uint32_t)c_PERIOD_SET[per_ix]);
+        st.rep_ix[(size_t)i * st.U + u] = (uint8_t)rep_ix;
+        st.period_ix[(size_t)i * st.U + u] = (uint8_t)per_ix;
+        st.next_abs[(size_t)i * st.U + u] = t;               // time == 0 after reset
+    }
+    st.ctr[u] = r.n;
+    st.q_n[u] = 0;
+    st.time[u] = 0;
+    st.acc[(size_t)u * 3 + 0] = st.acc[(size_t)u * 3 + 1] = st.acc[(size_t)u * 3 + 2] = 0.0;
+}
+
+__global__ void __launch_bounds__(128) mmtc_step_kernel(const __grid_constant__ StepParams p,
+                                                        const __grid_constant__ MmtcState st) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int U = st.U;
+    if (u >= U) return;
+    const int env = u / p.n_mmtc, m = u - env * p.n_mmtc, s = p.n_embb + m;
+    uint32_t flags = 0;
+    // PRBs of this slice after clamping (mMTC ignores i_prb, slice_l1.py:50-51)
+    int n_prbs;
+    {
+        const int32_t *a = p.action + (size_t)env * p.S;
+        int off = 0, mine = 0;
+        for (int j = 0; j <= s; ++j) {
+            int v = a[j];
+            if (v < 0) { v = 0; flags |= 4u; }
+            if (off + v > p.n_prbs) { v = p.n_prbs - off; flags |= 4u; }
+            if (j == s) mine = v; else off += v;
+        }
+        n_prbs = mine;
+    }
+    st.cur_prbs[u] = n_prbs;
+
+    const uint32_t t0 = st.time[u];
+    // ---- arrivals of this period: devices whose next arrival falls in (t0, t0+slots], in (slot, device) order
+    uint16_t arr_dev[MTC_MAX_ARR];
+    uint8_t arr_slot[MTC_MAX_ARR];
+    int n_arr = 0;
+    for (int i = 0; i < N_MTC_DEV; ++i) {
+        const uint32_t d = st.next_abs[(size_t)i * U + u] - t0;     // wrap-safe: periods << 2^31
+        if (d >= 1u && d <= (uint32_t)p.slots) {
+            if (n_arr < MTC_MAX_ARR) { arr_dev[n_arr] = (uint16_t)i; arr_slot[n_arr] = (uint8_t)d; ++n_arr; }
+            else flags |= 16u;
+            st.next_abs[(size_t)i * U + u] += (uint32_t)c_PERIOD_SET[st.period_ix[(size_t)i * U + u]];  // period >= 1000 > slots
+        }
+    }
+    int q_n = st.q_n[u];
+    double a_delay = 0.0, a_rep = 0.0;
+    long long a_dev = 0;
+    for (int t = 1; t <= p.slots; ++t) {
+        const uint32_t now = t0 + (uint32_t)t;                     // self.time += 1
+        for (int k = 0; k < n_arr; ++k)                            // add_users, ascending device index (np.where)
+            if (arr_slot[k] == t) {
+                if (q_n < st.Q) {
+                    st.q_rep[(size_t)q_n * U + u] = c_REP_SET[st.rep_ix[(size_t)arr_dev[k] * U + u]];
+                    st.q_t0[(size_t)q_n * U + u] = now;
+                    ++q_n;
+                } else flags |= 16u;
+            }
+        const int n_tx = min(n_prbs, q_n);                         // one carrier (PRB) per device
+        int w = 0;
+        long long sd = 0, sr = 0;
+        for (int k = 0; k < q_n; ++k) {
+            int rep = st.q_rep[(size_t)k * U + u];
+            if (k < n_tx) rep -= 1;
+            if (rep > 0) {
+                const uint32_t t_start = st.q_t0[(size_t)k * U + u];
+                if (w != k) st.q_t0[(size_t)w * U + u] = t_start;
+                st.q_rep[(size_t)w * U + u] = rep;
+                sd += (long long)(now - t_start);                  // np.maximum(0, time - t_start): never negative
+                sr += rep;
+                ++w;
+            }
+        }
+        q_n = w;
+        if (w > 0) {
+            a_delay += (double)sd / (double)w;                     // delays.mean()
+            a_rep += rint((double)sr / (double)w);                 // np.rint(repetitions.mean())
+            a_dev += w;
+        }
+    }
+    st.q_n[u] = q_n;
+    st.time[u] = t0 + (uint32_t)p.slots;
+
+    // ---- state (slice_ran.py:133-137), SLA (:145-148)
+    const double acc[3] = {(double)a_dev, a_rep, a_delay};
+    float *obs = p.obs + (size_t)env * p.V + p.n_embb * 10 + m * 3;
+    for (int j = 0; j < 3; ++j) { obs[j] = (float)(acc[j] / p.norm_mmtc[j]); st.acc[(size_t)u * 3 + j] = acc[j]; }
+    const int viol = !(a_delay / (double)p.slots < 300.0);
+    p.violations[(size_t)env * p.S + s] = viol;
+    p.labels[(size_t)env * p.S + s] = viol ? -1 : 1;
+    if (flags) atomicOr(p.flags_acc + env, flags);
+}
+
+// RanSlice.step epilogue (ran_slice.py:45-54): one thread per env
+__global__ void __launch_bounds__(256) reward_kernel(const __grid_constant__ StepParams p) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.N) return;
+    int tv = 0, asum = 0;
+    for (int s = 0; s < p.S; ++s) {
+        tv += p.violations[(size_t)env * p.S + s];
+        asum += p.action[(size_t)env * p.S + s];
+    }
+    const double r = tv > 0 ? -1.0 * p.penalty * (double)tv : (double)max(0, p.n_prbs - asum);
+    p.reward[env] = (float)r;
+    const uint32_t f = p.flags_acc[env];
+    p.flags[env] = f;
+    if (f) p.flags_acc[env] = 0u;
+}
+
+void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
+    mmtc_reset_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
+}
+void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
+    mmtc_step_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
+}
+void launch_reward(const StepParams &p, cudaStream_t stream) {
+    reward_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p);
+}
+
+}  // namespace rs

@@ -1,0 +1,352 @@
+// C ABI of libranslice_b200 (include/ranslice_b200.h): handle lifecycle, HBM state arena, table
+// upload, step orchestration.  No torch types; the Python layer binds it with ctypes.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ranslice_b200.h"
+#include "ranslice_state.cuh"
+
+namespace rs {
+void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+void launch_embb_coop(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, int sm_count);
+void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
+void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
+void launch_reward(const StepParams &p, cudaStream_t stream);
+}  // namespace rs
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(RS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
+    } while (0)
+
+struct rs_handle {
+    rs_config cfg;
+    rs::StepParams p;
+    rs::EmbbState embb;
+    rs::MmtcState mmtc;
+    rs::Tables tb;
+    int sm_count;
+    // persistent state arena (checkpointable)
+    char *arena;
+    size_t arena_bytes;
+    // tables + I/O staging
+    double *d_trace;
+    float *d_trace32;
+    int32_t *d_action;
+    float *d_obs, *d_reward;
+    int32_t *d_labels, *d_violations;
+    uint32_t *d_flags, *d_flags_acc;
+    unsigned long long *d_trace_elems;
+    cudaStream_t stream;
+    uint64_t launches;
+    bool was_reset;
+};
+
+namespace {
+
+struct Carver {
+    size_t off = 0;
+    char *base = nullptr;
+    template <typename T>
+    T *take(size_t n) {
+        off = (off + 255) & ~size_t(255);
+        T *ptr = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return ptr;
+    }
+};
+
+void carve(rs_handle *h, Carver &c) {
+    rs::EmbbState &e = h->embb;
+    const size_t U = (size_t)e.U, K = (size_t)e.K, MB = (size_t)e.MB;
+    e.n_ues = c.take<int32_t>(U);
+    e.cbr_next = c.take<int32_t>(U);
+    e.vbr_next = c.take<int32_t>(U);
+    e.ctr = c.take<uint32_t>(4 * U);
+    e.meta = c.take<uint32_t>(K * U);
+    e.rem = c.take<int32_t>(K * U);
+    e.nominal = c.take<double>(K * U);
+    e.queue = c.take<long long>(K * U);
+    e.th = c.take<double>(K * U);
+    e.bits = c.take<int32_t>(K * U);
+    e.pe = c.take<int32_t>(K * U);
+    e.vnext = c.take<int32_t>(K * U);
+    e.nb = c.take<int32_t>(K * U);
+    e.togo = c.take<int32_t>(K * MB * U);
+    e.acc = c.take<double>(U * 10);
+    e.cur_prbs = c.take<int32_t>(U);
+    rs::MmtcState &m = h->mmtc;
+    const size_t UM = (size_t)m.U, Q = (size_t)m.Q, D = (size_t)rs::N_MTC_DEV;
+    m.next_abs = c.take<uint32_t>(D * UM);
+    m.period_ix = c.take<uint8_t>(D * UM);
+    m.rep_ix = c.take<uint8_t>(D * UM);
+    m.q_rep = c.take<int32_t>(Q * UM);
+    m.q_t0 = c.take<uint32_t>(Q * UM);
+    m.q_n = c.take<int32_t>(UM);
+    m.time = c.take<uint32_t>(UM);
+    m.ctr = c.take<uint32_t>(UM);
+    m.acc = c.take<double>(UM * 3);
+    m.cur_prbs = c.take<int32_t>(UM);
+}
+
+double sigmoid(double x) { return 1.0 / (1.0 + std::exp(-x)); }
+
+// MCSCodeset.compute_factors / mcs_rate_vs_error (channel_models.py:272-295) folded into an integer LUT
+void build_tables(const rs_tables *t, rs::Tables &tb) {
+    double A = 1.0 / 0.1;
+    A = A * (std::log(1.0 / sigmoid(0.1) - 1.0) - std::log(1.0 / sigmoid(0.9) - 1.0));
+    const double B = -std::log(1.0 / sigmoid(0.9) - 1.0);
+    tb.A = A; tb.B = B;
+    for (int m = 0; m < 26; ++m) { tb.snr_ref[m] = t->mcs_snr[m]; tb.mod[m] = (int8_t)t->mcs_mod[m]; }
+    const double target = 1.0 - 0.1;
+    for (int i = 0; i < 256; ++i) {
+        const double snr = (double)(i - 128);
+        int mcs = 0, sel = 25, rate_ix = 25;
+        for (mcs = 0; mcs < 26; ++mcs)
+            if (sigmoid(A * (snr - t->mcs_snr[mcs]) - B) < target) { sel = mcs - 1 > 0 ? mcs - 1 : 0; rate_ix = mcs; break; }
+        const double bps = t->mcs_rate[rate_ix] * t->mcs_order[rate_ix];   // rate of the FAILING mcs
+        tb.lut_mcs[i] = (int8_t)sel;
+        tb.lut_rate[i] = (int16_t)(int)(158 * bps);                       // schedulers.py:45 truncation
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rs_last_error(void) { return g_err.c_str(); }
+
+int rs_n_variables(const rs_handle *h) { return h ? h->p.V : 0; }
+
+int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
+    if (!cfg || !tables || !out) return fail(RS_E_ARG, "null argument");
+    if (cfg->abi_version != RS_ABI_VERSION) return fail(RS_E_ARG, "abi_version mismatch");
+    if (cfg->n_envs <= 0 || cfg->n_embb < 0 || cfg->n_mmtc < 0 || cfg->n_embb + cfg->n_mmtc <= 0 ||
+        cfg->n_embb + cfg->n_mmtc > rs::MAX_SLICES)
+        return fail(RS_E_ARG, "bad n_envs / slice counts");
+    if (cfg->n_prbs <= 0 || cfg->n_prbs > 2 * rs::TRACE_ROWS)
+        return fail(RS_E_ARG, "n_prbs must be in [1, 200] (the trace rows wrap once, channel_models.py:144-148)");
+    if (cfg->slots_per_step <= 0 || cfg->slots_per_step > 255) return fail(RS_E_ARG, "slots_per_step must be in [1,255]");
+    const int K = cfg->max_ues ? cfg->max_ues : 16, MB = cfg->max_bursts ? cfg->max_bursts : 8;
+    const int Q = cfg->mtc_queue_cap ? cfg->mtc_queue_cap : 128;
+    if (K < 2 || K > 32 || MB < 1 || MB > 16 || Q < 1) return fail(RS_E_ARG, "caps out of range");
+    if (!tables->trace || !tables->mcs_rate || !tables->mcs_snr || !tables->mcs_order || !tables->mcs_mod)
+        return fail(RS_E_ARG, "null table pointer");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(RS_E_ARG, "bad device ordinal");
+    CU(cudaSetDevice(cfg->device));
+
+    rs_handle *h = new rs_handle();
+    std::memset(static_cast<void *>(h), 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->cfg.max_ues = K; h->cfg.max_bursts = MB; h->cfg.mtc_queue_cap = Q;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+
+    rs::StepParams &p = h->p;
+    p.N = cfg->n_envs; p.n_embb = cfg->n_embb; p.n_mmtc = cfg->n_mmtc; p.S = cfg->n_embb + cfg->n_mmtc;
+    p.n_prbs = cfg->n_prbs; p.slots = cfg->slots_per_step; p.V = 10 * cfg->n_embb + 3 * cfg->n_mmtc;
+    p.penalty = cfg->penalty; p.prop_A = cfg->prop_A; p.prop_B = cfg->prop_B;
+    p.seed0 = cfg->base_seed + cfg->first_env_id;
+    {   // scenario_creator.py:106,115-134 (same fp64 expressions)
+        const double tps = cfg->slots_per_step * 1e-3;
+        const int sps = cfg->slots_per_step;
+        const double ne[10] = {5e6 * tps, 10e6 * tps, 25.0 * sps, 10e4 * sps, 35.0 * sps,
+                               5e6 * tps, 10e6 * tps, 35.0 * sps, 10e4 * sps, 35.0 * sps};
+        std::memcpy(p.norm_embb, ne, sizeof ne);
+        for (int i = 0; i < 3; ++i) p.norm_mmtc[i] = 100.0 * sps;
+        p.obs_time = cfg->slots_per_step * 1e-3;
+    }
+    h->embb.U = cfg->n_envs * cfg->n_embb; h->embb.K = K; h->embb.MB = MB;
+    h->mmtc.U = cfg->n_envs * cfg->n_mmtc; h->mmtc.Q = Q;
+
+    Carver sizing;
+    carve(h, sizing);
+    h->arena_bytes = (sizing.off + 255) & ~size_t(255);
+    CU(cudaMalloc(&h->arena, h->arena_bytes));
+    CU(cudaMemset(h->arena, 0, h->arena_bytes));
+    Carver real; real.base = h->arena;
+    carve(h, real);
+
+    const size_t n_trace = (size_t)3 * rs::N_SAMPLES * rs::TRACE_ROWS;
+    CU(cudaMalloc(&h->d_trace, n_trace * sizeof(double)));
+    CU(cudaMemcpy(h->d_trace, tables->trace, n_trace * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<float> t32(n_trace);
+        for (size_t i = 0; i < n_trace; ++i) t32[i] = (float)tables->trace[i];
+        CU(cudaMalloc(&h->d_trace32, n_trace * sizeof(float)));
+        CU(cudaMemcpy(h->d_trace32, t32.data(), n_trace * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    build_tables(tables, h->tb);
+    h->tb.trace = h->d_trace; h->tb.trace32 = h->d_trace32;
+
+    const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;
+    CU(cudaMalloc(&h->d_action, N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_obs, N * V * sizeof(float)));
+    CU(cudaMalloc(&h->d_reward, N * sizeof(float)));
+    CU(cudaMalloc(&h->d_labels, N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_violations, N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_flags, N * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_flags_acc, N * sizeof(uint32_t)));
+    CU(cudaMemset(h->d_flags_acc, 0, N * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_trace_elems, sizeof(unsigned long long)));
+    CU(cudaMemset(h->d_trace_elems, 0, sizeof(unsigned long long)));
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    p.flags_acc = h->d_flags_acc;
+    p.trace_elems = h->d_trace_elems;
+    *out = h;
+    return RS_OK;
+}
+
+int rs_destroy(rs_handle *h) {
+    if (!h) return RS_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace32); cudaFree(h->d_action); cudaFree(h->d_obs);
+    cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
+    cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return RS_OK;
+}
+
+int rs_reset(rs_handle *h, float *obs) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    // NodeB.reset (node_b.py:17-22): UEs, timers and accumulators cleared; RNG counters keep running
+    // (the reference never reseeds on reset).  eMBB: zero everything but the counters.
+    rs::EmbbState &e = h->embb;
+    const size_t U = (size_t)e.U;
+    if (U) {
+        CU(cudaMemsetAsync(e.n_ues, 0, U * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(e.cbr_next, 0, U * sizeof(int32_t), h->stream));   // slice_ran.py:185-186
+        CU(cudaMemsetAsync(e.vbr_next, 0, U * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(e.acc, 0, U * 10 * sizeof(double), h->stream));
+    }
+    if (h->mmtc.U) {
+        rs::launch_mmtc_reset(h->p, h->mmtc, h->stream);
+        h->launches += 1;
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (obs) std::memset(obs, 0, sizeof(float) * (size_t)h->p.N * h->p.V);
+    h->was_reset = true;
+    return RS_OK;
+}
+
+int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d_reward, int32_t *d_labels,
+                   int32_t *d_violations, uint32_t *d_flags, void *stream) {
+    if (!h || !d_action) return fail(RS_E_ARG, "null handle/action");
+    if (!h->was_reset) return fail(RS_E_STATE, "rs_step before rs_reset");
+    CU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rs::StepParams p = h->p;
+    p.action = d_action;
+    p.obs = d_obs ? d_obs : h->d_obs;
+    p.reward = d_reward ? d_reward : h->d_reward;
+    p.labels = d_labels ? d_labels : h->d_labels;
+    p.violations = d_violations ? d_violations : h->d_violations;
+    p.flags = d_flags ? d_flags : h->d_flags;
+    CU(cudaMemsetAsync(h->d_trace_elems, 0, sizeof(unsigned long long), st));
+    if (h->embb.U) {
+        if (h->cfg.kernel_variant == 1) rs::launch_embb_unit_thread(p, h->embb, h->tb, st);
+        else rs::launch_embb_coop(p, h->embb, h->tb, st, h->sm_count);
+        h->launches += 1;
+    }
+    if (h->mmtc.U) { rs::launch_mmtc_step(p, h->mmtc, st); h->launches += 1; }
+    rs::launch_reward(p, st);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return RS_OK;
+}
+
+int rs_step(rs_handle *h, const int32_t *action, float *obs, float *reward, int32_t *labels, int32_t *violations,
+            uint32_t *flags) {
+    if (!h || !action) return fail(RS_E_ARG, "null handle/action");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)h->p.N, S = (size_t)h->p.S, V = (size_t)h->p.V;
+    CU(cudaMemcpyAsync(h->d_action, action, N * S * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = rs_step_device(h, h->d_action, nullptr, nullptr, nullptr, nullptr, nullptr, h->stream);
+    if (rc) return rc;
+    if (obs) CU(cudaMemcpyAsync(obs, h->d_obs, N * V * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (reward) CU(cudaMemcpyAsync(reward, h->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (labels) CU(cudaMemcpyAsync(labels, h->d_labels, N * S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (violations) CU(cudaMemcpyAsync(violations, h->d_violations, N * S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, h->d_flags, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int rs_get_info(rs_handle *h, int32_t env, double *acc, int32_t *n_prbs) {
+    if (!h || env < 0 || env >= h->p.N) return fail(RS_E_ARG, "bad handle/env");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    const int ne = h->p.n_embb, nm = h->p.n_mmtc;
+    if (acc) {
+        std::memset(acc, 0, sizeof(double) * 10 * (size_t)h->p.S);
+        if (ne) CU(cudaMemcpy(acc, h->embb.acc + (size_t)env * ne * 10, sizeof(double) * 10 * ne, cudaMemcpyDeviceToHost));
+        for (int m = 0; m < nm; ++m)
+            CU(cudaMemcpy(acc + (size_t)(ne + m) * 10, h->mmtc.acc + ((size_t)env * nm + m) * 3, sizeof(double) * 3,
+                          cudaMemcpyDeviceToHost));
+    }
+    if (n_prbs) {
+        if (ne) CU(cudaMemcpy(n_prbs, h->embb.cur_prbs + (size_t)env * ne, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost));
+        if (nm) CU(cudaMemcpy(n_prbs + ne, h->mmtc.cur_prbs + (size_t)env * nm, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost));
+    }
+    return RS_OK;
+}
+
+int rs_get_n_ues(rs_handle *h, int32_t *n_ues) {
+    if (!h || !n_ues) return fail(RS_E_ARG, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (h->embb.U) CU(cudaMemcpy(n_ues, h->embb.n_ues, sizeof(int32_t) * (size_t)h->embb.U, cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+int rs_state_size(rs_handle *h, size_t *bytes) {
+    if (!h || !bytes) return fail(RS_E_ARG, "null argument");
+    *bytes = h->arena_bytes;
+    return RS_OK;
+}
+int rs_get_state(rs_handle *h, void *blob, size_t bytes) {
+    if (!h || !blob || bytes != h->arena_bytes) return fail(RS_E_ARG, "bad blob size");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(blob, h->arena, bytes, cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+int rs_set_state(rs_handle *h, const void *blob, size_t bytes) {
+    if (!h || !blob || bytes != h->arena_bytes) return fail(RS_E_ARG, "bad blob size");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->arena, blob, bytes, cudaMemcpyHostToDevice));
+    h->was_reset = true;
+    return RS_OK;
+}
+
+int rs_get_counters(rs_handle *h, uint64_t *kernel_launches, uint64_t *trace_elems_last_step) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (trace_elems_last_step) {
+        CU(cudaDeviceSynchronize());
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, h->d_trace_elems, sizeof v, cudaMemcpyDeviceToHost));
+        *trace_elems_last_step = v;
+    }
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Parity of the CUDA step path (through the C ABI) against the pinned oracle and the golden fixtures.
+Bit-exact on every output: obs float32, reward, SLA labels, violations (BASELINE north_star bar)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+SCN = {0: (5, 200), 1: (5, 150), 2: (5, 100), 3: (2, 70)}
+VARIANTS = [0, 1]
+
+
+def simplex_actions(rng, N, S, n_prbs):
+    w = rng.random((N, S + 1))
+    return np.floor(n_prbs * w[:, :S] / w.sum(axis=1, keepdims=True)).astype(np.int32)
+
+
+def make_env(scn, N, seed, **kw):
+    from ranslice_b200 import create_batched_env
+    return create_batched_env(seed, scn, N, **kw)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name,scn", [("B_scn0", 0), ("B_scn1", 1), ("B_scn3", 3)])
+def test_golden_B_reference_fixture(golden, name, scn, variant):
+    """CUDA vs the unmodified reference (Philox-injected fixture)."""
+    g = golden(name)
+    E, T, S = g["actions"].shape
+    env = make_env(scn, E, int(g["base_seed"]), kernel_variant=variant)
+    assert np.array_equal(env.reset(), g["obs0"])
+    for t in range(T):
+        obs, rew, _, info = env.step(g["actions"][:, t])
+        assert not info["flags"].any()
+        assert np.array_equal(obs, g["obs"][:, t]), "obs diverged at step %d" % t
+        assert np.array_equal(rew.astype(np.float64), g["reward"][:, t])
+        assert np.array_equal(info["SLA_labels"], g["labels"][:, t])
+        assert np.array_equal(info["violations"], g["violations"][:, t])
+    acc, prbs = env.get_info(E - 1)
+    assert np.array_equal(acc, g["acc"][E - 1, T - 1])
+    env.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("scn,N,T", [(0, 192, 120), (3, 160, 150), (1, 96, 100), (2, 64, 100)])
+def test_vs_oracle_seeded(tables, scn, N, T, variant):
+    S, n_prbs = SCN[scn]
+    seed = 31337 + scn
+    env = make_env(scn, N, seed, kernel_variant=variant)
+    orc = ol.OracleBatch(tables, scn, N, seed, n_threads=8)
+    assert np.array_equal(env.reset(), orc.reset())
+    rng = np.random.default_rng(5)
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        if t % 7 == 3:
+            a[::5] = 0                      # starved slices (stale bits/prbs accumulation)
+        if t % 11 == 5:
+            a[1::9, 0] = n_prbs             # one slice takes everything
+            a[1::9, 1:] = 0
+        obs, rew, _, info = env.step(a)
+        o_obs, o_rew, o_lab, o_vio, o_fl = orc.step(a)
+        ok = (info["flags"] == 0) & (o_fl == 0)          # cap events differ by design (caps 16/8 vs 64/64)
+        assert ok.mean() > 0.95
+        assert np.array_equal(obs[ok], o_obs[ok]), "obs diverged at step %d" % t
+        assert np.array_equal(rew[ok].astype(np.float64), o_rew[ok])
+        assert np.array_equal(info["SLA_labels"][ok], o_lab[ok])
+        assert np.array_equal(info["violations"][ok], o_vio[ok])
+    env.close()
+
+
+def test_out_of_contract_actions_are_clamped_and_flagged(tables):
+    N, scn = 8, 0
+    env = make_env(scn, N, 99)
+    orc = ol.OracleBatch(tables, scn, N, 99)
+    env.reset(); orc.reset()
+    a = np.full((N, 5), 60, np.int32)       # sum 300 > 200
+    a[0] = [-3, 10, 10, 10, 10]
+    for _ in range(5):
+        obs, rew, _, info = env.step(a)
+        o_obs, o_rew, o_lab, o_vio, o_fl = orc.step(a)
+        assert (info["flags"] & 4).all() and (o_fl & 4).all()
+        assert np.array_equal(obs, o_obs) and np.array_equal(rew.astype(np.float64), o_rew)
+    with pytest.raises(ValueError):
+        env.step(np.zeros((N, 4), np.int32))
+    env.close()
+
+
+def test_sharding_invariance_and_checkpoint():
+    """Env results depend on the global env id, not on the device split; state blob round trip."""
+    scn, N, T = 0, 64, 40
+    S, n_prbs = SCN[scn]
+    whole = make_env(scn, N, 777)
+    lo = make_env(scn, N // 2, 777, first_env_id=0)
+    hi = make_env(scn, N // 2, 777, first_env_id=N // 2)
+    for e in (whole, lo, hi):
+        e.reset()
+    rng = np.random.default_rng(1)
+    blob = None
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        obs, rew, _, info = whole.step(a)
+        o1, r1, _, _ = lo.step(a[:N // 2])
+        o2, r2, _, _ = hi.step(a[N // 2:])
+        assert np.array_equal(obs, np.concatenate([o1, o2])) and np.array_equal(rew, np.concatenate([r1, r2]))
+        if t == T // 2:
+            blob = whole.get_state()
+            keep = []
+        if t > T // 2:
+            keep.append((a, obs, rew))
+    whole.set_state(blob)                    # rewind and replay: identical trajectories
+    for a, obs, rew in keep:
+        o, r, _, _ = whole.step(a)
+        assert np.array_equal(o, obs) and np.array_equal(r, rew)
+    for e in (whole, lo, hi):
+        e.close()
+
+
+def test_single_env_facade_matches_reference_surface(golden):
+    """create_env(rng, n) returns the RanSlice surface (ran_slice.py:15-57) and reproduces the fixture."""
+    from ranslice_b200 import create_env
+    g = golden("B_scn3")
+    env = create_env(int(g["base_seed"]), 3)
+    assert (env.n_prbs, env.n_slices, env.n_variables) == (70, 2, 13)
+    assert env.action_space.shape == (2,) and env.observation_space.shape == (13,)
+    obs = env.reset()
+    assert obs.dtype == np.float32 and not obs.any()
+    for t in range(40):
+        obs, reward, done, info = env.step(g["actions"][0, t])
+        assert isinstance(reward, float) and done is False
+        assert np.array_equal(obs, g["obs"][0, t]) and reward == g["reward"][0, t]
+        assert np.array_equal(info["SLA_labels"], g["labels"][0, t])
+        assert info["total_violations"] == g["violations"][0, t].sum()
+        assert set(info) >= {"l1_info", "SLA_labels", "violations", "n_prbs", "total_violations"}
+        assert info["l1_info"][0][0]["cbr_th"] == g["acc"][0, t, 0, 1]
+        assert info["l1_info"][1][0]["delay"] == g["acc"][0, t, 1, 2]
+
+
+def test_device_path_matches_host_path():
+    import torch
+    scn, N = 0, 128
+    S, n_prbs = SCN[scn]
+    a_env = make_env(scn, N, 4242)
+    b_env = make_env(scn, N, 4242)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(3)
+    for t in range(20):
+        a = simplex_actions(rng, N, S, n_prbs)
+        obs, rew, _, info = a_env.step(a)
+        out = b_env.step_device(torch.from_numpy(a).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(out["obs"].cpu().numpy(), obs) and np.array_equal(out["reward"].cpu().numpy(), rew)
+        assert np.array_equal(out["violations"].cpu().numpy(), info["violations"])
+    k, tr = b_env.counters()
+    assert k >= 40 and tr > 0
+
+
+def test_population_statistics_large_batch():
+    """Size-independent properties at scale (4096 envs): reward identity, label/violation consistency,
+    obs finite, UE population in the survey's range (mean ~3.5 UEs per slice)."""
+    scn, N, T = 0, 4096, 80
+    S, n_prbs = SCN[scn]
+    env = make_env(scn, N, 2024)
+    env.reset()
+    rng = np.random.default_rng(8)
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        obs, rew, _, info = env.step(a)
+        v = info["violations"]
+        assert np.isfinite(obs).all()
+        assert np.array_equal(info["SLA_labels"], 1 - 2 * v)
+        tv = v.sum(axis=1)
+        want = np.where(tv > 0, -100.0 * tv, np.maximum(0, n_prbs - a.sum(axis=1)))
+        assert np.array_equal(rew, want.astype(np.float32))
+    nu = env.n_ues()
+    assert 1.0 < nu.mean() < 6.0 and nu.max() <= 16
+    env.close()
