@@ -100,6 +100,20 @@ int rs_set_state(rs_handle *h, const void *blob, size_t bytes);
  * the last step summed over envs (B_trace of SURVEY 8d, 0 if the variant does not count) */
 int rs_get_counters(rs_handle *h, uint64_t *kernel_launches, uint64_t *trace_elems_last_step);
 
+/* profiling: when enabled, rs_step_device brackets each of its kernels with CUDA events recorded on
+ * the launching stream; rs_get_profile synchronises and returns the summed durations (ms) and the
+ * number of profiled steps since the last call (bench.py's roofline.achieved denominator). */
+int rs_set_profiling(rs_handle *h, int32_t enable);
+int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *reward_ms, uint64_t *steps);
+
+/* guard-band validation (tests): with debug_check on, the default eMBB kernel evaluates the exact fp64
+ * expression next to every fast-path decision.  rs_get_diag: out[0] max |p64 - p32| / eps over
+ * reception decisions, out[1] max |mean64 - mean_fast| / 1e-6 over SNR estimates, out[2] decisions
+ * that would have differed (must be 0), out[3] / out[4] fp64 re-evaluations taken in the last step
+ * (SNR rounding guard / reception guard). */
+int rs_set_debug_check(rs_handle *h, int32_t enable);
+int rs_get_diag(rs_handle *h, double *out, int32_t n);
+
 int rs_n_variables(const rs_handle *h);
 const char *rs_last_error(void);
 

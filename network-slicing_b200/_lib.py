@@ -12,13 +12,6 @@ SO_PATH = os.path.join(_PKG, "libranslice_b200.so")
 RS_ABI_VERSION = 1
 FLAG_UE_CAP, FLAG_BURST_CAP, FLAG_ACTION_CLAMP, FLAG_SAME_SLOT_DEP, FLAG_MTC_QUEUE_CAP = 1, 2, 4, 8, 16
 
-# every symbol include/ranslice_b200.h declares
-EXPORTS = ["rs_create", "rs_destroy", "rs_reset", "rs_step", "rs_step_device", "rs_get_info", "rs_get_n_ues",
-           "rs_state_size", "rs_get_state", "rs_set_state", "rs_get_counters", "rs_n_variables", "rs_last_error",
-           "kb_create", "kb_destroy", "kb_reset", "kb_predict", "kb_update", "kb_control_step", "kb_get_sizes",
-           "kb_get_learner", "kb_get_counters"]
-
-
 class RsConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_envs", C.c_int32),
                 ("n_prbs", C.c_int32), ("n_embb", C.c_int32), ("n_mmtc", C.c_int32),
@@ -62,9 +55,15 @@ def lib():
     L.rs_set_state.argtypes = [vp, vp, C.c_size_t]
     L.rs_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rs_n_variables.argtypes = [vp]
+    L.rs_set_debug_check.argtypes = [vp, i32]
+    L.rs_get_diag.argtypes = [vp, C.POINTER(C.c_double), i32]
+    L.rs_set_profiling.argtypes = [vp, i32]
+    L.rs_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                 C.POINTER(C.c_uint64)]
     L.rs_last_error.restype = C.c_char_p
     for name in ("rs_create", "rs_destroy", "rs_reset", "rs_step", "rs_step_device", "rs_get_info", "rs_get_n_ues",
-                 "rs_state_size", "rs_get_state", "rs_set_state", "rs_get_counters", "rs_n_variables"):
+                 "rs_state_size", "rs_get_state", "rs_set_state", "rs_get_counters", "rs_n_variables",
+                 "rs_set_profiling", "rs_get_profile", "rs_set_debug_check", "rs_get_diag"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -137,6 +137,40 @@ class BatchedRanSlice:
         _lib.check(_lib.lib().rs_get_counters(self._h, C.byref(k), C.byref(t)))
         return int(k.value), int(t.value)
 
+    def state_bytes(self):
+        n = C.c_size_t()
+        _lib.check(_lib.lib().rs_state_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    VARIANT_NAMES = {0: "embb_step_fast (PRB-sorted units, guarded fast math)", 1: "embb_step_unit_thread (all fp64)"}
+
+    def kernel_variant_name(self):
+        return self.VARIANT_NAMES.get(self._cfg.kernel_variant, str(self._cfg.kernel_variant))
+
+    def profile_steps(self, actions, out=None):
+        """Runs step_device over ``actions`` with per-kernel CUDA events (inside the library, on the
+        launching stream); returns average per-launch durations in ms."""
+        L = _lib.lib()
+        _lib.check(L.rs_set_profiling(self._h, 1))
+        for a in actions:
+            out = self.step_device(a, out)
+        e, m, r, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
+        _lib.check(L.rs_get_profile(self._h, C.byref(e), C.byref(m), C.byref(r), C.byref(n)))
+        _lib.check(L.rs_set_profiling(self._h, 0))
+        k = max(int(n.value), 1)
+        return {"embb_ms": e.value / k, "mmtc_ms": m.value / k, "reward_ms": r.value / k, "steps": int(n.value),
+                "kernel": self.kernel_variant_name()}
+
+    def set_debug_check(self, on=True):
+        _lib.check(_lib.lib().rs_set_debug_check(self._h, int(bool(on))))
+
+    def diag(self):
+        """Guard-band diagnostics of the default kernel (see rs_get_diag in include/ranslice_b200.h)."""
+        out = (C.c_double * 5)()
+        _lib.check(_lib.lib().rs_get_diag(self._h, out, 5))
+        return {"max_p_err_over_eps": out[0], "max_mean_err_over_guard": out[1], "decision_mismatches": int(out[2]),
+                "slow_snr_last_step": int(out[3]), "slow_rx_last_step": int(out[4])}
+
     def get_state(self):
         n = C.c_size_t()
         _lib.check(_lib.lib().rs_state_size(self._h, C.byref(n)))

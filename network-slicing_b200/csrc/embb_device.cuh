@@ -30,6 +30,9 @@ __device__ __forceinline__ void slice_window(const StepParams &p, int env, int s
     i_prb = off; n_prbs = mine;
 }
 
+// window of a unit precomputed by window_kernel (embb_fast.cu)
+__device__ __forceinline__ void unpack_window(uint32_t w, int &i_prb, int &n_prbs) { i_prb = (int)(w & 0xFFFFu); n_prbs = (int)(w >> 16); }
+
 __device__ __forceinline__ int exp_slots_ms(PhiloxStream &r, double scale) {   // np.rint(exp / slot_length)
     return __double2int_rn(r.exponential(scale) / SLOT_LEN);
 }
@@ -48,7 +51,7 @@ __device__ __forceinline__ bool in_cell(double x, double y) {
            (y < find_y(0, 0.5, 0.25, 1, x)) && (y < find_y(0.75, 1, 1, .5, x));
 }
 // macro_cell (channel_models.py:80-97) with location (:62-68) and antenna_pattern (:76-78)
-__device__ __noinline__ double draw_nominal_sinr(PhiloxStream &r, double A, double B) {
+static __device__ __noinline__ double draw_nominal_sinr(PhiloxStream &r, double A, double B) {
     double x, y;
     do { x = r.u01(); y = r.u01(); } while (!in_cell(x, y));
     const double logf = r.normal(0.0, 10.0);
@@ -77,44 +80,47 @@ __device__ __forceinline__ void walk_trace(PhiloxStream &r, int &index, int &ste
     }
 }
 
-// VbrSource.step (traffic_generators.py:70-99); returns the bits generated this slot
-template <int MB>
-__device__ __forceinline__ int vbr_source_step(const EmbbState &st, int u, int k, PhiloxStream &r_vbr,
-                                               uint32_t &flags) {
-    const int U = st.U, MBc = st.MB;
-    int nb = st.nb[k * U + u], w = 0, bits = 0;
-    for (int j = 0; j < nb; ++j) {
-        const int tg = st.togo[(k * MBc + j) * U + u] - 1;
-        if (tg == 0) continue;                   // burst ends: contributes nothing this slot
-        bits += 1000;
-        st.togo[(k * MBc + w) * U + u] = tg;
-        ++w;
+// VbrSource.step (traffic_generators.py:70-99) on a UE record held in registers; returns this slot's bits.
+// The order of the burst list never matters (bits = 1000 per non-ending burst; draws only on arrival), so
+// slots are not compacted: togo[j] == 0 marks a free slot, and a length drawn as 0 (a burst that never
+// ends) is stored as -1, which behaves identically (never hits 0; saturates at -32768).
+__device__ __forceinline__ int vbr_source_step(UeRec &r, PhiloxStream &r_vbr, uint32_t &flags) {
+    int bits = 0, nb = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_BURSTS; ++j) {
+        int tg = r.togo[j];
+        if (tg != 0) {
+            tg = max(tg - 1, -32768);
+            if (tg != 0) { bits += 1000; ++nb; }              // == 0: burst ends, contributes nothing this slot
+            r.togo[j] = (int16_t)tg;
+        }
     }
-    nb = w;
-    int vn = st.vnext[k * U + u] - 1;
+    int vn = r.vnext - 1;
     if (vn == 0) {
-        const int len = exp_slots(r_vbr, 500.0);
-        if (nb < MBc) st.togo[(k * MBc + nb++) * U + u] = len; else flags |= 2u;
+        int len = exp_slots(r_vbr, 500.0);
+        if (len == 0) len = -1;
+        bool placed = false;
+#pragma unroll
+        for (int j = 0; j < MAX_BURSTS; ++j)
+            if (!placed && r.togo[j] == 0) { r.togo[j] = (int16_t)len; placed = true; }
+        if (placed) ++nb; else flags |= 2u;
         vn = exp_slots(r_vbr, 1000.0);
     }
-    st.vnext[k * U + u] = vn;
-    st.nb[k * U + u] = nb;
+    r.vnext = vn;
+    r.nb = nb;
     return bits;
 }
 
-template <int MB>
-__device__ __forceinline__ void move_ue(const EmbbState &st, int u, int from, int to) {
-    const int U = st.U, MBc = st.MB;
-    st.meta[to * U + u] = st.meta[from * U + u];
-    st.nominal[to * U + u] = st.nominal[from * U + u];
-    st.queue[to * U + u] = st.queue[from * U + u];
-    st.th[to * U + u] = st.th[from * U + u];
-    st.bits[to * U + u] = st.bits[from * U + u];
-    st.pe[to * U + u] = st.pe[from * U + u];
-    st.vnext[to * U + u] = st.vnext[from * U + u];
-    const int nb = st.nb[from * U + u];
-    st.nb[to * U + u] = nb;
-    for (int j = 0; j < nb; ++j) st.togo[(to * MBc + j) * U + u] = st.togo[(from * MBc + j) * U + u];
+// 128-bit moves of a UE record between HBM and registers
+__device__ __forceinline__ void load_rec(const UeRec *g, UeRec &r) {
+    const int4 *s = reinterpret_cast<const int4 *>(g);
+    int4 *d = reinterpret_cast<int4 *>(&r);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+__device__ __forceinline__ void store_rec(UeRec *g, const UeRec &r) {
+    const int4 *s = reinterpret_cast<const int4 *>(&r);
+    int4 *d = reinterpret_cast<int4 *>(g);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 
 __device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }

@@ -1,7 +1,8 @@
-// K1 (variant 1, "unit-per-thread"): one thread advances one (env, eMBB slice) unit through the
-// whole observation period (slots_per_step TTIs) in a single launch.  All decision arithmetic is
-// fp64 in the reference's operation order (compiled with --fmad=false); this variant is the
-// in-product correctness anchor for the faster variants.
+// K1 variant 1 ("unit-per-thread, all fp64"): one thread advances one (env, eMBB slice) unit through
+// the whole observation period (slots_per_step TTIs) in a single launch, units in natural order.
+// Every decision is evaluated in fp64 in the reference's operation order (compiled with
+// --fmad=false).  This is the in-product correctness anchor: the default variant (embb_fast.cu)
+// must produce identical results.
 //
 // Reference path restated here (file:line in the reference tree):
 //   SliceL1eMBB.slot                slice_l1.py:193-228
@@ -15,13 +16,12 @@
 
 namespace rs {
 
-template <int K, int MB>
+template <int K>
 __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_constant__ StepParams p,
                                                              const __grid_constant__ EmbbState st,
                                                              const __grid_constant__ Tables tb) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int U = st.U;
-    if (u >= U) return;
+    if (u >= st.U) return;
     const int env = u / p.n_embb, s = u - env * p.n_embb;
 
     // ---- NodeB.step prologue: PRB window of this slice (node_b.py:71-74), clamped
@@ -30,14 +30,15 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
     slice_window(p, env, s, i_prb, n_prbs, flags);
     st.cur_prbs[u] = n_prbs;
 
+    UnitHdr hdr = st.hdr[u];
+    UeRec *ue = st.ue + (size_t)u * st.K;
     const uint64_t seed = p.seed0 + (uint64_t)env;
-    PhiloxStream r_ran{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_RAN, st.ctr[0 * U + u]};
-    PhiloxStream r_chan{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_CHAN, st.ctr[1 * U + u]};
-    PhiloxStream r_rx{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_L1RX, st.ctr[2 * U + u]};
-    PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, st.ctr[3 * U + u]};
+    PhiloxStream r_ran{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_RAN, hdr.ctr[0]};
+    PhiloxStream r_chan{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_CHAN, hdr.ctr[1]};
+    PhiloxStream r_rx{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_L1RX, hdr.ctr[2]};
+    PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
 
-    int n_ues = st.n_ues[u];
-    int cbr_next = st.cbr_next[u], vbr_next = st.vbr_next[u];
+    int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
     int a_traffic[2] = {0, 0}, a_th[2] = {0, 0}, a_prb[2] = {0, 0};     // slice_ran.py:270-273 reset_info
     double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
     unsigned long long trace_elems = 0;
@@ -64,10 +65,10 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
         {
             int w = 0;
             for (int k = 0; k < n_ues; ++k) {
-                const int rem = st.rem[k * U + u] - 1;
+                const int rem = ue[k].rem - 1;
                 if (rem != 0) {
-                    if (w != k) move_ue<MB>(st, u, k, w);
-                    st.rem[w * U + u] = rem;
+                    if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
+                    ue[w].rem = rem;
                     ++w;
                 }
             }
@@ -78,50 +79,47 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
             const int rem = arr_rem[a] - 1;                      // this slot's departures() already ticked it
             if (rem == 0) { flags |= 8u; continue; }
             if (n_ues >= st.K) { flags |= 1u; continue; }
+            UeRec r;
             const int fading = (int)r_chan.integers(3);
             const int index = (int)r_chan.integers(N_SAMPLES);
             const int step = r_chan.integers(2) ? 1 : -1;
-            const double nominal = draw_nominal_sinr(r_chan, p.prop_A, p.prop_B);
-            const int k = n_ues++;
-            st.meta[k * U + u] = pack_meta(arr_type[a], fading, step, index);
-            st.rem[k * U + u] = rem;
-            st.nominal[k * U + u] = nominal;
-            st.queue[k * U + u] = 0;
-            st.th[k * U + u] = 0.0;
-            st.bits[k * U + u] = 0;
-            st.pe[k * U + u] = 0;
-            st.vnext[k * U + u] = arr_vnext[a];
-            st.nb[k * U + u] = 0;
+            r.nominal = draw_nominal_sinr(r_chan, p.prop_A, p.prop_B);
+            r.meta = pack_meta(arr_type[a], fading, step, index);
+            r.rem = rem; r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
+#pragma unroll
+            for (int j = 0; j < MAX_BURSTS; ++j) r.togo[j] = 0;
+            store_rec(ue + n_ues, r);
+            ++n_ues;
         }
         // ================= per-UE traffic + SNR estimate (slice_l1.py:200-213)
         long long queued = 0;
         int new_bits[K];
         for (int k = 0; k < n_ues; ++k) {
-            uint32_t meta = st.meta[k * U + u];
+            UeRec r;
+            load_rec(ue + k, r);
             int nb_bits;
-            if ((meta & 1u) == 0) nb_bits = 500;                 // CbrSource: 500000 b/s * 1e-3 every slot
-            else nb_bits = vbr_source_step<MB>(st, u, k, r_vbr, flags);
+            if ((r.meta & 1u) == 0) nb_bits = 500;               // CbrSource: 500000 b/s * 1e-3 every slot
+            else nb_bits = vbr_source_step(r, r_vbr, flags);
             new_bits[k] = nb_bits;
-            const long long q = st.queue[k * U + u] + nb_bits;
-            st.queue[k * U + u] = q;
-            queued += q;
+            r.queue += nb_bits;
+            queued += r.queue;
             if (n_prbs > 0) {
-                int index = (int)(meta >> 4), step = (meta & 8u) ? 1 : -1;
-                const int fading = (int)((meta >> 1) & 3u);
+                int index = (int)(r.meta >> 4), step = (r.meta & 8u) ? 1 : -1;
+                const int fading = (int)((r.meta >> 1) & 3u);
                 walk_trace(r_chan, index, step);                 // channel_models.py:171-191
-                st.meta[k * U + u] = pack_meta((int)(meta & 1u), fading, step, index);
+                r.meta = pack_meta((int)(r.meta & 1u), fading, step, index);
                 const double *col = tb.trace + ((size_t)fading * N_SAMPLES + index) * TRACE_ROWS;
-                const double nominal = st.nominal[k * U + u];
                 double sum = 0.0;
                 int row = i_prb % TRACE_ROWS;
                 for (int j = 0; j < n_prbs; ++j) {
-                    sum += col[row] + nominal;
+                    sum += col[row] + r.nominal;
                     row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
                 }
                 trace_elems += (unsigned)n_prbs;
                 const int e_snr = __double2int_rn(sum / (double)n_prbs);         // round(np.mean(snr)), slice_ran.py:43-45
-                st.pe[k * U + u] = (st.pe[k * U + u] & 0xFFFF) | (e_snr << 16);
+                r.pe = (r.pe & 0xFFFF) | (e_snr << 16);
             }
+            store_rec(ue + k, r);
         }
         // ================= scheduling + reception (slice_l1.py:215-224)
         if (queued > 0 && n_prbs > 0) {
@@ -129,11 +127,10 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
             long long bits[K], qq[K];
             double th[K];
             for (int k = 0; k < n_ues; ++k) {                    // schedulers.py:37-45
-                const double uth = st.th[k * U + u];
+                const double uth = ue[k].th;
                 th[k] = uth > 1.0 ? uth : 1.0;
-                qq[k] = st.queue[k * U + u];
-                const int e_snr = st.pe[k * U + u] >> 16;
-                const int e = min(max(e_snr, -128), 127) + 128;
+                qq[k] = ue[k].queue;
+                const int e = min(max(ue[k].pe >> 16, -128), 127) + 128;
                 mcs[k] = tb.lut_mcs[e];
                 rate[k] = tb.lut_rate[e];
                 rbs[k] = 0; bits[k] = 0;
@@ -158,19 +155,19 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
                 const int prbs = rbs[k];
                 long long b = bits[k];
                 if (prbs) {
-                    const uint32_t meta = st.meta[k * U + u];
+                    const uint32_t meta = ue[k].meta;
                     const double *col = tb.trace + ((size_t)((meta >> 1) & 3u) * N_SAMPLES + (meta >> 4)) * TRACE_ROWS;
-                    const double pr = response_fp64(tb, mcs[k], col, (i_prb + o) % TRACE_ROWS, prbs, st.nominal[k * U + u]);
+                    const double pr = response_fp64(tb, mcs[k], col, (i_prb + o) % TRACE_ROWS, prbs, ue[k].nominal);
                     trace_elems += (unsigned)prbs;
                     const bool received = r_rx.u01() < pr;
                     if (!received) b = 0;
                 } else b = 0;
                 o += prbs;
-                const long long q = st.queue[k * U + u] - b;     // UE.transmission_step, slice_ran.py:51-55
-                st.queue[k * U + u] = q > 0 ? q : 0;
-                st.th[k * U + u] = PF_A * st.th[k * U + u] + PF_B * (double)b / SLOT_LEN;
-                st.bits[k * U + u] = (int)b;
-                st.pe[k * U + u] = (st.pe[k * U + u] & 0xFFFF0000) | prbs;
+                const long long q = ue[k].queue - b;             // UE.transmission_step, slice_ran.py:51-55
+                ue[k].queue = q > 0 ? q : 0;
+                ue[k].th = PF_A * ue[k].th + PF_B * (double)b / SLOT_LEN;
+                ue[k].bits = (int)b;
+                ue[k].pe = (ue[k].pe & 0xFFFF0000) | prbs;
             }
         }
         // ================= update_info (slice_ran.py:278-305)
@@ -178,12 +175,12 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
             long long q[2] = {0, 0};
             int sn[2] = {0, 0}, n[2] = {0, 0};
             for (int k = 0; k < n_ues; ++k) {
-                const int ty = (int)(st.meta[k * U + u] & 1u);
-                const int pe = st.pe[k * U + u];
+                const int ty = (int)(ue[k].meta & 1u);
+                const int pe = ue[k].pe;
                 a_traffic[ty] += new_bits[k];
-                a_th[ty] += st.bits[k * U + u];
+                a_th[ty] += ue[k].bits;
                 a_prb[ty] += pe & 0xFFFF;
-                q[ty] += st.queue[k * U + u];
+                q[ty] += ue[k].queue;
                 sn[ty] += pe >> 16;
                 n[ty] += 1;
             }
@@ -196,8 +193,9 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
     }
 
     // ---- persist slice scalars
-    st.n_ues[u] = n_ues; st.cbr_next[u] = cbr_next; st.vbr_next[u] = vbr_next;
-    st.ctr[0 * U + u] = r_ran.n; st.ctr[1 * U + u] = r_chan.n; st.ctr[2 * U + u] = r_rx.n; st.ctr[3 * U + u] = r_vbr.n;
+    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next;
+    hdr.ctr[0] = r_ran.n; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
+    st.hdr[u] = hdr;
 
     // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
     const double acc[10] = {(double)a_traffic[0], (double)a_th[0], (double)a_prb[0], a_queue[0], a_snr[0],
@@ -208,16 +206,9 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
 
 void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
     const int threads = 128, blocks = (st.U + threads - 1) / threads;
-    // template K only sizes the per-thread scratch arrays; the caps themselves are st.K / st.MB (<= 32 / 16)
-    if (st.K <= 16) embb_step_unit_thread<16, 8><<<blocks, threads, 0, stream>>>(p, st, tb);
-    else embb_step_unit_thread<32, 16><<<blocks, threads, 0, stream>>>(p, st, tb);
+    // template K only sizes the per-thread scratch arrays; the cap itself is st.K (<= 32)
+    if (st.K <= 16) embb_step_unit_thread<16><<<blocks, threads, 0, stream>>>(p, st, tb);
+    else embb_step_unit_thread<32><<<blocks, threads, 0, stream>>>(p, st, tb);
 }
 
-}  // namespace rs
-
-namespace rs {
-// placeholder until the cooperative variant lands
-void launch_embb_coop(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, int) {
-    launch_embb_unit_thread(p, st, tb, stream);
-}
 }  // namespace rs

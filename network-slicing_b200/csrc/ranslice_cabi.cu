@@ -13,7 +13,8 @@
 
 namespace rs {
 void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
-void launch_embb_coop(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, int sm_count);
+int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 void launch_reward(const StepParams &p, cudaStream_t stream);
@@ -40,7 +41,9 @@ struct rs_handle {
     size_t arena_bytes;
     // tables + I/O staging
     double *d_trace;
-    float *d_trace32;
+    int32_t *d_trace_q24;
+    char *scratch;
+    unsigned long long *d_slow_paths;
     int32_t *d_action;
     float *d_obs, *d_reward;
     int32_t *d_labels, *d_violations;
@@ -49,6 +52,8 @@ struct rs_handle {
     cudaStream_t stream;
     uint64_t launches;
     bool was_reset;
+    bool profiling;
+    std::vector<cudaEvent_t> *prof_events;   // 4 per profiled step
 };
 
 namespace {
@@ -67,21 +72,9 @@ struct Carver {
 
 void carve(rs_handle *h, Carver &c) {
     rs::EmbbState &e = h->embb;
-    const size_t U = (size_t)e.U, K = (size_t)e.K, MB = (size_t)e.MB;
-    e.n_ues = c.take<int32_t>(U);
-    e.cbr_next = c.take<int32_t>(U);
-    e.vbr_next = c.take<int32_t>(U);
-    e.ctr = c.take<uint32_t>(4 * U);
-    e.meta = c.take<uint32_t>(K * U);
-    e.rem = c.take<int32_t>(K * U);
-    e.nominal = c.take<double>(K * U);
-    e.queue = c.take<long long>(K * U);
-    e.th = c.take<double>(K * U);
-    e.bits = c.take<int32_t>(K * U);
-    e.pe = c.take<int32_t>(K * U);
-    e.vnext = c.take<int32_t>(K * U);
-    e.nb = c.take<int32_t>(K * U);
-    e.togo = c.take<int32_t>(K * MB * U);
+    const size_t U = (size_t)e.U, K = (size_t)e.K;
+    e.hdr = c.take<rs::UnitHdr>(U);
+    e.ue = c.take<rs::UeRec>(U * K);
     e.acc = c.take<double>(U * 10);
     e.cur_prbs = c.take<int32_t>(U);
     rs::MmtcState &m = h->mmtc;
@@ -182,14 +175,29 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     const size_t n_trace = (size_t)3 * rs::N_SAMPLES * rs::TRACE_ROWS;
     CU(cudaMalloc(&h->d_trace, n_trace * sizeof(double)));
     CU(cudaMemcpy(h->d_trace, tables->trace, n_trace * sizeof(double), cudaMemcpyHostToDevice));
-    {
-        std::vector<float> t32(n_trace);
-        for (size_t i = 0; i < n_trace; ++i) t32[i] = (float)tables->trace[i];
-        CU(cudaMalloc(&h->d_trace32, n_trace * sizeof(float)));
-        CU(cudaMemcpy(h->d_trace32, t32.data(), n_trace * sizeof(float), cudaMemcpyHostToDevice));
+    {   // 2^-24 fixed-point copy (|v| < 128 dB): exact integer window sums on the fast path
+        std::vector<int32_t> q24(n_trace);
+        for (size_t i = 0; i < n_trace; ++i) {
+            const double v = tables->trace[i];
+            if (std::isnan(v)) { q24[i] = 0; continue; }
+            if (std::fabs(v) >= 127.0) { delete h; return fail(RS_E_ARG, "fading trace value out of the +-127 dB fixed-point range"); }
+            q24[i] = (int32_t)std::llrint(v * 16777216.0);
+        }
+        CU(cudaMalloc(&h->d_trace_q24, n_trace * sizeof(int32_t)));
+        CU(cudaMemcpy(h->d_trace_q24, q24.data(), n_trace * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     build_tables(tables, h->tb);
-    h->tb.trace = h->d_trace; h->tb.trace32 = h->d_trace32;
+    h->tb.trace = h->d_trace; h->tb.trace_q24 = h->d_trace_q24;
+    {   // per-step scheduling scratch (outside the checkpoint arena)
+        Carver sc;
+        const size_t U = (size_t)h->embb.U;
+        sc.take<uint32_t>(U); sc.take<int32_t>(U); sc.take<uint32_t>(512); sc.take<float>(8);
+        CU(cudaMalloc(&h->scratch, sc.off + 256));
+        CU(cudaMemset(h->scratch, 0, sc.off + 256));
+        Carver rc; rc.base = h->scratch;
+        h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(U);
+        h->embb.hist = rc.take<uint32_t>(512); h->embb.dbg = rc.take<float>(8);
+    }
 
     const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;
     CU(cudaMalloc(&h->d_action, N * S * sizeof(int32_t)));
@@ -200,11 +208,14 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     CU(cudaMalloc(&h->d_flags, N * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_flags_acc, N * sizeof(uint32_t)));
     CU(cudaMemset(h->d_flags_acc, 0, N * sizeof(uint32_t)));
-    CU(cudaMalloc(&h->d_trace_elems, sizeof(unsigned long long)));
-    CU(cudaMemset(h->d_trace_elems, 0, sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_trace_elems, 4 * sizeof(unsigned long long)));
+    CU(cudaMemset(h->d_trace_elems, 0, 4 * sizeof(unsigned long long)));
+    h->d_slow_paths = h->d_trace_elems + 1;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     p.flags_acc = h->d_flags_acc;
     p.trace_elems = h->d_trace_elems;
+    p.slow_paths = h->d_slow_paths;
+    p.debug_check = 0;
     *out = h;
     return RS_OK;
 }
@@ -213,10 +224,11 @@ int rs_destroy(rs_handle *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace32); cudaFree(h->d_action); cudaFree(h->d_obs);
+    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_q24); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
     cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
     cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->prof_events) { for (auto e : *h->prof_events) cudaEventDestroy(e); delete h->prof_events; }
     delete h;
     return RS_OK;
 }
@@ -226,14 +238,7 @@ int rs_reset(rs_handle *h, float *obs) {
     CU(cudaSetDevice(h->cfg.device));
     // NodeB.reset (node_b.py:17-22): UEs, timers and accumulators cleared; RNG counters keep running
     // (the reference never reseeds on reset).  eMBB: zero everything but the counters.
-    rs::EmbbState &e = h->embb;
-    const size_t U = (size_t)e.U;
-    if (U) {
-        CU(cudaMemsetAsync(e.n_ues, 0, U * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(e.cbr_next, 0, U * sizeof(int32_t), h->stream));   // slice_ran.py:185-186
-        CU(cudaMemsetAsync(e.vbr_next, 0, U * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(e.acc, 0, U * 10 * sizeof(double), h->stream));
-    }
+    if (h->embb.U) { rs::launch_embb_reset(h->embb, h->stream); h->launches += 1; }
     if (h->mmtc.U) {
         rs::launch_mmtc_reset(h->p, h->mmtc, h->stream);
         h->launches += 1;
@@ -258,15 +263,25 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     p.labels = d_labels ? d_labels : h->d_labels;
     p.violations = d_violations ? d_violations : h->d_violations;
     p.flags = d_flags ? d_flags : h->d_flags;
-    CU(cudaMemsetAsync(h->d_trace_elems, 0, sizeof(unsigned long long), st));
-    if (h->embb.U) {
-        if (h->cfg.kernel_variant == 1) rs::launch_embb_unit_thread(p, h->embb, h->tb, st);
-        else rs::launch_embb_coop(p, h->embb, h->tb, st, h->sm_count);
-        h->launches += 1;
+    CU(cudaMemsetAsync(h->d_trace_elems, 0, 3 * sizeof(unsigned long long), st));
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (h->profiling) {
+        for (auto &e : ev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(ev[0], st));
     }
+    if (h->embb.U) {
+        if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
+        else h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
+    }
+    if (h->profiling) CU(cudaEventRecord(ev[1], st));
     if (h->mmtc.U) { rs::launch_mmtc_step(p, h->mmtc, st); h->launches += 1; }
+    if (h->profiling) CU(cudaEventRecord(ev[2], st));
     rs::launch_reward(p, st);
     h->launches += 1;
+    if (h->profiling) {
+        CU(cudaEventRecord(ev[3], st));
+        for (auto &e : ev) h->prof_events->push_back(e);
+    }
     CU(cudaGetLastError());
     return RS_OK;
 }
@@ -311,7 +326,11 @@ int rs_get_n_ues(rs_handle *h, int32_t *n_ues) {
     if (!h || !n_ues) return fail(RS_E_ARG, "null argument");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    if (h->embb.U) CU(cudaMemcpy(n_ues, h->embb.n_ues, sizeof(int32_t) * (size_t)h->embb.U, cudaMemcpyDeviceToHost));
+    if (h->embb.U) {
+        std::vector<rs::UnitHdr> hd((size_t)h->embb.U);
+        CU(cudaMemcpy(hd.data(), h->embb.hdr, sizeof(rs::UnitHdr) * hd.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < hd.size(); ++i) n_ues[i] = hd[i].n_ues;
+    }
     return RS_OK;
 }
 
@@ -333,6 +352,59 @@ int rs_set_state(rs_handle *h, const void *blob, size_t bytes) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h->arena, blob, bytes, cudaMemcpyHostToDevice));
     h->was_reset = true;
+    return RS_OK;
+}
+
+int rs_set_debug_check(rs_handle *h, int32_t enable) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    h->p.debug_check = enable != 0;
+    return RS_OK;
+}
+
+int rs_get_diag(rs_handle *h, double *out, int32_t n) {
+    if (!h || !out || n < 5) return fail(RS_E_ARG, "need room for 5 doubles");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    float dbg[8];
+    unsigned long long ctr[4];
+    CU(cudaMemcpy(dbg, h->embb.dbg, sizeof dbg, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ctr, h->d_trace_elems, sizeof ctr, cudaMemcpyDeviceToHost));
+    unsigned mism;
+    std::memcpy(&mism, &dbg[2], sizeof mism);
+    out[0] = dbg[0]; out[1] = dbg[1]; out[2] = (double)mism; out[3] = (double)ctr[1]; out[4] = (double)ctr[2];
+    return RS_OK;
+}
+
+int rs_set_profiling(rs_handle *h, int32_t enable) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    if (!h->prof_events) h->prof_events = new std::vector<cudaEvent_t>();
+    h->profiling = enable != 0;
+    return RS_OK;
+}
+
+int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *reward_ms, uint64_t *steps) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    double s[3] = {0, 0, 0};
+    uint64_t n = 0;
+    if (h->prof_events) {
+        std::vector<cudaEvent_t> &v = *h->prof_events;
+        for (size_t i = 0; i + 3 < v.size(); i += 4) {
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, v[i + j], v[i + j + 1]));
+                s[j] += ms;
+            }
+            ++n;
+        }
+        for (auto e : v) cudaEventDestroy(e);
+        v.clear();
+    }
+    if (embb_ms) *embb_ms = s[0];
+    if (mmtc_ms) *mmtc_ms = s[1];
+    if (reward_ms) *reward_ms = s[2];
+    if (steps) *steps = n;
     return RS_OK;
 }
 

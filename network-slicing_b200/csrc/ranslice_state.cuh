@@ -1,9 +1,7 @@
 // Internal device-state layout of libranslice_b200 (not part of the C ABI).
 //
 // A "unit" is one (env, eMBB slice) pair: u = env * n_embb + s.  SURVEY hard-part 1 shows units
-// are independent given their PRB window, so they are the grain of parallelism.  All per-UE
-// fields are SoA, UE-slot-major: field[k * U + u], so that neighbouring units (neighbouring
-// lanes) touch neighbouring addresses (coalesced 128 B per warp per field).
+// are independent given their PRB window, so they are the grain of parallelism (one thread each).
 #pragma once
 #include <cstdint>
 
@@ -19,24 +17,44 @@ __host__ __device__ inline uint32_t pack_meta(int type, int fading, int step, in
     return (uint32_t)type | ((uint32_t)fading << 1) | ((step > 0 ? 1u : 0u) << 3) | ((uint32_t)index << 4);
 }
 
+// One live UE = one 64-byte record (4 x 16 B quads, so a thread moves it with 128-bit loads/stores).
+// Units are processed in PRB-sorted order (see embb_fast.cu), i.e. gathered, so the record is AoS:
+// everything a UE needs in one TTI sits in two 32 B sectors.
+constexpr int MAX_BURSTS = 8;      // VbrSource active bursts kept per UE (P(>8) ~ 1e-9 per UE-sample, flagged)
+struct __align__(16) UeRec {
+    uint32_t meta;         // type / fading / step / trace index (pack_meta)
+    int32_t rem;           // remaining holding time, slots   (slice_ran.py:222)
+    int32_t vnext;         // VbrSource.steps_to_next_arrival (traffic_generators.py:66)
+    int32_t bits;          // ue.bits of the last scheduled TTI (stale when unscheduled)
+    double nominal;        // nominal SINR dB                 (channel_models.py:167)
+    double th;             // ue.th EWMA throughput           (slice_ran.py:55)
+    long long queue;       // ue.queue, bits
+    int32_t pe;            // ue.prbs (low 16) | ue.e_snr (high 16, signed)
+    int32_t nb;            // active bursts
+    int16_t togo[MAX_BURSTS]; // VbrSource.steps_to_go; draws are <= 18369 (53-bit uniform), saturating at -32768
+};
+static_assert(sizeof(UeRec) == 64, "UeRec must be 64 bytes");
+
+struct __align__(16) UnitHdr {
+    int32_t n_ues;
+    int32_t cbr_next;      // slice_ran.py:185 cbr_steps_next_arrival
+    int32_t vbr_next;
+    int32_t pad;
+    uint32_t ctr[4];       // Philox draw counters: RAN, CHAN, L1RX, VBR
+};
+static_assert(sizeof(UnitHdr) == 32, "UnitHdr must be 32 bytes");
+
 struct EmbbState {
-    int U, K, MB;          // units, UE slots per unit, burst slots per UE
-    int32_t *n_ues;        // [U]
-    int32_t *cbr_next;     // [U] slice_ran.py:185 cbr_steps_next_arrival
-    int32_t *vbr_next;     // [U]
-    uint32_t *ctr;         // [4][U] Philox draw counters: RAN, CHAN, L1RX, VBR
-    uint32_t *meta;        // [K][U]
-    int32_t *rem;          // [K][U] remaining holding time (slice_ran.py:222)
-    double *nominal;       // [K][U] nominal SINR dB (channel_models.py:167)
-    long long *queue;      // [K][U] ue.queue (bits)
-    double *th;            // [K][U] ue.th EWMA throughput
-    int32_t *bits;         // [K][U] ue.bits of the last scheduled TTI (stale when unscheduled)
-    int32_t *pe;           // [K][U] ue.prbs (low 16) | ue.e_snr (high 16, signed)
-    int32_t *vnext;        // [K][U] VbrSource.steps_to_next_arrival
-    int32_t *nb;           // [K][U] active bursts
-    int32_t *togo;         // [K][MB][U] VbrSource.steps_to_go
+    int U, K, MB;          // units, UE records per unit, burst slots per UE (== MAX_BURSTS)
+    UnitHdr *hdr;          // [U]
+    UeRec *ue;             // [U][K], live UEs first, in arrival order (order decides PF ties and RNG draw order)
     double *acc;           // [U][10] raw accumulators of the last step (info['l1_info'])
     int32_t *cur_prbs;     // [U] PRBs in force (after clamping)
+    // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
+    uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
+    int32_t *perm;         // [U] unit ids sorted by descending n_prbs
+    uint32_t *hist;        // [512] histogram (256) + scatter cursors (256)
+    float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
 struct MmtcState {
@@ -55,7 +73,7 @@ struct MmtcState {
 
 struct Tables {
     const double *trace;   // [3][N_SAMPLES][TRACE_ROWS] fp64, time-major
-    const float *trace32;  // same, fp32 (fast path; decisions near a boundary are redone in fp64)
+    const int32_t *trace_q24; // same, fixed point round(v * 2^24): exact integer window sums on the fast path
     int8_t lut_mcs[256];   // e_snr + 128 -> mcs        (MCSCodeset.mcs_rate_vs_error, channel_models.py:288-295)
     int16_t lut_rate[256]; // e_snr + 128 -> int(158 * rate*order)  (schedulers.py:45)
     double snr_ref[26];    // mcs -> snr_ref
@@ -76,6 +94,8 @@ struct StepParams {
     uint32_t *flags;               // [N]
     uint32_t *flags_acc;           // [N] scratch OR-ed by the slice kernels
     unsigned long long *trace_elems; // [1] algorithmic trace elements touched (B_trace counter)
+    unsigned long long *slow_paths;  // [2] fp64 re-evaluations taken: [0] e_snr rounding guard, [1] reception guard
+    int debug_check;                 // tests only: evaluate fp64 next to every fast decision and record error/guard ratios
 };
 
 }  // namespace rs

@@ -174,3 +174,26 @@ def test_population_statistics_large_batch():
     nu = env.n_ues()
     assert 1.0 < nu.mean() < 6.0 and nu.max() <= 16
     env.close()
+
+
+def test_fast_path_guard_bands_hold():
+    """debug_check evaluates the exact fp64 expression next to every fast decision of the default
+    kernel: the error bound eps must cover |p64 - p32| (ratio < 1), the fixed-point mean must stay
+    far inside its 1e-6 guard, and no decision may differ."""
+    scn, N, T = 0, 2048, 150
+    S, n_prbs = SCN[scn]
+    env = make_env(scn, N, 555)
+    env.reset()
+    env.set_debug_check(True)
+    rng = np.random.default_rng(12)
+    slow = 0
+    for t in range(T):
+        env.step(simplex_actions(rng, N, S, n_prbs))
+        slow += env.diag()["slow_rx_last_step"]
+    d = env.diag()
+    print(d, "slow reception paths per env-step: %.4f" % (slow / (N * T)))
+    assert d["decision_mismatches"] == 0
+    assert d["max_p_err_over_eps"] < 0.6, d
+    assert d["max_mean_err_over_guard"] < 0.1, d
+    assert slow / (N * T) < 1.0          # ~500 reception draws per env-step: well under 1 % re-evaluated
+    env.close()
