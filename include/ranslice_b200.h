@@ -114,6 +114,9 @@ int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *rewar
 int rs_set_debug_check(rs_handle *h, int32_t enable);
 int rs_get_diag(rs_handle *h, double *out, int32_t n);
 
+/* host-only self test of the exact-arithmetic identities the default kernel relies on */
+int rs_selftest(void);
+
 int rs_n_variables(const rs_handle *h);
 const char *rs_last_error(void);
 

@@ -1,114 +1,248 @@
 // K1 default variant ("sorted unit-per-thread, guarded fast math").
 //
 // Same algorithm and results as embb_step.cu (bit-exact: tests compare both against the oracle), but
-// organised for lane utilisation and instruction count on B200:
+// organised for lane utilisation and instruction count on B200.  One thread still owns one
+// (env, eMBB slice) unit for the whole observation period; what changes is who shares its warp and
+// how each decision is evaluated:
 //
-//  * window_kernel + scatter_kernel sort the units of a step by their PRB count (counting sort on
-//    n_prbs, descending).  The PF loop runs ceil(n_prbs/2) dependent iterations and the MI loop
-//    n_prbs iterations, so after sorting the 32 lanes of a warp have (nearly) equal trip counts.
-//    Measured on the unsorted variant: 6.2 of 32 lanes active per instruction.
+//  * window_kernel / scan_kernel / scatter_kernel sort the units of a step (counting sort) by
+//    (n_prbs, PF contention class, live UEs), descending.  Every inner loop of the step has a trip
+//    count given by one of those three numbers (window mean: UEs x PRBs, MI: PRBs, PF: contended RB
+//    chunks), so after the sort the 32 lanes of a warp run the same loops the same number of times.
+//    The unsorted variant measured 6.2 of 32 lanes active per instruction.
+//  * every phase of a TTI starts with __syncwarp: lanes that drifted apart on a rare branch (arrival,
+//    fp64 re-evaluation) are NOT re-merged by the hardware on their own (measured: lanes of one warp
+//    working on different TTIs).
 //  * the window mean behind round(np.mean(snr)) (slice_ran.py:43-45) is an exact int64 sum over a
-//    2^-24 fixed-point copy of the traces (128-bit loads); only when the mean lies within 1e-6 of a
-//    rounding boundary is it recomputed from the fp64 table.
+//    2^-24 fixed-point copy of the traces, read as aligned 128-bit quads with the two end quads
+//    masked; only when the mean lies within 1e-6 of a rounding boundary is it recomputed in fp64.
 //  * the MI-effective-SNR reception probability (channel_models.py:297-313) is evaluated in fp32
 //    (ex2/rcp/lg2 SFU ops) together with a bound eps on |p32 - p64|; the Bernoulli decision
 //    u < p (slice_l1.py:223) is taken from p32 unless |u - p32| <= eps, in which case p is
 //    recomputed in fp64 exactly like the reference.  Saturated sub-bands (mean MI within 1e-4 of 0
-//    or 1) give p == 1.0 / p < 2^-53 in fp64 and need no evaluation at all.
-//  * the PF loop (schedulers.py:47-63) keeps the per-UE metric rate/th cached: one fp64 division
-//    per RB chunk (only the served UE's metric changes), closed form once a single UE is backlogged,
-//    early exit when every queue is drained (the remaining PRBs go to UE 0 with 0 bits).
+//    or 1) give p == 1.0 / p < 2^-53 in fp64 and need no evaluation at all.  The per-PRB MI loop is
+//    flattened over (served UE, quad) so that its trip count is ~n_prbs/4 for every lane.
+//  * the PF loop (schedulers.py:47-63) keeps an fp32 copy of the metric rate/th and takes the
+//    argmax from it when the runner-up is more than 1e-6 (relative) behind; otherwise the candidates
+//    are compared with the exact fp64 quotient.  (b*bits)/slot_length is an exactly rounded
+//    division by a constant (two FMAs, Markstein; exhaustively checked over the domain by
+//    rs_selftest).  Closed form once a single UE is backlogged, early exit when every queue is
+//    drained (the remaining PRBs go to UE 0 with 0 bits, schedulers.py:52 argmax of all-zero).
 #include "embb_device.cuh"
 
 namespace rs {
 
-// ---------------------------------------------------------------------------------------------
-// Pre-pass 1: PRB windows of all eMBB units of a step (node_b.py:71-74) + histogram of n_prbs.
-__global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ StepParams p,
-                                                     const __grid_constant__ EmbbState st) {
-    __shared__ uint32_t s_hist[256];
-    s_hist[threadIdx.x] = 0;
-    __syncthreads();
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env < p.N) {
-        const int32_t *a = p.action + (size_t)env * p.S;
-        int off = 0;
-        uint32_t flags = 0;
-        for (int s = 0; s < p.n_embb; ++s) {
-            int v = a[s];
-            if (v < 0) { v = 0; flags |= 4u; }
-            if (off + v > p.n_prbs) { v = p.n_prbs - off; flags |= 4u; }
-            const int u = env * p.n_embb + s;
-            st.win[u] = (uint32_t)off | ((uint32_t)v << 16);
-            st.cur_prbs[u] = v;
-            atomicAdd(&s_hist[v], 1u);
-            off += v;
-        }
-        if (flags) atomicOr(p.flags_acc + env, flags);
-    }
-    __syncthreads();
-    if (s_hist[threadIdx.x]) atomicAdd(&st.hist[threadIdx.x], s_hist[threadIdx.x]);
+constexpr uint32_t KEY_BINS = SORT_BINS;
+
+// contention class from the previous step's PF work (general RB-loop iterations per TTI)
+__device__ __forceinline__ uint32_t contention_class(uint32_t pf_iters_prev, int slots) {
+    const uint32_t per_tti = pf_iters_prev / (uint32_t)slots;
+    return per_tti >= 16 ? 3u : (per_tti >= 4 ? 2u : (per_tti >= 1 ? 1u : 0u));
 }
 
-// Pre-pass 2: counting-sort scatter, descending n_prbs (long units first).
-__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ EmbbState st) {
-    __shared__ uint32_t s_off[256];
-    // exclusive prefix over bins in descending order: off[n] = sum_{m > n} hist[m]
-    {
-        __shared__ uint32_t s_h[256];
-        s_h[threadIdx.x] = st.hist[threadIdx.x];
+// ---------------------------------------------------------------------------------------------
+// Pre-pass 1: PRB windows of all eMBB units of a step (node_b.py:71-74) + histogram of sort keys.
+__global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ StepParams p,
+                                                     const __grid_constant__ EmbbState st) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.N) return;
+    const int32_t *a = p.action + (size_t)env * p.S;
+    int off = 0;
+    uint32_t flags = 0;
+    for (int s = 0; s < p.n_embb; ++s) {
+        int v = a[s];
+        if (v < 0) { v = 0; flags |= 4u; }
+        if (off + v > p.n_prbs) { v = p.n_prbs - off; flags |= 4u; }
+        const int u = env * p.n_embb + s;
+        st.win[u] = (uint32_t)off | ((uint32_t)v << 16);
+        st.cur_prbs[u] = v;
+        const uint32_t key = ((uint32_t)v << 6) | (contention_class(st.hint[u], p.slots) << 4) |
+                             (uint32_t)min(st.hdr[u].n_ues, 15);
+        atomicAdd(&st.hist[key], 1u);
+        off += v;
+    }
+    if (flags) atomicOr(p.flags_acc + env, flags);
+}
+
+// Pre-pass 2 (one block): exclusive prefix of the histogram in DESCENDING key order (long units first).
+__global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ EmbbState st) {
+    constexpr int PER = KEY_BINS / 1024;
+    __shared__ uint32_t s_tot[1024];
+    uint32_t loc[PER];
+    uint32_t sum = 0;
+    const int base = (1023 - (int)threadIdx.x) * PER;        // thread 0 owns the highest keys
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { loc[i] = st.hist[base + PER - 1 - i]; sum += loc[i]; }
+    s_tot[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                      // Hillis-Steele inclusive scan
+        const uint32_t v = threadIdx.x >= (unsigned)d ? s_tot[threadIdx.x - d] : 0u;
         __syncthreads();
-        uint32_t acc = 0;
-        for (int m = 255; m > (int)threadIdx.x; --m) acc += s_h[m];
-        s_off[threadIdx.x] = acc;
+        s_tot[threadIdx.x] += v;
         __syncthreads();
     }
+    uint32_t run = s_tot[threadIdx.x] - sum;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { st.hist[KEY_BINS + base + PER - 1 - i] = run; run += loc[i]; }
+}
+
+// Pre-pass 3: scatter.
+__global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ StepParams p,
+                                                      const __grid_constant__ EmbbState st) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
-    const uint32_t n = st.win[u] >> 16;
-    const uint32_t pos = s_off[n] + atomicAdd(&st.hist[256 + n], 1u);
+    const uint32_t key = ((st.win[u] >> 16) << 6) | (contention_class(st.hint[u], p.slots) << 4) |
+                         (uint32_t)min(st.hdr[u].n_ues, 15);
+    const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], 1u);
     st.perm[pos] = u;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Walk the PRB window [row0, row0 + n) of one trace column (rows wrap at TRACE_ROWS) with 128-bit
-// loads where the address allows; f(v) is called once per element, in order.
-template <typename F>
-__device__ __forceinline__ void for_window(const int32_t *col, int row0, int n, F &&f) {
-    int row = row0, left = n;
-    while (left > 0) {
-        const int seg = min(left, TRACE_ROWS - row);
-        const int32_t *ptr = col + row;
-        int i = 0;
-        const int head = min(seg, (4 - (int)((reinterpret_cast<uintptr_t>(ptr) >> 2) & 3)) & 3);
-        for (; i < head; ++i) f(__ldg(ptr + i));
-        for (; i + 4 <= seg; i += 4) {
-            const int4 v = __ldg(reinterpret_cast<const int4 *>(ptr + i));
-            f(v.x); f(v.y); f(v.z); f(v.w);
-        }
-        for (; i < seg; ++i) f(__ldg(ptr + i));
-        left -= seg;
-        row = 0;
-    }
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ void atomic_max_float(float *addr, float v) {   // v >= 0
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
 constexpr float Q24_SCALE = 1.0f / 16777216.0f;
 constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr int QUADS_PER_COL = TRACE_ROWS / 4;                // 25: quads never straddle the row wrap
+
+// (b * bits) / slot_length, exactly rounded: q = RN(y * 1000), r = y - q * 1e-3 (exact, FMA),
+// q' = RN(q + r * 1000).  rs_selftest checks q' == y / 1e-3 for every bits in the domain.
+__device__ __forceinline__ double b_bits_over_slot(int bits) {
+    const double y = __dmul_rn(PF_B, (double)bits);
+    const double q = __dmul_rn(y, 1000.0);
+    const double r = __fma_rn(-q, SLOT_LEN, y);
+    return __fma_rn(r, 1000.0, q);
+}
+
+// Exact integer sum of the window [row0, row0 + n) of one trace column; aligned quads, end quads masked.
+__device__ __forceinline__ long long window_sum_q24(const int32_t *col, int row0, int n) {
+    const int4 *col4 = reinterpret_cast<const int4 *>(col);
+    const int lo = row0, hi = row0 + n;                      // absolute rows, may run past 100 (wrap)
+    int q = lo >> 2;
+    const int q_last = (hi - 1) >> 2;
+    long long sum = 0;
+    {   // first quad (masked below lo and at/after hi)
+        const int qq = q >= QUADS_PER_COL ? q - QUADS_PER_COL : q;
+        const int4 v = __ldg(col4 + qq);
+        const int b = q << 2;
+        sum += (b + 0 >= lo && b + 0 < hi) ? v.x : 0;
+        sum += (b + 1 >= lo && b + 1 < hi) ? v.y : 0;
+        sum += (b + 2 >= lo && b + 2 < hi) ? v.z : 0;
+        sum += (b + 3 >= lo && b + 3 < hi) ? v.w : 0;
+        ++q;
+    }
+    int qq = q;
+    while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    for (; q < q_last; ++q) {                                // interior quads: no masks
+        const int4 v = __ldg(col4 + qq);
+        sum += (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
+        qq = (qq + 1 == QUADS_PER_COL) ? 0 : qq + 1;
+    }
+    if (q == q_last) {                                       // last quad (masked at/after hi)
+        const int4 v = __ldg(col4 + qq);
+        const int b = q << 2;
+        sum += (b + 0 < hi) ? v.x : 0;
+        sum += (b + 1 < hi) ? v.y : 0;
+        sum += (b + 2 < hi) ? v.z : 0;
+        sum += (b + 3 < hi) ? v.w : 0;
+    }
+    return sum;
+}
+
+// exact fp64 window mean (same operation order as embb_step.cu); rare
+__device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
+    double sum = 0.0;
+    int row = row0;
+    for (int j = 0; j < n; ++j) {
+        sum += col[row] + nominal;
+        row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
+    }
+    return sum / (double)n;
+}
+
+// State a rare-event call may change; copied in/out around the call so that the hot loop keeps it in registers.
+struct RanCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
+
+// Rare RAN events of a slot, exactly in the reference's order (slice_ran.py:263-268, slice_l1.py:196-198):
+// cbr_arrivals (+CAC), vbr_arrivals, departures, extract_users, add_users -> insert_user.
+__device__ __noinline__ void ran_events(const StepParams &p, const EmbbState &st, UeRec *ue, uint32_t k0, uint32_t k1,
+                                        uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, RanCtx &c) {
+    struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran}, {k0, k1, s, STREAM_CHAN, c.c_chan},
+                                                {k0, k1, s, STREAM_VBR, c.c_vbr}};
+    int n_ues = c.n_ues, cbr_next = c.cbr_next, vbr_next = c.vbr_next;
+    uint32_t next_dep = c.next_dep, flags = c.flags;
+    int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
+    if (cbr_next == 0) {                                                          // slice_ran.py:205-227
+        cbr_next = exp_slots_ms(rng.ran, 1.0 / (2.0 / 60.0));
+        const double cbr_prb = (double)a_prb0 / (double)t;                        // cbr_cac, :195-203
+        const double cbr_th = (double)a_th0 / ((double)t * 1e-3);
+        if (!(cbr_prb >= 20.0 || cbr_th >= 10e6)) {
+            arr_type[n_arr] = 0; arr_vnext[n_arr] = 0;
+            arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
+        }
+    } else cbr_next -= 1;
+    if (vbr_next == 0) {                                                          // :229-249
+        arr_type[n_arr] = 1;
+        arr_vnext[n_arr] = exp_slots(rng.vbr, (1.0 / 1) / 1e-3);                  // VbrSource.__init__, traffic_generators.py:65-66
+        arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
+        vbr_next = exp_slots_ms(rng.ran, 1.0 / (5.0 / 60.0));
+    } else vbr_next -= 1;
+    if (clock == next_dep) {                                                      // departures, :251-261 (order kept)
+        int w = 0;
+        uint32_t nd = DEP_NEVER;
+        for (int k = 0; k < n_ues; ++k) {
+            const uint32_t d = ue[k].dep_at;
+            if (d != clock) {
+                if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
+                nd = min(nd, d);
+                ++w;
+            }
+        }
+        n_ues = w;
+        next_dep = nd;
+    }
+    for (int a = 0; a < n_arr; ++a) {                                             // slice_l1.py:183-186
+        const int rem = arr_rem[a] - 1;                          // this slot's departures() already ticked it
+        if (rem == 0) { flags |= 8u; continue; }
+        if (n_ues >= st.K) { flags |= 1u; continue; }
+        UeRec r;
+        const int fading = (int)rng.chan.integers(3);                             // channel_models.py:163-169
+        const int index = (int)rng.chan.integers(N_SAMPLES);
+        const int step = rng.chan.integers(2) ? 1 : -1;
+        r.nominal = draw_nominal_sinr(rng.chan, p.prop_A, p.prop_B);
+        r.meta = pack_meta(arr_type[a], fading, step, index);
+        r.dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem;
+        r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
+#pragma unroll
+        for (int j = 0; j < MAX_BURSTS; ++j) r.togo[j] = 0;
+        store_rec(ue + n_ues, r);
+        next_dep = min(next_dep, r.dep_at);
+        ++n_ues;
+    }
+    c.c_ran = rng.ran.n; c.c_chan = rng.chan.n; c.c_vbr = rng.vbr.n;
+    c.n_ues = n_ues; c.cbr_next = cbr_next; c.vbr_next = vbr_next; c.next_dep = next_dep; c.flags = flags;
+}
+
+// exact reception probability (reference fp64 path); rare
+__device__ __noinline__ double response_exact(const Tables &tb, int mcs, size_t col_off, int row0, int n, double nominal) {
+    return response_fp64(tb, mcs, tb.trace + col_off, row0, n, nominal);
+}
 
 template <int K>
-__global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ StepParams p,
-                                                      const __grid_constant__ EmbbState st,
-                                                      const __grid_constant__ Tables tb) {
+__global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__ StepParams p,
+                                                         const __grid_constant__ EmbbState st,
+                                                         const __grid_constant__ Tables tb) {
     // small lookup tables: constant-bank reads with divergent indices serialise, shared memory does not
     __shared__ int16_t s_rate[256];
     __shared__ int8_t s_mcs[256];
@@ -119,6 +253,7 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
     __syncthreads();
 
     const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < st.U);
     if (tix >= st.U) return;
     const int u = st.perm[tix];
     const int env = u / p.n_embb, s = u - env * p.n_embb;
@@ -130,175 +265,204 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
     UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
     const uint64_t seed = p.seed0 + (uint64_t)env;
-    PhiloxStream r_ran{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_RAN, hdr.ctr[0]};
-    PhiloxStream r_chan{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_CHAN, hdr.ctr[1]};
-    PhiloxStream r_rx{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_L1RX, hdr.ctr[2]};
-    PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c_ran = hdr.ctr[0];
+    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1]}, r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2]},
+        r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
 
     int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
+    uint32_t clock = hdr.clock, next_dep = DEP_NEVER;
+    for (int k = 0; k < n_ues; ++k) next_dep = min(next_dep, ue[k].dep_at);
     int a_traffic[2] = {0, 0}, a_th[2] = {0, 0}, a_prb[2] = {0, 0};     // slice_ran.py:270-273 reset_info
     double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
-    unsigned long long trace_elems = 0;
-    unsigned slow_snr = 0, slow_rx = 0;
+    unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
     const float Af = (float)tb.A, Bf = (float)tb.B;
     const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * 16777216.0) : 0.0;
 
+    // per-UE scratch of one TTI (local memory, only the first n_ues entries are touched)
+    long long qq[K];
+    double th[K];
+    float metf[K], nomf[K], mavg[K];
+    int coloff[K], bits[K], pe_l[K];
+    int16_t rate[K], new_bits[K];
+    int8_t mcs[K];
+    uint8_t rbs[K];
+
     for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
-        // ================= slice_ran.slot(): arrivals (slice_ran.py:205-249)
-        int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
-        if (cbr_next == 0) {
-            cbr_next = exp_slots_ms(r_ran, 1.0 / (2.0 / 60.0));
-            const double cbr_prb = (double)a_prb[0] / (double)t;                 // cbr_cac, :195-203
-            const double cbr_th = (double)a_th[0] / ((double)t * 1e-3);
-            if (!(cbr_prb >= 20.0 || cbr_th >= 10e6)) {
-                arr_type[n_arr] = 0; arr_vnext[n_arr] = 0;
-                arr_rem[n_arr++] = exp_slots_ms(r_ran, 30.0);
-            }
-        } else cbr_next -= 1;
-        if (vbr_next == 0) {
-            arr_type[n_arr] = 1;
-            arr_vnext[n_arr] = exp_slots(r_vbr, (1.0 / 1) / 1e-3);              // VbrSource.__init__, traffic_generators.py:65-66
-            arr_rem[n_arr++] = exp_slots_ms(r_ran, 30.0);
-            vbr_next = exp_slots_ms(r_ran, 1.0 / (5.0 / 60.0));
-        } else vbr_next -= 1;
-        // ================= departures (slice_ran.py:251-261) + order-preserving compaction (slice_l1.py:188-191)
-        {
-            int w = 0;
-            for (int k = 0; k < n_ues; ++k) {
-                const int rem = ue[k].rem - 1;
-                if (rem != 0) {
-                    if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
-                    ue[w].rem = rem;
-                    ++w;
-                }
-            }
-            n_ues = w;
-        }
-        // ================= add_users (slice_l1.py:183-186) -> insert_user (channel_models.py:163-169)
-        for (int a = 0; a < n_arr; ++a) {
-            const int rem = arr_rem[a] - 1;                      // this slot's departures() already ticked it
-            if (rem == 0) { flags |= 8u; continue; }
-            if (n_ues >= st.K) { flags |= 1u; continue; }
-            UeRec r;
-            const int fading = (int)r_chan.integers(3);
-            const int index = (int)r_chan.integers(N_SAMPLES);
-            const int step = r_chan.integers(2) ? 1 : -1;
-            r.nominal = draw_nominal_sinr(r_chan, p.prop_A, p.prop_B);
-            r.meta = pack_meta(arr_type[a], fading, step, index);
-            r.rem = rem; r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
-#pragma unroll
-            for (int j = 0; j < MAX_BURSTS; ++j) r.togo[j] = 0;
-            store_rec(ue + n_ues, r);
-            ++n_ues;
-        }
+        __syncwarp(warp_mask);
+        ++clock;
+        // ================= slice_ran.slot(): arrivals / departures only on event slots
+        if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
+            RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
+            ran_events(p, st, ue, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], c);
+            c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
+            n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
+        } else { cbr_next -= 1; vbr_next -= 1; }
+
         // ================= per-UE traffic + SNR estimate (slice_l1.py:200-213); fills the PF scratch
+        __syncwarp(warp_mask);
         long long queued = 0;
-        int16_t new_bits[K];
-        long long qq[K];
-        double th[K], met[K];
-        int16_t rate[K];
-        int8_t mcs[K];
         int n_backlog = 0;
+        uint32_t types = 0;
         for (int k = 0; k < n_ues; ++k) {
             UeRec r;
             load_rec(ue + k, r);
             int nb_bits;
             if ((r.meta & 1u) == 0) nb_bits = 500;               // CbrSource: 500000 b/s * 1e-3 every slot
-            else nb_bits = vbr_source_step(r, r_vbr, flags);
+            else { nb_bits = vbr_source_step(r, r_vbr, flags); types |= 1u << k; }
             new_bits[k] = (int16_t)nb_bits;
             r.queue += nb_bits;
             queued += r.queue;
             if (n_prbs > 0) {
                 int index = (int)(r.meta >> 4), step = (r.meta & 8u) ? 1 : -1;
                 const int fading = (int)((r.meta >> 1) & 3u);
-                walk_trace(r_chan, index, step);                 // channel_models.py:171-191
+                walk_trace(r_chan, index, step);               // channel_models.py:171-191
                 r.meta = pack_meta((int)(r.meta & 1u), fading, step, index);
-                const size_t col_off = ((size_t)fading * N_SAMPLES + index) * TRACE_ROWS;
-                long long isum = 0;
-                for_window(tb.trace_q24 + col_off, row_base, n_prbs, [&](int v) { isum += v; });
+                const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
+                coloff[k] = col_off;
+                const long long isum = window_sum_q24(tb.trace_q24 + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
                 double mean = (double)isum * inv_n + r.nominal;  // |mean - reference mean| < 2^-25 + few ulp
                 const double fr = mean - floor(mean);
-                if (fabs(fr - 0.5) < 1e-6 || p.debug_check) {    // within the guard of a rounding boundary: exact path
-                    const double *col = tb.trace + col_off;
-                    double sum = 0.0;
-                    int row = row_base;
-                    for (int j = 0; j < n_prbs; ++j) {
-                        sum += col[row] + r.nominal;
-                        row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
-                    }
-                    const double exact = sum / (double)n_prbs;
+                const bool near = fabs(fr - 0.5) < 1e-6;         // within the guard of a rounding boundary
+                if (near || p.debug_check) {
+                    const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, r.nominal);
                     if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / 1e-6));
-                    if (fabs(fr - 0.5) < 1e-6) { mean = exact; ++slow_snr; }
+                    if (near) { mean = exact; ++slow_snr; }
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
                 r.pe = (r.pe & 0xFFFF) | (e_snr << 16);
             }
-            store_rec(ue + k, r);
+            // write back what changed: quad 0 (meta, vnext), quad 2 (queue, pe, nb), quad 3 (bursts, VBR only)
+            {
+                int4 *g = reinterpret_cast<int4 *>(ue + k);
+                const int4 *l = reinterpret_cast<const int4 *>(&r);
+                g[0] = l[0]; g[2] = l[2];
+                if (r.meta & 1u) g[3] = l[3];
+            }
             // PF scratch (schedulers.py:37-45)
             const int e = min(max(r.pe >> 16, -128), 127) + 128;
             mcs[k] = s_mcs[e];
             rate[k] = s_rate[e];
             th[k] = r.th > 1.0 ? r.th : 1.0;
             qq[k] = r.queue;
+            nomf[k] = (float)r.nominal;
+            bits[k] = r.bits;                                    // stale values, kept if the slice is not scheduled
+            pe_l[k] = r.pe;
             n_backlog += r.queue > 0;
         }
         // ================= scheduling + reception (slice_l1.py:215-224)
-        if (queued > 0 && n_prbs > 0) {
-            uint8_t rbs[K];
-            int bits[K];
+        __syncwarp(warp_mask);
+        const bool scheduled = queued > 0 && n_prbs > 0;
+        const unsigned sched_mask = __ballot_sync(warp_mask, scheduled);
+        if (scheduled) {
             for (int k = 0; k < n_ues; ++k) { rbs[k] = 0; bits[k] = 0; }
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63)
             int r = 0;
             if (n_backlog > 1)
-                for (int k = 0; k < n_ues; ++k) met[k] = qq[k] > 0 ? (double)rate[k] / th[k] : 0.0;
+                for (int k = 0; k < n_ues; ++k)
+                    metf[k] = qq[k] > 0 ? (float)rate[k] * rcp_approx((float)th[k]) : 0.0f;
             while (r < n_prbs) {
                 if (n_backlog == 0) { rbs[0] += n_prbs - r; break; }        // all metrics 0 -> argmax 0, tx 0
                 if (n_backlog == 1) {                                       // no competition: closed form
                     int j = 0;
                     while (qq[j] <= 0) ++j;
-                    const int left = n_prbs - r;
-                    const long long cap2 = 2ll * rate[j];
-                    const long long need = (qq[j] + cap2 - 1) / cap2;       // 2-PRB chunks until drained
-                    const int full = left >> 1;
-                    if (need <= full) {
-                        rbs[j] += 2 * (int)need; bits[j] += (int)qq[j]; qq[j] = 0; r += 2 * (int)need;
+                    const int left = n_prbs - r, full = left >> 1;
+                    const int cap2 = 2 * rate[j];
+                    if (qq[j] <= (long long)full * cap2) {                  // drained within the 2-PRB chunks
+                        const int q32 = (int)qq[j];
+                        const int need = (q32 + cap2 - 1) / cap2;
+                        rbs[j] += 2 * need; bits[j] += q32; qq[j] = 0; r += 2 * need;
                         n_backlog = 0;
                         continue;
                     }
-                    long long tx = (long long)full * cap2;
-                    rbs[j] += 2 * full; qq[j] -= tx; bits[j] += (int)tx;
+                    int tx = full * cap2;
+                    rbs[j] += 2 * full; qq[j] -= tx; bits[j] += tx;
                     if (left & 1) {                                         // last, single-PRB chunk
-                        tx = min((long long)rate[j], qq[j]);
-                        rbs[j] += 1; qq[j] -= tx; bits[j] += (int)tx;
+                        tx = (int)min((long long)rate[j], qq[j]);
+                        rbs[j] += 1; qq[j] -= tx; bits[j] += tx;
                     }
                     break;
                 }
+                ++pf_iters;
                 const int c = min(n_prbs - r, 2);
+                // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 copy, exact when close
                 int idx = 0;
-                double best = met[0];
-                for (int k = 1; k < n_ues; ++k)                             // np.argmax -> first maximum
-                    if (met[k] > best) { best = met[k]; idx = k; }
+                float best = metf[0], second = -1.0f;
+                for (int k = 1; k < n_ues; ++k) {
+                    const float m = metf[k];
+                    if (m > best) { second = best; best = m; idx = k; }
+                    else second = fmaxf(second, m);
+                }
+                if (second >= best * (1.0f - 1e-6f)) {                      // too close for fp32: exact quotients
+                    const float lim = best * (1.0f - 1e-6f);
+                    double best64 = -1.0;
+                    for (int k = 0; k < n_ues; ++k)
+                        if (metf[k] >= lim && qq[k] > 0) {
+                            const double m64 = (double)rate[k] / th[k];
+                            if (m64 > best64) { best64 = m64; idx = k; }
+                        }
+                }
                 rbs[idx] += c;
-                const long long cap = (long long)c * rate[idx];
-                const long long tx = cap < qq[idx] ? cap : qq[idx];
+                const int cap = c * rate[idx];
+                const int tx = (long long)cap < qq[idx] ? cap : (int)qq[idx];
                 qq[idx] -= tx;
-                bits[idx] += (int)tx;
-                th[idx] = PF_A * th[idx] + PF_B * (double)bits[idx] / SLOT_LEN;
-                if (qq[idx] > 0) met[idx] = (double)rate[idx] / th[idx];
-                else { met[idx] = 0.0; --n_backlog; }
+                bits[idx] += tx;
+                th[idx] = __dadd_rn(__dmul_rn(PF_A, th[idx]), b_bits_over_slot(bits[idx]));
+                if (qq[idx] > 0) metf[idx] = (float)rate[idx] * rcp_approx((float)th[idx]);
+                else { metf[idx] = 0.0f; --n_backlog; }
                 r += 2;
             }
+            // ---- MI sums of the served sub-bands, flattened over (UE, quad): ~n_prbs/4 iterations per lane
+            __syncwarp(sched_mask);
+            {
+                int k = -1, left = 0, q = 0, lo = 0, hi = 0, o = row_base;
+                float c0 = 0.f, c1 = 0.f, nf = 0.f;
+                double msum = 0.0;
+                const int4 *col4 = nullptr;
+                for (;;) {
+                    if (left == 0) {
+                        if (k >= 0) mavg[k] = (float)(msum / (double)rbs[k]);
+                        do { ++k; if (k < n_ues) { lo = o; o += rbs[k]; } } while (k < n_ues && rbs[k] < 2);
+                        if (k >= n_ues) break;
+                        hi = lo + rbs[k];
+                        q = lo >> 2;
+                        left = ((hi - 1) >> 2) - q + 1;
+                        const int m = s_mod[mcs[k]];
+                        const float kf = (float)c_MI_K[m], x0f = (float)c_MI_X0[m];
+                        c1 = -kf * LOG2E_F; c0 = kf * x0f * LOG2E_F; nf = nomf[k];
+                        col4 = reinterpret_cast<const int4 *>(tb.trace_q24 + coloff[k]);
+                        msum = 0.0;
+                    }
+                    int qq4 = q;
+                    while (qq4 >= QUADS_PER_COL) qq4 -= QUADS_PER_COL;
+                    const int4 v = __ldg(col4 + qq4);
+                    const int b = q << 2;
+                    float part = 0.f;
+                    {
+                        const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.x, Q24_SCALE, nf), c1, c0));
+                        const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.y, Q24_SCALE, nf), c1, c0));
+                        const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.z, Q24_SCALE, nf), c1, c0));
+                        const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.w, Q24_SCALE, nf), c1, c0));
+                        const float m0 = rcp_approx(1.0f + e0), m1 = rcp_approx(1.0f + e1);
+                        const float m2 = rcp_approx(1.0f + e2), m3 = rcp_approx(1.0f + e3);
+                        part += (b + 0 >= lo && b + 0 < hi) ? m0 : 0.f;
+                        part += (b + 1 >= lo && b + 1 < hi) ? m1 : 0.f;
+                        part += (b + 2 >= lo && b + 2 < hi) ? m2 : 0.f;
+                        part += (b + 3 >= lo && b + 3 < hi) ? m3 : 0.f;
+                    }
+                    msum += (double)part;
+                    ++q; --left;
+                }
+            }
             // ---- per-UE reception (schedulers.py:66-76, slice_l1.py:219-224) + transmission_step (slice_ran.py:51-55)
+            __syncwarp(sched_mask);
             int o = 0;
             for (int k = 0; k < n_ues; ++k) {
                 const int prbs = rbs[k];
                 int b = bits[k];
                 UeRec *g = ue + k;
                 if (prbs) {
-                    const uint32_t meta = g->meta;
-                    const double nominal = g->nominal;
-                    const size_t col_off = ((size_t)((meta >> 1) & 3u) * N_SAMPLES + (meta >> 4)) * TRACE_ROWS;
                     const int row0 = (row_base + o) % TRACE_ROWS;
                     const double u01 = r_rx.u01();
                     trace_elems += (unsigned)prbs;
@@ -306,28 +470,17 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
                     float dbg_p32 = -1.f, dbg_eps = 0.f;
                     if (prbs == 1) need_exact = true;                        // single RB: no MI averaging, one fp64 sigmoid
                     else {
-                        const int m = s_mod[mcs[k]];
-                        const float kf = (float)c_MI_K[m], x0f = (float)c_MI_X0[m];
-                        const float c1 = -kf * LOG2E_F, c0 = kf * x0f * LOG2E_F, nomf = (float)nominal;
-                        double msum = 0.0;
-                        float part = 0.f;
-                        int cnt = 0;
-                        for_window(tb.trace_q24 + col_off, row0, prbs, [&](int v) {
-                            const float snr = __fmaf_rn((float)v, Q24_SCALE, nomf);
-                            const float e = ex2_approx(__fmaf_rn(snr, c1, c0));      // exp(-k (snr - x0))
-                            part += __fdividef(1.0f, 1.0f + e);
-                            if (++cnt == 4) { msum += (double)part; part = 0.f; cnt = 0; }
-                        });
-                        msum += (double)part;
-                        const float mavg = (float)(msum / (double)prbs);
-                        if (mavg >= 1.0f - 1e-4f) received = true;          // p == 1.0 exactly in fp64
-                        else if (mavg <= 1e-4f) received = false;           // p < 2^-53 (see header)
+                        const float m = mavg[k];
+                        if (m >= 1.0f - 1e-4f) received = true;              // p == 1.0 exactly in fp64
+                        else if (m <= 1e-4f) received = false;               // p < 2^-53
                         else {
-                            const float rr = __fdividef(1.0f, mavg) - 1.0f;
+                            const int md = s_mod[mcs[k]];
+                            const float kf = (float)c_MI_K[md], x0f = (float)c_MI_X0[md];
+                            const float rr = rcp_approx(m) - 1.0f;
                             const float seff = x0f - __logf(rr) / kf;       // inv_sigmoid, channel_models.py:39-41
                             const float L = Af * (seff - s_ref[mcs[k]]) - Bf;
-                            const float p32 = __fdividef(1.0f, 1.0f + __expf(-L));
-                            const float epsL = 2e-5f / (kf * mavg * (1.0f - mavg)) + 4e-5f;   // 8 * dm / (k m (1-m)), dm <= 2.5e-6
+                            const float p32 = rcp_approx(1.0f + __expf(-L));
+                            const float epsL = 2e-5f / (kf * m * (1.0f - m)) + 4e-5f;   // 8 dm / (k m (1-m)), dm <= 2.5e-6
                             const float eps = 1.1f * p32 * (1.0f - p32) * epsL + 5e-7f;
                             const double d = u01 - (double)p32;
                             received = d < 0.0;
@@ -336,7 +489,7 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
                         }
                     }
                     if (need_exact || p.debug_check) {
-                        const double pr = response_fp64(tb, mcs[k], tb.trace + col_off, row0, prbs, nominal);
+                        const double pr = response_exact(tb, mcs[k], (size_t)coloff[k], row0, prbs, g->nominal);
                         const bool exact = u01 < pr;
                         if (p.debug_check && !need_exact) {
                             if (dbg_p32 >= 0.f) atomic_max_float(st.dbg + 0, (float)(fabs(pr - (double)dbg_p32) / (double)dbg_eps));
@@ -347,28 +500,31 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
                     if (!received) b = 0;
                 } else b = 0;
                 o += prbs;
-                const long long q = g->queue - b;
-                g->queue = q > 0 ? q : 0;
-                g->th = PF_A * g->th + PF_B * (double)b / SLOT_LEN;
+                const long long q = qq[k] + bits[k] - b;         // ue.queue - received bits (qq already had bits[k] taken out)
+                g->queue = q;
+                g->th = __dadd_rn(__dmul_rn(PF_A, g->th), b_bits_over_slot(b));
                 g->bits = b;
-                g->pe = (g->pe & 0xFFFF0000) | prbs;
+                pe_l[k] = (pe_l[k] & 0xFFFF0000) | prbs;
+                g->pe = pe_l[k];
+                bits[k] = b;
+                qq[k] = q;
             }
         }
-        // ================= update_info (slice_ran.py:278-305)
+        // ================= update_info (slice_ran.py:278-305), from the per-TTI scratch
+        __syncwarp(warp_mask);
         {
             long long q[2] = {0, 0};
             int sn[2] = {0, 0}, n[2] = {0, 0};
             for (int k = 0; k < n_ues; ++k) {
-                const UeRec *g = ue + k;
-                const int ty = (int)(g->meta & 1u);
-                const int pe = g->pe;
+                const int ty = (int)((types >> k) & 1u);
                 a_traffic[ty] += new_bits[k];
-                a_th[ty] += g->bits;
-                a_prb[ty] += pe & 0xFFFF;
-                q[ty] += g->queue;
-                sn[ty] += pe >> 16;
+                a_th[ty] += bits[k];
+                a_prb[ty] += pe_l[k] & 0xFFFF;
+                q[ty] += qq[k];
+                sn[ty] += pe_l[k] >> 16;
                 n[ty] += 1;
             }
+#pragma unroll
             for (int ty = 0; ty < 2; ++ty) {
                 const double nn = (double)max(n[ty], 1);
                 a_queue[ty] += (double)q[ty] / nn;
@@ -377,28 +533,31 @@ __global__ void __launch_bounds__(128) embb_step_fast(const __grid_constant__ St
         }
     }
 
+    __syncwarp(warp_mask);
     // ---- persist slice scalars
-    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next;
-    hdr.ctr[0] = r_ran.n; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
+    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
+    hdr.ctr[0] = c_ran; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
     st.hdr[u] = hdr;
+    st.hint[u] = pf_iters;
 
     // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
     const double acc[10] = {(double)a_traffic[0], (double)a_th[0], (double)a_prb[0], a_queue[0], a_snr[0],
                             (double)a_traffic[1], (double)a_th[1], (double)a_prb[1], a_queue[1], a_snr[1]};
     finish_embb_unit(p, st, env, s, u, acc, flags);
-    if (trace_elems) atomicAdd(p.trace_elems, trace_elems);
+    if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
     if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
     if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
 }
 
 // NodeB.reset for the eMBB units (slice_l1.py:145-148, slice_ran.py:182-190): UEs and timers cleared,
-// Philox counters keep running (the reference never reseeds on reset).
+// Philox counters and the unit clock keep running (the reference never reseeds on reset).
 __global__ void __launch_bounds__(256) embb_reset_kernel(const __grid_constant__ EmbbState st) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
     UnitHdr h = st.hdr[u];
-    h.n_ues = 0; h.cbr_next = 0; h.vbr_next = 0; h.pad = 0;
+    h.n_ues = 0; h.cbr_next = 0; h.vbr_next = 0;
     st.hdr[u] = h;
+    st.hint[u] = 0;
     for (int j = 0; j < 10; ++j) st.acc[(size_t)u * 10 + j] = 0.0;
 }
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
@@ -406,13 +565,14 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
 }
 
 int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    cudaMemsetAsync(st.hist, 0, 512 * sizeof(uint32_t), stream);
+    cudaMemsetAsync(st.hist, 0, 2 * KEY_BINS * sizeof(uint32_t), stream);
     window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st);
-    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(st);
+    scan_kernel<<<1, 1024, 0, stream>>>(st);
+    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st);
     const int threads = 128, blocks = (st.U + threads - 1) / threads;
     if (st.K <= 16) embb_step_fast<16><<<blocks, threads, 0, stream>>>(p, st, tb);
     else embb_step_fast<32><<<blocks, threads, 0, stream>>>(p, st, tb);
-    return 3;   // kernels launched
+    return 4;   // kernels launched
 }
 
 }  // namespace rs

@@ -39,11 +39,13 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
     PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
 
     int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
+    uint32_t clock = hdr.clock;
     int a_traffic[2] = {0, 0}, a_th[2] = {0, 0}, a_prb[2] = {0, 0};     // slice_ran.py:270-273 reset_info
     double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
     unsigned long long trace_elems = 0;
 
     for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
+        ++clock;
         // ================= slice_ran.slot(): arrivals (slice_ran.py:205-249)
         int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
         if (cbr_next == 0) {
@@ -65,10 +67,8 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
         {
             int w = 0;
             for (int k = 0; k < n_ues; ++k) {
-                const int rem = ue[k].rem - 1;
-                if (rem != 0) {
+                if (ue[k].dep_at != clock) {                     // remaining_time hits 0 exactly at dep_at
                     if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
-                    ue[w].rem = rem;
                     ++w;
                 }
             }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
             const int step = r_chan.integers(2) ? 1 : -1;
             r.nominal = draw_nominal_sinr(r_chan, p.prop_A, p.prop_B);
             r.meta = pack_meta(arr_type[a], fading, step, index);
-            r.rem = rem; r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
+            r.dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem; r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
 #pragma unroll
             for (int j = 0; j < MAX_BURSTS; ++j) r.togo[j] = 0;
             store_rec(ue + n_ues, r);
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
     }
 
     // ---- persist slice scalars
-    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next;
+    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
     hdr.ctr[0] = r_ran.n; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
     st.hdr[u] = hdr;
 

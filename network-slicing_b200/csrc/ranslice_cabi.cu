@@ -191,12 +191,12 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
-        sc.take<uint32_t>(U); sc.take<int32_t>(U); sc.take<uint32_t>(512); sc.take<float>(8);
+        sc.take<uint32_t>(U); sc.take<int32_t>(U); sc.take<uint32_t>(2 * rs::SORT_BINS); sc.take<uint32_t>(U); sc.take<float>(8);
         CU(cudaMalloc(&h->scratch, sc.off + 256));
         CU(cudaMemset(h->scratch, 0, sc.off + 256));
         Carver rc; rc.base = h->scratch;
         h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(U);
-        h->embb.hist = rc.take<uint32_t>(512); h->embb.dbg = rc.take<float>(8);
+        h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
     }
 
     const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;
@@ -352,6 +352,23 @@ int rs_set_state(rs_handle *h, const void *blob, size_t bytes) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(h->arena, blob, bytes, cudaMemcpyHostToDevice));
     h->was_reset = true;
+    return RS_OK;
+}
+
+// Host-side exhaustive check of the identities the fast kernel relies on (no GPU needed):
+//  (1) the two-FMA division by slot_length equals the IEEE quotient for every bits value a TTI can carry
+//      ((b * bits) / slot_length, schedulers.py:63 / slice_ran.py:55; bits <= 200 PRBs * 853 bits);
+//  (2) PF_A / PF_B are the reference's 1 - 1/50 and 1/50.
+int rs_selftest(void) {
+    const double b = 1.0 / 50, a = 1 - b, slot = 1e-3;
+    if (a != 0.98 || b != 0.02) return fail(RS_E_STATE, "EWMA constants differ from 1-1/50, 1/50");
+    for (int bits = 0; bits <= 200 * 853 + 1000; ++bits) {
+        const double y = b * (double)bits;
+        const double q = y * 1000.0;
+        const double r = std::fma(-q, slot, y);
+        const double q2 = std::fma(r, 1000.0, q);
+        if (q2 != y / slot) return fail(RS_E_STATE, "two-FMA division by slot_length is not exact for bits=" + std::to_string(bits));
+    }
     return RS_OK;
 }
 

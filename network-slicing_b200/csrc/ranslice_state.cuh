@@ -23,7 +23,7 @@ __host__ __device__ inline uint32_t pack_meta(int type, int fading, int step, in
 constexpr int MAX_BURSTS = 8;      // VbrSource active bursts kept per UE (P(>8) ~ 1e-9 per UE-sample, flagged)
 struct __align__(16) UeRec {
     uint32_t meta;         // type / fading / step / trace index (pack_meta)
-    int32_t rem;           // remaining holding time, slots   (slice_ran.py:222)
+    uint32_t dep_at;       // unit clock value at which the UE departs (slice_ran.py:222,251-261 as an absolute time; DEP_NEVER = holding drawn as 0)
     int32_t vnext;         // VbrSource.steps_to_next_arrival (traffic_generators.py:66)
     int32_t bits;          // ue.bits of the last scheduled TTI (stale when unscheduled)
     double nominal;        // nominal SINR dB                 (channel_models.py:167)
@@ -35,11 +35,12 @@ struct __align__(16) UeRec {
 };
 static_assert(sizeof(UeRec) == 64, "UeRec must be 64 bytes");
 
+constexpr uint32_t DEP_NEVER = 0xFFFFFFFFu;
 struct __align__(16) UnitHdr {
     int32_t n_ues;
     int32_t cbr_next;      // slice_ran.py:185 cbr_steps_next_arrival
     int32_t vbr_next;
-    int32_t pad;
+    uint32_t clock;        // slots simulated by this unit since rs_create (wraps after 2^32 slots = 8.6e7 steps)
     uint32_t ctr[4];       // Philox draw counters: RAN, CHAN, L1RX, VBR
 };
 static_assert(sizeof(UnitHdr) == 32, "UnitHdr must be 32 bytes");
@@ -52,10 +53,13 @@ struct EmbbState {
     int32_t *cur_prbs;     // [U] PRBs in force (after clamping)
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
-    int32_t *perm;         // [U] unit ids sorted by descending n_prbs
-    uint32_t *hist;        // [512] histogram (256) + scatter cursors (256)
+    int32_t *perm;         // [U] unit ids sorted by descending (n_prbs, contention class, live UEs)
+    uint32_t *hist;        // [2 * SORT_BINS] histogram / offsets + scatter cursors
+    uint32_t *hint;        // [U] PF-loop iterations of the previous step (sort hint only; never affects results)
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
+
+constexpr int SORT_BINS = 16384;   // key = n_prbs << 6 | contention class << 4 | min(live UEs, 15)
 
 struct MmtcState {
     int U, Q;              // units (env * n_mmtc + m), backlog cap
