@@ -26,6 +26,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
+    extra = os.environ.get("RS_NVCC_EXTRA", "").split()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "ranslice_b200.h"))
     objdir = os.path.join(PKG, "build")
@@ -38,7 +39,7 @@ def build(force=False, verbose=False):
         src, obj = pair
         if not force and not _stale(obj, [os.path.join(CSRC, src)] + headers):
             return
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src] = r.stderr
         if r.returncode != 0:

@@ -34,6 +34,26 @@ namespace rs {
 
 constexpr uint32_t KEY_BINS = SORT_BINS;
 
+// RS_EXP: bit mask of timing experiments (results become wrong; never set in a release build)
+//   1: window-mean trace loads replaced by a constant   2: MI-loop trace loads replaced by a constant
+//   4: skip the MI loop                                   8: skip the contended PF iterations
+#ifndef RS_EXP
+#define RS_EXP 0
+#endif
+#if RS_EXP & 1
+#define LDQ_B(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
+#else
+#define LDQ_B(p) __ldg(p)
+#endif
+#if RS_EXP & 2
+#define LDQ_D(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
+#else
+#define LDQ_D(p) __ldg(p)
+#endif
+#ifndef RS_FAST_MIN_BLOCKS
+#define RS_FAST_MIN_BLOCKS 4      // resident 128-thread blocks per SM the register budget is sized for
+#endif
+
 // contention class from the previous step's PF work (general RB-loop iterations per TTI)
 __device__ __forceinline__ uint32_t contention_class(uint32_t pf_iters_prev, int slots) {
     const uint32_t per_tti = pf_iters_prev / (uint32_t)slots;
@@ -112,6 +132,8 @@ __device__ __forceinline__ void atomic_max_float(float *addr, float v) {   // v 
     atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 constexpr float Q24_SCALE = 1.0f / 16777216.0f;
 constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr int QUADS_PER_COL = TRACE_ROWS / 4;                // 25: quads never straddle the row wrap
@@ -134,7 +156,7 @@ __device__ __forceinline__ long long window_sum_q24(const int32_t *col, int row0
     long long sum = 0;
     {   // first quad (masked below lo and at/after hi)
         const int qq = q >= QUADS_PER_COL ? q - QUADS_PER_COL : q;
-        const int4 v = __ldg(col4 + qq);
+        const int4 v = LDQ_B(col4 + qq);
         const int b = q << 2;
         sum += (b + 0 >= lo && b + 0 < hi) ? v.x : 0;
         sum += (b + 1 >= lo && b + 1 < hi) ? v.y : 0;
@@ -144,13 +166,26 @@ __device__ __forceinline__ long long window_sum_q24(const int32_t *col, int row0
     }
     int qq = q;
     while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
-    for (; q < q_last; ++q) {                                // interior quads: no masks
-        const int4 v = __ldg(col4 + qq);
+    for (; q + 4 <= q_last; q += 4) {                        // interior quads, 4 independent loads in flight
+        int i0 = qq, i1 = qq + 1, i2 = qq + 2, i3 = qq + 3;
+        if (i1 >= QUADS_PER_COL) i1 -= QUADS_PER_COL;
+        if (i2 >= QUADS_PER_COL) i2 -= QUADS_PER_COL;
+        if (i3 >= QUADS_PER_COL) i3 -= QUADS_PER_COL;
+        const int4 v0 = LDQ_B(col4 + i0), v1 = LDQ_B(col4 + i1), v2 = LDQ_B(col4 + i2), v3 = LDQ_B(col4 + i3);
+        sum += ((long long)v0.x + (long long)v0.y + (long long)v0.z + (long long)v0.w) +
+               ((long long)v1.x + (long long)v1.y + (long long)v1.z + (long long)v1.w) +
+               ((long long)v2.x + (long long)v2.y + (long long)v2.z + (long long)v2.w) +
+               ((long long)v3.x + (long long)v3.y + (long long)v3.z + (long long)v3.w);
+        qq += 4;
+        if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    }
+    for (; q < q_last; ++q) {                                // remaining interior quads: no masks
+        const int4 v = LDQ_B(col4 + qq);
         sum += (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
         qq = (qq + 1 == QUADS_PER_COL) ? 0 : qq + 1;
     }
     if (q == q_last) {                                       // last quad (masked at/after hi)
-        const int4 v = __ldg(col4 + qq);
+        const int4 v = LDQ_B(col4 + qq);
         const int b = q << 2;
         sum += (b + 0 < hi) ? v.x : 0;
         sum += (b + 1 < hi) ? v.y : 0;
@@ -240,7 +275,7 @@ __device__ __noinline__ double response_exact(const Tables &tb, int mcs, size_t 
 }
 
 template <int K>
-__global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const __grid_constant__ StepParams p,
                                                          const __grid_constant__ EmbbState st,
                                                          const __grid_constant__ Tables tb) {
     // small lookup tables: constant-bank reads with divergent indices serialise, shared memory does not
@@ -307,6 +342,7 @@ __global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__
         for (int k = 0; k < n_ues; ++k) {
             UeRec r;
             load_rec(ue + k, r);
+            if (k + 1 < n_ues) prefetch_l1(ue + k + 1);          // next record while this UE's trace window is summed
             int nb_bits;
             if ((r.meta & 1u) == 0) nb_bits = 500;               // CbrSource: 500000 b/s * 1e-3 every slot
             else { nb_bits = vbr_source_step(r, r_vbr, flags); types |= 1u << k; }
@@ -385,6 +421,7 @@ __global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__
                     break;
                 }
                 ++pf_iters;
+                if (RS_EXP & 8) { rbs[0] += n_prbs - r; break; }
                 const int c = min(n_prbs - r, 2);
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 copy, exact when close
                 int idx = 0;
@@ -420,7 +457,7 @@ __global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__
                 float c0 = 0.f, c1 = 0.f, nf = 0.f;
                 double msum = 0.0;
                 const int4 *col4 = nullptr;
-                for (;;) {
+                for (; !(RS_EXP & 4);) {
                     if (left == 0) {
                         if (k >= 0) mavg[k] = (float)(msum / (double)rbs[k]);
                         do { ++k; if (k < n_ues) { lo = o; o += rbs[k]; } } while (k < n_ues && rbs[k] < 2);
@@ -436,7 +473,7 @@ __global__ void __launch_bounds__(128, 4) embb_step_fast(const __grid_constant__
                     }
                     int qq4 = q;
                     while (qq4 >= QUADS_PER_COL) qq4 -= QUADS_PER_COL;
-                    const int4 v = __ldg(col4 + qq4);
+                    const int4 v = LDQ_D(col4 + qq4);
                     const int b = q << 2;
                     float part = 0.f;
                     {
