@@ -142,7 +142,8 @@ class BatchedRanSlice:
         _lib.check(_lib.lib().rs_state_size(self._h, C.byref(n)))
         return int(n.value)
 
-    VARIANT_NAMES = {0: "embb_step_fast (PRB-sorted units, guarded fast math)", 1: "embb_step_unit_thread (all fp64)"}
+    VARIANT_NAMES = {0: "embb_step_smem (PRB-sorted units, UE table in shared memory, guarded fast math)",
+                     1: "embb_step_unit_thread (all fp64)", 2: "embb_step_fast (PRB-sorted units, guarded fast math)"}
 
     def kernel_variant_name(self):
         return self.VARIANT_NAMES.get(self._cfg.kernel_variant, str(self._cfg.kernel_variant))

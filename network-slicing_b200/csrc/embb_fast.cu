@@ -29,27 +29,12 @@
 //    rs_selftest).  Closed form once a single UE is backlogged, early exit when every queue is
 //    drained (the remaining PRBs go to UE 0 with 0 bits, schedulers.py:52 argmax of all-zero).
 #include "embb_device.cuh"
+#include "embb_fastmath.cuh"
 
 namespace rs {
 
 constexpr uint32_t KEY_BINS = SORT_BINS;
 
-// RS_EXP: bit mask of timing experiments (results become wrong; never set in a release build)
-//   1: window-mean trace loads replaced by a constant   2: MI-loop trace loads replaced by a constant
-//   4: skip the MI loop                                   8: skip the contended PF iterations
-#ifndef RS_EXP
-#define RS_EXP 0
-#endif
-#if RS_EXP & 1
-#define LDQ_B(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
-#else
-#define LDQ_B(p) __ldg(p)
-#endif
-#if RS_EXP & 2
-#define LDQ_D(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
-#else
-#define LDQ_D(p) __ldg(p)
-#endif
 #ifndef RS_FAST_MIN_BLOCKS
 #define RS_FAST_MIN_BLOCKS 4      // resident 128-thread blocks per SM the register budget is sized for
 #endif
@@ -62,8 +47,10 @@ __device__ __forceinline__ uint32_t contention_class(uint32_t pf_iters_prev, int
 
 // ---------------------------------------------------------------------------------------------
 // Pre-pass 1: PRB windows of all eMBB units of a step (node_b.py:71-74) + histogram of sort keys.
+// Units whose live-UE count fits the shared-memory kernel (embb_smem.cu) are counting-sorted into the
+// front of perm[]; the others are appended from the back (list L) for the general kernel below.
 __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ StepParams p,
-                                                     const __grid_constant__ EmbbState st) {
+                                                     const __grid_constant__ EmbbState st, const int max_front_ues) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.N) return;
     const int32_t *a = p.action + (size_t)env * p.S;
@@ -76,9 +63,13 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         const int u = env * p.n_embb + s;
         st.win[u] = (uint32_t)off | ((uint32_t)v << 16);
         st.cur_prbs[u] = v;
-        const uint32_t key = ((uint32_t)v << 6) | (contention_class(st.hint[u], p.slots) << 4) |
-                             (uint32_t)min(st.hdr[u].n_ues, 15);
-        atomicAdd(&st.hist[key], 1u);
+        const int n_ues = st.hdr[u].n_ues;
+        if (n_ues <= max_front_ues) {
+            const uint32_t key = ((uint32_t)v << 6) | (contention_class(st.hint[u], p.slots) << 4) | (uint32_t)min(n_ues, 15);
+            atomicAdd(&st.hist[key], 1u);
+        } else {
+            st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
+        }
         off += v;
     }
     if (flags) atomicOr(p.flags_acc + env, flags);
@@ -104,110 +95,20 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Embb
     uint32_t run = s_tot[threadIdx.x] - sum;
 #pragma unroll
     for (int i = 0; i < PER; ++i) { st.hist[KEY_BINS + base + PER - 1 - i] = run; run += loc[i]; }
+    if (threadIdx.x == 1023) st.hist[2 * KEY_BINS + 0] = s_tot[1023];        // size of the sorted front list
 }
 
 // Pre-pass 3: scatter.
 __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ StepParams p,
-                                                      const __grid_constant__ EmbbState st) {
+                                                      const __grid_constant__ EmbbState st, const int max_front_ues) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
+    if (st.hdr[u].n_ues > max_front_ues) return;
     const uint32_t key = ((st.win[u] >> 16) << 6) | (contention_class(st.hint[u], p.slots) << 4) |
                          (uint32_t)min(st.hdr[u].n_ues, 15);
     const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], 1u);
     st.perm[pos] = u;
 }
-
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ void atomic_max_float(float *addr, float v) {   // v >= 0
-    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
-}
-
-__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
-
-constexpr float Q24_SCALE = 1.0f / 16777216.0f;
-constexpr float LOG2E_F = 1.4426950408889634f;
-constexpr int QUADS_PER_COL = TRACE_ROWS / 4;                // 25: quads never straddle the row wrap
-
-// (b * bits) / slot_length, exactly rounded: q = RN(y * 1000), r = y - q * 1e-3 (exact, FMA),
-// q' = RN(q + r * 1000).  rs_selftest checks q' == y / 1e-3 for every bits in the domain.
-__device__ __forceinline__ double b_bits_over_slot(int bits) {
-    const double y = __dmul_rn(PF_B, (double)bits);
-    const double q = __dmul_rn(y, 1000.0);
-    const double r = __fma_rn(-q, SLOT_LEN, y);
-    return __fma_rn(r, 1000.0, q);
-}
-
-// Exact integer sum of the window [row0, row0 + n) of one trace column; aligned quads, end quads masked.
-__device__ __forceinline__ long long window_sum_q24(const int32_t *col, int row0, int n) {
-    const int4 *col4 = reinterpret_cast<const int4 *>(col);
-    const int lo = row0, hi = row0 + n;                      // absolute rows, may run past 100 (wrap)
-    int q = lo >> 2;
-    const int q_last = (hi - 1) >> 2;
-    long long sum = 0;
-    {   // first quad (masked below lo and at/after hi)
-        const int qq = q >= QUADS_PER_COL ? q - QUADS_PER_COL : q;
-        const int4 v = LDQ_B(col4 + qq);
-        const int b = q << 2;
-        sum += (b + 0 >= lo && b + 0 < hi) ? v.x : 0;
-        sum += (b + 1 >= lo && b + 1 < hi) ? v.y : 0;
-        sum += (b + 2 >= lo && b + 2 < hi) ? v.z : 0;
-        sum += (b + 3 >= lo && b + 3 < hi) ? v.w : 0;
-        ++q;
-    }
-    int qq = q;
-    while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
-    for (; q + 4 <= q_last; q += 4) {                        // interior quads, 4 independent loads in flight
-        int i0 = qq, i1 = qq + 1, i2 = qq + 2, i3 = qq + 3;
-        if (i1 >= QUADS_PER_COL) i1 -= QUADS_PER_COL;
-        if (i2 >= QUADS_PER_COL) i2 -= QUADS_PER_COL;
-        if (i3 >= QUADS_PER_COL) i3 -= QUADS_PER_COL;
-        const int4 v0 = LDQ_B(col4 + i0), v1 = LDQ_B(col4 + i1), v2 = LDQ_B(col4 + i2), v3 = LDQ_B(col4 + i3);
-        sum += ((long long)v0.x + (long long)v0.y + (long long)v0.z + (long long)v0.w) +
-               ((long long)v1.x + (long long)v1.y + (long long)v1.z + (long long)v1.w) +
-               ((long long)v2.x + (long long)v2.y + (long long)v2.z + (long long)v2.w) +
-               ((long long)v3.x + (long long)v3.y + (long long)v3.z + (long long)v3.w);
-        qq += 4;
-        if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
-    }
-    for (; q < q_last; ++q) {                                // remaining interior quads: no masks
-        const int4 v = LDQ_B(col4 + qq);
-        sum += (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
-        qq = (qq + 1 == QUADS_PER_COL) ? 0 : qq + 1;
-    }
-    if (q == q_last) {                                       // last quad (masked at/after hi)
-        const int4 v = LDQ_B(col4 + qq);
-        const int b = q << 2;
-        sum += (b + 0 < hi) ? v.x : 0;
-        sum += (b + 1 < hi) ? v.y : 0;
-        sum += (b + 2 < hi) ? v.z : 0;
-        sum += (b + 3 < hi) ? v.w : 0;
-    }
-    return sum;
-}
-
-// exact fp64 window mean (same operation order as embb_step.cu); rare
-__device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
-    double sum = 0.0;
-    int row = row0;
-    for (int j = 0; j < n; ++j) {
-        sum += col[row] + nominal;
-        row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
-    }
-    return sum / (double)n;
-}
-
-// State a rare-event call may change; copied in/out around the call so that the hot loop keeps it in registers.
-struct RanCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
 
 // Rare RAN events of a slot, exactly in the reference's order (slice_ran.py:263-268, slice_l1.py:196-198):
 // cbr_arrivals (+CAC), vbr_arrivals, departures, extract_users, add_users -> insert_user.
@@ -269,15 +170,10 @@ __device__ __noinline__ void ran_events(const StepParams &p, const EmbbState &st
     c.n_ues = n_ues; c.cbr_next = cbr_next; c.vbr_next = vbr_next; c.next_dep = next_dep; c.flags = flags;
 }
 
-// exact reception probability (reference fp64 path); rare
-__device__ __noinline__ double response_exact(const Tables &tb, int mcs, size_t col_off, int row0, int n, double nominal) {
-    return response_fp64(tb, mcs, tb.trace + col_off, row0, n, nominal);
-}
-
 template <int K>
 __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const __grid_constant__ StepParams p,
                                                          const __grid_constant__ EmbbState st,
-                                                         const __grid_constant__ Tables tb) {
+                                                         const __grid_constant__ Tables tb, const int back_list) {
     // small lookup tables: constant-bank reads with divergent indices serialise, shared memory does not
     __shared__ int16_t s_rate[256];
     __shared__ int8_t s_mcs[256];
@@ -288,9 +184,10 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     __syncthreads();
 
     const int tix = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < st.U);
-    if (tix >= st.U) return;
-    const int u = st.perm[tix];
+    const int count = (int)st.hist[2 * KEY_BINS + back_list];           // front (sorted) list or back list L
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
+    if (tix >= count) return;
+    const int u = st.perm[back_list ? 2 * st.U - 1 - tix : tix];
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
     unpack_window(st.win[u], i_prb, n_prbs);
@@ -601,14 +498,24 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
     embb_reset_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(st);
 }
 
-int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    cudaMemsetAsync(st.hist, 0, 2 * KEY_BINS * sizeof(uint32_t), stream);
-    window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st);
+void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, cudaStream_t stream) {
+    cudaMemsetAsync(st.hist, 0, (2 * KEY_BINS + 4) * sizeof(uint32_t), stream);
+    window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues);
     scan_kernel<<<1, 1024, 0, stream>>>(st);
-    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st);
+    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues);
+}
+
+// general kernel over the front list (back_list = 0) or over list L (back_list = 1)
+void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream) {
     const int threads = 128, blocks = (st.U + threads - 1) / threads;
-    if (st.K <= 16) embb_step_fast<16><<<blocks, threads, 0, stream>>>(p, st, tb);
-    else embb_step_fast<32><<<blocks, threads, 0, stream>>>(p, st, tb);
+    if (st.K <= 16) embb_step_fast<16><<<blocks, threads, 0, stream>>>(p, st, tb, back_list);
+    else embb_step_fast<32><<<blocks, threads, 0, stream>>>(p, st, tb, back_list);
+}
+
+// variant 2: every unit through the general kernel, sorted
+int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
+    launch_embb_sort(p, st, 1 << 30, stream);
+    launch_embb_general(p, st, tb, 0, stream);
     return 4;   // kernels launched
 }
 

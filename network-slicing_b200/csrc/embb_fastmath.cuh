@@ -1,0 +1,121 @@
+// Guarded fast-math building blocks shared by the default eMBB kernels (embb_smem.cu, embb_fast.cu).
+#pragma once
+#include "embb_device.cuh"
+
+namespace rs {
+
+// RS_EXP: bit mask of timing experiments (results become wrong; never set in a release build)
+//   1: window-mean trace loads replaced by a constant   2: MI-loop trace loads replaced by a constant
+//   4: skip the MI loop                                   8: skip the contended PF iterations
+#ifndef RS_EXP
+#define RS_EXP 0
+#endif
+#if RS_EXP & 1
+#define LDQ_B(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
+#else
+#define LDQ_B(p) __ldg(p)
+#endif
+#if RS_EXP & 2
+#define LDQ_D(p) make_int4(1 << 24, 2 << 24, 3 << 24, 4 << 24)
+#else
+#define LDQ_D(p) __ldg(p)
+#endif
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void atomic_max_float(float *addr, float v) {   // v >= 0
+    atomicMax(reinterpret_cast<int *>(addr), __float_as_int(v));
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+constexpr float Q24_SCALE = 1.0f / 16777216.0f;
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr int QUADS_PER_COL = TRACE_ROWS / 4;                // 25: quads never straddle the row wrap
+
+// (b * bits) / slot_length, exactly rounded: q = RN(y * 1000), r = y - q * 1e-3 (exact, FMA),
+// q' = RN(q + r * 1000).  rs_selftest checks q' == y / 1e-3 for every bits in the domain.
+__device__ __forceinline__ double b_bits_over_slot(int bits) {
+    const double y = __dmul_rn(PF_B, (double)bits);
+    const double q = __dmul_rn(y, 1000.0);
+    const double r = __fma_rn(-q, SLOT_LEN, y);
+    return __fma_rn(r, 1000.0, q);
+}
+
+// Exact integer sum of the window [row0, row0 + n) of one trace column; aligned quads, end quads masked.
+__device__ __forceinline__ long long window_sum_q24(const int32_t *col, int row0, int n) {
+    const int4 *col4 = reinterpret_cast<const int4 *>(col);
+    const int lo = row0, hi = row0 + n;                      // absolute rows, may run past 100 (wrap)
+    int q = lo >> 2;
+    const int q_last = (hi - 1) >> 2;
+    long long sum = 0;
+    {   // first quad (masked below lo and at/after hi)
+        const int qq = q >= QUADS_PER_COL ? q - QUADS_PER_COL : q;
+        const int4 v = LDQ_B(col4 + qq);
+        const int b = q << 2;
+        sum += (b + 0 >= lo && b + 0 < hi) ? v.x : 0;
+        sum += (b + 1 >= lo && b + 1 < hi) ? v.y : 0;
+        sum += (b + 2 >= lo && b + 2 < hi) ? v.z : 0;
+        sum += (b + 3 >= lo && b + 3 < hi) ? v.w : 0;
+        ++q;
+    }
+    int qq = q;
+    while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    for (; q + 4 <= q_last; q += 4) {                        // interior quads, 4 independent loads in flight
+        int i0 = qq, i1 = qq + 1, i2 = qq + 2, i3 = qq + 3;
+        if (i1 >= QUADS_PER_COL) i1 -= QUADS_PER_COL;
+        if (i2 >= QUADS_PER_COL) i2 -= QUADS_PER_COL;
+        if (i3 >= QUADS_PER_COL) i3 -= QUADS_PER_COL;
+        const int4 v0 = LDQ_B(col4 + i0), v1 = LDQ_B(col4 + i1), v2 = LDQ_B(col4 + i2), v3 = LDQ_B(col4 + i3);
+        sum += ((long long)v0.x + (long long)v0.y + (long long)v0.z + (long long)v0.w) +
+               ((long long)v1.x + (long long)v1.y + (long long)v1.z + (long long)v1.w) +
+               ((long long)v2.x + (long long)v2.y + (long long)v2.z + (long long)v2.w) +
+               ((long long)v3.x + (long long)v3.y + (long long)v3.z + (long long)v3.w);
+        qq += 4;
+        if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    }
+    for (; q < q_last; ++q) {                                // remaining interior quads: no masks
+        const int4 v = LDQ_B(col4 + qq);
+        sum += (long long)v.x + (long long)v.y + (long long)v.z + (long long)v.w;
+        qq = (qq + 1 == QUADS_PER_COL) ? 0 : qq + 1;
+    }
+    if (q == q_last) {                                       // last quad (masked at/after hi)
+        const int4 v = LDQ_B(col4 + qq);
+        const int b = q << 2;
+        sum += (b + 0 < hi) ? v.x : 0;
+        sum += (b + 1 < hi) ? v.y : 0;
+        sum += (b + 2 < hi) ? v.z : 0;
+        sum += (b + 3 < hi) ? v.w : 0;
+    }
+    return sum;
+}
+
+// exact fp64 window mean (same operation order as embb_step.cu); rare
+static __device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
+    double sum = 0.0;
+    int row = row0;
+    for (int j = 0; j < n; ++j) {
+        sum += col[row] + nominal;
+        row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
+    }
+    return sum / (double)n;
+}
+
+// exact reception probability (reference fp64 path); rare
+static __device__ __noinline__ double response_exact(const Tables &tb, int mcs, size_t col_off, int row0, int n, double nominal) {
+    return response_fp64(tb, mcs, tb.trace + col_off, row0, n, nominal);
+}
+
+
+// State a rare-event call may change; copied in/out around the call so that the hot loop keeps it in registers.
+struct RanCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
+
+}  // namespace rs

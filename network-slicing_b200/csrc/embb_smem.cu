@@ -1,0 +1,513 @@
+// K1 default variant: the unit's UE table stays in SHARED MEMORY for the whole observation period.
+//
+// Same algorithm, same guarded fast math and same PRB-sorted thread->unit mapping as embb_fast.cu
+// (which remains the general kernel).  What changes is where the state lives during the 50 TTIs:
+// the general kernel re-reads and re-writes every 64-byte UE record in global memory each TTI and
+// keeps its per-TTI PF scratch in local memory; both go through L1, which is far too small for
+// 512 threads x (records + scratch + fading-trace lines) and is write-through (measured: 10.7 GB of
+// L2 writes per launch, ~2000 cycles average wait per L1-missing load).  Here each thread loads its
+// unit's records once, keeps them as conflict-free SoA words smem[(slot, word)][thread], runs the 50
+// TTIs out of shared memory, and writes the records back once.  L1 then only serves the trace lines.
+//
+// Capacity: KS = 8 slots of 17 words per thread (68 KB per 128-thread block, 3 blocks per SM).  Units
+// with more than KS - 2 live UEs at the start of the step go to the general kernel (list L of the
+// sort pre-pass); a unit that outgrows its slots during the step (or whose queue no longer fits 31
+// bits) ABORTS before writing anything and is appended to list L, i.e. it is replayed from its
+// untouched state by the general kernel.  Results are therefore independent of the routing.
+#include "embb_device.cuh"
+#include "embb_fastmath.cuh"
+
+namespace rs {
+
+constexpr int SM_THREADS = 128;
+constexpr int SM_KS = 8;          // UE slots per thread held in shared memory
+constexpr int SM_WORDS = 17;      // 32-bit words per slot
+constexpr int SM_MAX_START_UES = SM_KS - 2;
+constexpr int QUEUE_LIMIT = 1 << 30;
+
+// word offsets inside a slot (64-bit fields first so that they are 8-byte aligned in their own planes)
+struct SmemView {
+    double *th;        // [KS][T] ue.th
+    double *thpf;      // [KS][T] scheduler's working copy of max(th, 1)   (schedulers.py:40)
+    double *nominal;   // [KS][T]
+    int *queue;        // [KS][T] ue.queue (bits, < 2^30 or the unit aborts)
+    uint32_t *meta;    // [KS][T]
+    uint32_t *dep;     // [KS][T]
+    int *vnext;        // [KS][T]
+    int *bits;         // [KS][T] ue.bits; doubles as the scheduler's ue_bits while a TTI is scheduled
+    int *pe;           // [KS][T] ue.prbs (bits 0-7) | ue.e_snr << 16; prbs doubles as ue_rbs
+    uint32_t *rm;      // [KS][T] rate (low 16) | mcs << 16 of this TTI
+    uint32_t *togo;    // [4][KS][T] 8 x int16 burst countdowns
+};
+
+__device__ __forceinline__ SmemView carve_smem(unsigned char *base) {
+    SmemView v;
+    constexpr int P = SM_KS * SM_THREADS;      // elements per plane
+    v.th = reinterpret_cast<double *>(base);
+    v.thpf = v.th + P;
+    v.nominal = v.thpf + P;
+    v.queue = reinterpret_cast<int *>(v.nominal + P);
+    v.meta = reinterpret_cast<uint32_t *>(v.queue + P);
+    v.dep = v.meta + P;
+    v.vnext = reinterpret_cast<int *>(v.dep + P);
+    v.bits = v.vnext + P;
+    v.pe = v.bits + P;
+    v.rm = reinterpret_cast<uint32_t *>(v.pe + P);
+    v.togo = v.rm + P;
+    return v;
+}
+static_assert(SM_WORDS == 3 * 2 + 7 + 4, "slot word budget");
+
+#define SIX(k) ((k) * SM_THREADS + tid)
+
+__device__ __forceinline__ void smem_move_slot(const SmemView &v, int tid, int from, int to) {
+    v.th[SIX(to)] = v.th[SIX(from)]; v.nominal[SIX(to)] = v.nominal[SIX(from)];
+    v.queue[SIX(to)] = v.queue[SIX(from)]; v.meta[SIX(to)] = v.meta[SIX(from)]; v.dep[SIX(to)] = v.dep[SIX(from)];
+    v.vnext[SIX(to)] = v.vnext[SIX(from)]; v.bits[SIX(to)] = v.bits[SIX(from)]; v.pe[SIX(to)] = v.pe[SIX(from)];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + to) * SM_THREADS + tid] = v.togo[(j * SM_KS + from) * SM_THREADS + tid];
+}
+
+// Rare RAN events of a slot on the shared-memory table; same order as ran_events in embb_fast.cu
+// (slice_ran.py:263-268, slice_l1.py:196-198).  Sets c.flags bit 31 when the unit must abort.
+__device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, int tid, uint32_t k0, uint32_t k1,
+                                             uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, RanCtx &c) {
+    struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran}, {k0, k1, s, STREAM_CHAN, c.c_chan},
+                                                {k0, k1, s, STREAM_VBR, c.c_vbr}};
+    int n_ues = c.n_ues, cbr_next = c.cbr_next, vbr_next = c.vbr_next;
+    uint32_t next_dep = c.next_dep, flags = c.flags;
+    int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
+    if (cbr_next == 0) {                                                          // slice_ran.py:205-227
+        cbr_next = exp_slots_ms(rng.ran, 1.0 / (2.0 / 60.0));
+        const double cbr_prb = (double)a_prb0 / (double)t;                        // cbr_cac, :195-203
+        const double cbr_th = (double)a_th0 / ((double)t * 1e-3);
+        if (!(cbr_prb >= 20.0 || cbr_th >= 10e6)) {
+            arr_type[n_arr] = 0; arr_vnext[n_arr] = 0;
+            arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
+        }
+    } else cbr_next -= 1;
+    if (vbr_next == 0) {                                                          // :229-249
+        arr_type[n_arr] = 1;
+        arr_vnext[n_arr] = exp_slots(rng.vbr, (1.0 / 1) / 1e-3);                  // VbrSource.__init__, traffic_generators.py:65-66
+        arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
+        vbr_next = exp_slots_ms(rng.ran, 1.0 / (5.0 / 60.0));
+    } else vbr_next -= 1;
+    if (clock == next_dep) {                                                      // departures, :251-261 (order kept)
+        int w = 0;
+        uint32_t nd = DEP_NEVER;
+        for (int k = 0; k < n_ues; ++k) {
+            const uint32_t d = v.dep[SIX(k)];
+            if (d != clock) {
+                if (w != k) smem_move_slot(v, tid, k, w);
+                nd = min(nd, d);
+                ++w;
+            }
+        }
+        n_ues = w;
+        next_dep = nd;
+    }
+    for (int a = 0; a < n_arr; ++a) {                                             // slice_l1.py:183-186
+        const int rem = arr_rem[a] - 1;                          // this slot's departures() already ticked it
+        if (rem == 0) { flags |= 8u; continue; }
+        if (n_ues >= SM_KS) { flags |= 0x80000000u; break; }     // out of slots: replay in the general kernel
+        const int fading = (int)rng.chan.integers(3);                             // channel_models.py:163-169
+        const int index = (int)rng.chan.integers(N_SAMPLES);
+        const int step = rng.chan.integers(2) ? 1 : -1;
+        const int k = n_ues;
+        v.nominal[SIX(k)] = draw_nominal_sinr(rng.chan, p.prop_A, p.prop_B);
+        v.meta[SIX(k)] = pack_meta(arr_type[a], fading, step, index);
+        const uint32_t dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem;
+        v.dep[SIX(k)] = dep_at;
+        v.vnext[SIX(k)] = arr_vnext[a]; v.bits[SIX(k)] = 0; v.th[SIX(k)] = 0.0; v.queue[SIX(k)] = 0; v.pe[SIX(k)] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = 0u;
+        next_dep = min(next_dep, dep_at);
+        ++n_ues;
+    }
+    c.c_ran = rng.ran.n; c.c_chan = rng.chan.n; c.c_vbr = rng.vbr.n;
+    c.n_ues = n_ues; c.cbr_next = cbr_next; c.vbr_next = vbr_next; c.next_dep = next_dep; c.flags = flags;
+}
+
+// VbrSource.step on the packed burst words of slot k (same semantics as vbr_source_step in embb_device.cuh)
+__device__ __forceinline__ int vbr_step_smem(const SmemView &v, int tid, int k, PhiloxStream &r_vbr, uint32_t &flags) {
+    uint32_t w[4];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { w[j] = v.togo[(j * SM_KS + k) * SM_THREADS + tid]; any |= w[j] != 0u; }
+    int bits = 0;
+    bool dirty = false;
+    if (any) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int lo = (int)(int16_t)(w[j] & 0xFFFFu), hi = (int)(int16_t)(w[j] >> 16);
+            if (lo != 0) { lo = max(lo - 1, -32768); bits += lo != 0 ? 1000 : 0; }
+            if (hi != 0) { hi = max(hi - 1, -32768); bits += hi != 0 ? 1000 : 0; }
+            w[j] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+        }
+        dirty = true;
+    }
+    const int vn = v.vnext[SIX(k)] - 1;
+    if (vn == 0) {                                               // burst arrival (traffic_generators.py:92-97)
+        int len = exp_slots(r_vbr, 500.0);
+        if (len == 0) len = -1;                                  // never ends
+        bool placed = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!placed && (w[j] & 0xFFFFu) == 0u) { w[j] |= (uint32_t)len & 0xFFFFu; placed = true; }
+            if (!placed && (w[j] >> 16) == 0u) { w[j] |= (uint32_t)len << 16; placed = true; }
+        }
+        if (!placed) flags |= 2u;
+        dirty = true;
+        v.vnext[SIX(k)] = exp_slots(r_vbr, 1000.0);
+    } else v.vnext[SIX(k)] = vn;
+    if (dirty) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = w[j];
+    }
+    return bits;
+}
+
+// x / n for a small positive integer count n: skip the division for n == 1 (the common case)
+__device__ __forceinline__ double div_count(double x, int n) { return n <= 1 ? x : x / (double)n; }
+
+__global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_constant__ StepParams p,
+                                                                const __grid_constant__ EmbbState st,
+                                                                const __grid_constant__ Tables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int16_t s_rate[256];
+    __shared__ int8_t s_mcs[256];
+    __shared__ float s_ref[26];
+    __shared__ int8_t s_mod[26];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += SM_THREADS) { s_rate[i] = tb.lut_rate[i]; s_mcs[i] = tb.lut_mcs[i]; }
+    if (tid < 26) { s_ref[tid] = (float)tb.snr_ref[tid]; s_mod[tid] = tb.mod[tid]; }
+    __syncthreads();
+    const SmemView v = carve_smem(smem_raw);
+
+    const int tix = blockIdx.x * SM_THREADS + tid;
+    const int count = (int)st.hist[2 * SORT_BINS + 0];
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
+    if (tix >= count) return;
+    const int u = st.perm[tix];
+    const int env = u / p.n_embb, s = u - env * p.n_embb;
+    int i_prb, n_prbs;
+    unpack_window(st.win[u], i_prb, n_prbs);
+    const int row_base = i_prb % TRACE_ROWS;
+    uint32_t flags = 0;
+
+    UnitHdr hdr = st.hdr[u];
+    UeRec *ue = st.ue + (size_t)u * st.K;
+    const uint64_t seed = p.seed0 + (uint64_t)env;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c_ran = hdr.ctr[0];
+    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1]}, r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2]},
+        r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
+
+    int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
+    uint32_t clock = hdr.clock, next_dep = DEP_NEVER;
+    bool dead = false;                                           // aborted: replayed by the general kernel
+
+    // ---- gather the unit's records into shared memory (once per step)
+    for (int k = 0; k < n_ues; ++k) {
+        UeRec r;
+        load_rec(ue + k, r);
+        v.th[SIX(k)] = r.th; v.nominal[SIX(k)] = r.nominal;
+        v.queue[SIX(k)] = (int)r.queue; v.meta[SIX(k)] = r.meta; v.dep[SIX(k)] = r.dep_at; v.vnext[SIX(k)] = r.vnext;
+        v.bits[SIX(k)] = r.bits; v.pe[SIX(k)] = r.pe;
+        const uint32_t *tg = reinterpret_cast<const uint32_t *>(r.togo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = tg[j];
+        next_dep = min(next_dep, r.dep_at);
+        dead |= r.queue >= QUEUE_LIMIT;
+    }
+    if (dead) n_ues = 0;
+
+    int a_traffic[2] = {0, 0}, a_th[2] = {0, 0}, a_prb[2] = {0, 0};     // slice_ran.py:270-273 reset_info
+    double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
+    unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
+    const float Af = (float)tb.A, Bf = (float)tb.B;
+    const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * 16777216.0) : 0.0;
+
+    for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
+        __syncwarp(warp_mask);
+        ++clock;
+        // ================= slice_ran.slot(): arrivals / departures only on event slots
+        if (!dead) {
+            if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
+                RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
+                ran_events_smem(p, v, tid, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], c);
+                c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
+                n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
+                if (flags & 0x80000000u) { dead = true; n_ues = 0; }
+            } else { cbr_next -= 1; vbr_next -= 1; }
+        }
+
+        // ================= per-UE traffic + SNR estimate (slice_l1.py:200-213)
+        __syncwarp(warp_mask);
+        int n_backlog = 0;
+        int sn[2] = {0, 0}, cnt[2] = {0, 0};
+        long long qsum[2] = {0, 0};
+        for (int k = 0; k < n_ues; ++k) {
+            uint32_t meta = v.meta[SIX(k)];
+            const int ty = (int)(meta & 1u);
+            const int nb_bits = ty == 0 ? 500 : vbr_step_smem(v, tid, k, r_vbr, flags);   // CbrSource: 500 bits every slot
+            a_traffic[ty] += nb_bits;
+            const int queue = v.queue[SIX(k)] + nb_bits;
+            v.queue[SIX(k)] = queue;
+            if (queue >= QUEUE_LIMIT) dead = true;
+            int pe = v.pe[SIX(k)];
+            if (n_prbs > 0) {
+                int index = (int)(meta >> 4), step = (meta & 8u) ? 1 : -1;
+                const int fading = (int)((meta >> 1) & 3u);
+                walk_trace(r_chan, index, step);                 // channel_models.py:171-191
+                meta = pack_meta(ty, fading, step, index);
+                v.meta[SIX(k)] = meta;
+                const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
+                const long long isum = window_sum_q24(tb.trace_q24 + col_off, row_base, n_prbs);
+                trace_elems += (unsigned)n_prbs;
+                const double nominal = v.nominal[SIX(k)];
+                double mean = (double)isum * inv_n + nominal;    // |mean - reference mean| < 2^-25 + few ulp
+                const double fr = mean - floor(mean);
+                const bool near = fabs(fr - 0.5) < 1e-6;         // within the guard of a rounding boundary
+                if (near || p.debug_check) {
+                    const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, nominal);
+                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / 1e-6));
+                    if (near) { mean = exact; ++slow_snr; }
+                }
+                const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
+                pe = (pe & 0xFFFF) | (e_snr << 16);
+                v.pe[SIX(k)] = pe;
+            }
+            // scheduler inputs (schedulers.py:37-45) + the update_info terms that are already final
+            const int e = min(max(pe >> 16, -128), 127) + 128;
+            v.rm[SIX(k)] = (uint32_t)(uint16_t)s_rate[e] | ((uint32_t)(uint8_t)s_mcs[e] << 16);
+            const double th = v.th[SIX(k)];
+            v.thpf[SIX(k)] = th > 1.0 ? th : 1.0;
+            n_backlog += queue > 0;
+            sn[ty] += pe >> 16;
+            cnt[ty] += 1;
+        }
+        if (dead) n_ues = 0;
+        // ================= scheduling + reception (slice_l1.py:215-224)
+        __syncwarp(warp_mask);
+        const bool scheduled = n_backlog > 0 && n_prbs > 0;      // queued_data > 0 <=> some queue > 0
+        const unsigned sched_mask = __ballot_sync(warp_mask, scheduled);
+        if (scheduled) {
+            for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= 0xFFFF0000; }   // ue_bits, ue_rbs
+            // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
+            int r = 0;
+            while (r < n_prbs) {
+                if (n_backlog == 0) { v.pe[SIX(0)] += n_prbs - r; break; }  // all metrics 0 -> argmax 0, tx 0
+                if (n_backlog == 1) {                                       // no competition: closed form
+                    int j = 0;
+                    while (v.queue[SIX(j)] - v.bits[SIX(j)] <= 0) ++j;
+                    const int left = n_prbs - r, full = left >> 1;
+                    const int rate = (int)(v.rm[SIX(j)] & 0xFFFFu), cap2 = 2 * rate;
+                    const int q32 = v.queue[SIX(j)] - v.bits[SIX(j)];
+                    if ((long long)q32 <= (long long)full * cap2) {         // drained within the 2-PRB chunks
+                        const int need = (q32 + cap2 - 1) / cap2;
+                        v.pe[SIX(j)] += 2 * need; v.bits[SIX(j)] += q32; r += 2 * need;
+                        n_backlog = 0;
+                        continue;
+                    }
+                    int tx = full * cap2;
+                    if (left & 1) tx += min(rate, q32 - tx);                // last, single-PRB chunk
+                    v.pe[SIX(j)] += left; v.bits[SIX(j)] += tx;
+                    break;
+                }
+                ++pf_iters;
+                if (RS_EXP & 8) { v.pe[SIX(0)] += n_prbs - r; break; }
+                const int c = min(n_prbs - r, 2);
+                // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 metric, exact when close
+                int idx = 0;
+                float best = -1.0f, second = -1.0f;
+                for (int k = 0; k < n_ues; ++k) {
+                    const bool has = v.queue[SIX(k)] - v.bits[SIX(k)] > 0;
+                    const float m = has ? (float)(v.rm[SIX(k)] & 0xFFFFu) * rcp_approx((float)v.thpf[SIX(k)]) : 0.0f;
+                    if (m > best) { second = best; best = m; idx = k; }
+                    else second = fmaxf(second, m);
+                }
+                if (second >= best * (1.0f - 1e-6f)) {                      // too close for fp32: exact quotients
+                    const float lim = best * (1.0f - 1e-6f);
+                    double best64 = -1.0;
+                    for (int k = 0; k < n_ues; ++k) {
+                        if (v.queue[SIX(k)] - v.bits[SIX(k)] <= 0) continue;
+                        const double thk = v.thpf[SIX(k)];
+                        const float rate_f = (float)(v.rm[SIX(k)] & 0xFFFFu);
+                        if (rate_f * rcp_approx((float)thk) >= lim) {
+                            const double m64 = (double)(v.rm[SIX(k)] & 0xFFFFu) / thk;
+                            if (m64 > best64) { best64 = m64; idx = k; }
+                        }
+                    }
+                }
+                const int rate = (int)(v.rm[SIX(idx)] & 0xFFFFu);
+                const int left_q = v.queue[SIX(idx)] - v.bits[SIX(idx)];
+                const int tx = min(c * rate, left_q);
+                const int nbits = v.bits[SIX(idx)] + tx;
+                v.bits[SIX(idx)] = nbits;
+                v.pe[SIX(idx)] += c;
+                v.thpf[SIX(idx)] = __dadd_rn(__dmul_rn(PF_A, v.thpf[SIX(idx)]), b_bits_over_slot(nbits));
+                if (left_q - tx <= 0) --n_backlog;
+                r += 2;
+            }
+            // ---- MI sums of the served sub-bands, flattened over (UE, quad): ~n_prbs/4 iterations per lane
+            __syncwarp(sched_mask);
+            {
+                int k = -1, left = 0, q = 0, lo = 0, hi = 0, o = row_base, rbs_k = 0;
+                float c0 = 0.f, c1 = 0.f, nf = 0.f;
+                double msum = 0.0;
+                const int4 *col4 = nullptr;
+                for (; !(RS_EXP & 4);) {
+                    if (left == 0) {
+                        if (k >= 0) v.thpf[SIX(k)] = msum / (double)rbs_k;   // mean MI; the PF copy of th is dead by now
+                        do { ++k; if (k < n_ues) { rbs_k = v.pe[SIX(k)] & 0xFF; lo = o; o += rbs_k; } } while (k < n_ues && rbs_k < 2);
+                        if (k >= n_ues) break;
+                        hi = lo + rbs_k;
+                        q = lo >> 2;
+                        left = ((hi - 1) >> 2) - q + 1;
+                        const uint32_t meta = v.meta[SIX(k)];
+                        const int m = s_mod[v.rm[SIX(k)] >> 16];
+                        const float kf = (float)c_MI_K[m], x0f = (float)c_MI_X0[m];
+                        c1 = -kf * LOG2E_F; c0 = kf * x0f * LOG2E_F; nf = (float)v.nominal[SIX(k)];
+                        col4 = reinterpret_cast<const int4 *>(tb.trace_q24 + ((int)((meta >> 1) & 3u) * N_SAMPLES + (int)(meta >> 4)) * TRACE_ROWS);
+                        msum = 0.0;
+                    }
+                    int qq4 = q;
+                    while (qq4 >= QUADS_PER_COL) qq4 -= QUADS_PER_COL;
+                    const int4 x = LDQ_D(col4 + qq4);
+                    const int b = q << 2;
+                    const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, Q24_SCALE, nf), c1, c0));
+                    const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, Q24_SCALE, nf), c1, c0));
+                    const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, Q24_SCALE, nf), c1, c0));
+                    const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.w, Q24_SCALE, nf), c1, c0));
+                    float part = (b + 0 >= lo && b + 0 < hi) ? rcp_approx(1.0f + e0) : 0.f;
+                    part += (b + 1 >= lo && b + 1 < hi) ? rcp_approx(1.0f + e1) : 0.f;
+                    part += (b + 2 >= lo && b + 2 < hi) ? rcp_approx(1.0f + e2) : 0.f;
+                    part += (b + 3 >= lo && b + 3 < hi) ? rcp_approx(1.0f + e3) : 0.f;
+                    msum += (double)part;
+                    ++q; --left;
+                }
+            }
+            // ---- per-UE reception (schedulers.py:66-76, slice_l1.py:219-224) + transmission_step (slice_ran.py:51-55)
+            __syncwarp(sched_mask);
+            int o = 0;
+            for (int k = 0; k < n_ues; ++k) {
+                {
+                    const int pe = v.pe[SIX(k)];
+                    const int prbs = pe & 0xFF;
+                    int b = v.bits[SIX(k)];
+                    const int ty = (int)(v.meta[SIX(k)] & 1u);
+                    if (prbs) {
+                        const int mcs = (int)(v.rm[SIX(k)] >> 16);
+                        const double u01 = r_rx.u01();
+                        trace_elems += (unsigned)prbs;
+                        bool received = false, need_exact = false;
+                        float dbg_p32 = -1.f, dbg_eps = 0.f;
+                        if (prbs == 1) need_exact = true;                    // single RB: no MI averaging, one fp64 sigmoid
+                        else {
+                            const float m = (float)v.thpf[SIX(k)];
+                            if (m >= 1.0f - 1e-4f) received = true;          // p == 1.0 exactly in fp64
+                            else if (m <= 1e-4f) received = false;           // p < 2^-53
+                            else {
+                                const int md = s_mod[mcs];
+                                const float kf = (float)c_MI_K[md], x0f = (float)c_MI_X0[md];
+                                const float rr = rcp_approx(m) - 1.0f;
+                                const float seff = x0f - __logf(rr) / kf;   // inv_sigmoid, channel_models.py:39-41
+                                const float L = Af * (seff - s_ref[mcs]) - Bf;
+                                const float p32 = rcp_approx(1.0f + __expf(-L));
+                                const float epsL = 2e-5f / (kf * m * (1.0f - m)) + 4e-5f;   // 8 dm / (k m (1-m)), dm <= 2.5e-6
+                                const float eps = 1.1f * p32 * (1.0f - p32) * epsL + 5e-7f;
+                                const double d = u01 - (double)p32;
+                                received = d < 0.0;
+                                need_exact = fabs(d) <= (double)eps;
+                                dbg_p32 = p32; dbg_eps = eps;
+                            }
+                        }
+                        if (need_exact || p.debug_check) {
+                            const uint32_t meta = v.meta[SIX(k)];
+                            const size_t col_off = (size_t)((int)((meta >> 1) & 3u) * N_SAMPLES + (int)(meta >> 4)) * TRACE_ROWS;
+                            const double pr = response_exact(tb, mcs, col_off, (row_base + o) % TRACE_ROWS, prbs, v.nominal[SIX(k)]);
+                            const bool exact = u01 < pr;
+                            if (p.debug_check && !need_exact) {
+                                if (dbg_p32 >= 0.f) atomic_max_float(st.dbg + 0, (float)(fabs(pr - (double)dbg_p32) / (double)dbg_eps));
+                                if (exact != received) atomicAdd(reinterpret_cast<unsigned *>(st.dbg + 2), 1u);
+                            }
+                            if (need_exact) { received = exact; slow_rx += prbs > 1; }
+                        }
+                        if (!received) b = 0;
+                    } else b = 0;
+                    o += prbs;
+                    const int queue = v.queue[SIX(k)] - b;       // max(queue - bits, 0): bits never exceed the queue
+                    v.queue[SIX(k)] = queue;
+                    v.th[SIX(k)] = __dadd_rn(__dmul_rn(PF_A, v.th[SIX(k)]), b_bits_over_slot(b));
+                    v.bits[SIX(k)] = b;
+                    a_th[ty] += b; a_prb[ty] += prbs; qsum[ty] += queue;     // update_info terms (slice_ran.py:278-305)
+                }
+            }
+        } else {
+            for (int k = 0; k < n_ues; ++k) {                    // nothing touched: stale bits / prbs accumulate
+                const int ty = (int)(v.meta[SIX(k)] & 1u);
+                a_th[ty] += v.bits[SIX(k)]; a_prb[ty] += v.pe[SIX(k)] & 0xFF; qsum[ty] += v.queue[SIX(k)];
+            }
+        }
+        // ================= update_info means (slice_ran.py:290-291, 304-305)
+#pragma unroll
+        for (int ty = 0; ty < 2; ++ty) {
+            a_queue[ty] += div_count((double)qsum[ty], cnt[ty]);
+            a_snr[ty] += div_count((double)sn[ty], cnt[ty]);
+        }
+    }
+
+    __syncwarp(warp_mask);
+    if (dead) {                                                  // replay this unit in the general kernel (list L)
+        st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * SORT_BINS + 1], 1u)] = u;
+        return;
+    }
+    // ---- scatter the records back (once per step) and persist the slice scalars
+    for (int k = 0; k < n_ues; ++k) {
+        UeRec r;
+        r.meta = v.meta[SIX(k)]; r.dep_at = v.dep[SIX(k)]; r.vnext = v.vnext[SIX(k)]; r.bits = v.bits[SIX(k)];
+        r.nominal = v.nominal[SIX(k)]; r.th = v.th[SIX(k)]; r.queue = v.queue[SIX(k)]; r.pe = v.pe[SIX(k)];
+        uint32_t *tg = reinterpret_cast<uint32_t *>(r.togo);
+        int nb = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            tg[j] = v.togo[(j * SM_KS + k) * SM_THREADS + tid];
+            nb += ((tg[j] & 0xFFFFu) != 0u) + ((tg[j] >> 16) != 0u);
+        }
+        r.nb = nb;
+        store_rec(ue + k, r);
+    }
+    hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
+    hdr.ctr[0] = c_ran; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
+    st.hdr[u] = hdr;
+    st.hint[u] = pf_iters;
+
+    // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
+    const double acc[10] = {(double)a_traffic[0], (double)a_th[0], (double)a_prb[0], a_queue[0], a_snr[0],
+                            (double)a_traffic[1], (double)a_th[1], (double)a_prb[1], a_queue[1], a_snr[1]};
+    finish_embb_unit(p, st, env, s, u, acc, flags);
+    if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
+    if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
+    if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
+}
+
+void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, cudaStream_t stream);
+void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream);
+
+// default variant: shared-memory kernel over the sorted front list, general kernel over list L
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
+    static bool configured = false;
+    constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
+    if (!configured) {
+        cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        configured = true;
+    }
+    launch_embb_sort(p, st, SM_MAX_START_UES, stream);
+    const int blocks = (st.U + SM_THREADS - 1) / SM_THREADS;
+    embb_step_smem<<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
+    launch_embb_general(p, st, tb, 1, stream);
+    return 5;   // kernels launched
+}
+
+}  // namespace rs

@@ -14,6 +14,7 @@
 namespace rs {
 void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
@@ -191,12 +192,12 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
-        sc.take<uint32_t>(U); sc.take<int32_t>(U); sc.take<uint32_t>(2 * rs::SORT_BINS); sc.take<uint32_t>(U); sc.take<float>(8);
+        sc.take<uint32_t>(U); sc.take<int32_t>(2 * U); sc.take<uint32_t>(2 * rs::SORT_BINS + 4); sc.take<uint32_t>(U); sc.take<float>(8);
         CU(cudaMalloc(&h->scratch, sc.off + 256));
         CU(cudaMemset(h->scratch, 0, sc.off + 256));
         Carver rc; rc.base = h->scratch;
-        h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(U);
-        h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
+        h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(2 * U);
+        h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
     }
 
     const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;
@@ -271,7 +272,8 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     }
     if (h->embb.U) {
         if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
-        else h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
+        else if (h->cfg.kernel_variant == 2 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
+        else h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st);
     }
     if (h->profiling) CU(cudaEventRecord(ev[1], st));
     if (h->mmtc.U) { rs::launch_mmtc_step(p, h->mmtc, st); h->launches += 1; }

@@ -53,8 +53,8 @@ struct EmbbState {
     int32_t *cur_prbs;     // [U] PRBs in force (after clamping)
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
-    int32_t *perm;         // [U] unit ids sorted by descending (n_prbs, contention class, live UEs)
-    uint32_t *hist;        // [2 * SORT_BINS] histogram / offsets + scatter cursors
+    int32_t *perm;         // [2U] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
+    uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
     uint32_t *hint;        // [U] PF-loop iterations of the previous step (sort hint only; never affects results)
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };

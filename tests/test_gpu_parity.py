@@ -8,7 +8,7 @@ import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 
 SCN = {0: (5, 200), 1: (5, 150), 2: (5, 100), 3: (2, 70)}
-VARIANTS = [0, 1]
+VARIANTS = [0, 1, 2]      # 0 shared-memory kernel (default), 1 all-fp64 anchor, 2 general fast kernel
 
 
 def simplex_actions(rng, N, S, n_prbs):
