@@ -39,10 +39,16 @@ constexpr uint32_t KEY_BINS = SORT_BINS;
 #define RS_FAST_MIN_BLOCKS 4      // resident 128-thread blocks per SM the register budget is sized for
 #endif
 
-// contention class from the previous step's PF work (general RB-loop iterations per TTI)
-__device__ __forceinline__ uint32_t contention_class(uint32_t pf_iters_prev, int slots) {
-    const uint32_t per_tti = pf_iters_prev / (uint32_t)slots;
-    return per_tti >= 16 ? 3u : (per_tti >= 4 ? 2u : (per_tti >= 1 ? 1u : 0u));
+// Contention class: predicted contended RB-loop iterations per TTI of this step, from the previous
+// step's count scaled to the new PRB allocation (hint = iterations << 8 | previous n_prbs); log2 buckets.
+// Only a scheduling hint: it decides which units share a warp, never what they compute.
+__device__ __forceinline__ uint32_t contention_class(uint32_t hint, int n_now, int slots) {
+    const uint32_t iters_prev = hint >> 8, n_prev = max(hint & 0xFFu, 1u);
+    const uint32_t pred = (uint32_t)(((unsigned long long)iters_prev * (unsigned)n_now) / ((unsigned long long)n_prev * (unsigned)slots));
+    return pred == 0 ? 0u : min(31u - (uint32_t)__clz(pred) + 1u, 7u);
+}
+__device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ues, int slots) {
+    return ((uint32_t)n_prbs << 7) | (contention_class(hint, n_prbs, slots) << 4) | (uint32_t)min(n_ues, 15);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -65,8 +71,7 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         st.cur_prbs[u] = v;
         const int n_ues = st.hdr[u].n_ues;
         if (n_ues <= max_front_ues) {
-            const uint32_t key = ((uint32_t)v << 6) | (contention_class(st.hint[u], p.slots) << 4) | (uint32_t)min(n_ues, 15);
-            atomicAdd(&st.hist[key], 1u);
+            atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots)], 1u);
         } else {
             st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
         }
@@ -104,8 +109,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ St
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
     if (st.hdr[u].n_ues > max_front_ues) return;
-    const uint32_t key = ((st.win[u] >> 16) << 6) | (contention_class(st.hint[u], p.slots) << 4) |
-                         (uint32_t)min(st.hdr[u].n_ues, 15);
+    const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], st.hdr[u].n_ues, p.slots);
     const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], 1u);
     st.perm[pos] = u;
 }
@@ -295,30 +299,10 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
             if (n_backlog > 1)
                 for (int k = 0; k < n_ues; ++k)
                     metf[k] = qq[k] > 0 ? (float)rate[k] * rcp_approx((float)th[k]) : 0.0f;
-            while (r < n_prbs) {
-                if (n_backlog == 0) { rbs[0] += n_prbs - r; break; }        // all metrics 0 -> argmax 0, tx 0
-                if (n_backlog == 1) {                                       // no competition: closed form
-                    int j = 0;
-                    while (qq[j] <= 0) ++j;
-                    const int left = n_prbs - r, full = left >> 1;
-                    const int cap2 = 2 * rate[j];
-                    if (qq[j] <= (long long)full * cap2) {                  // drained within the 2-PRB chunks
-                        const int q32 = (int)qq[j];
-                        const int need = (q32 + cap2 - 1) / cap2;
-                        rbs[j] += 2 * need; bits[j] += q32; qq[j] = 0; r += 2 * need;
-                        n_backlog = 0;
-                        continue;
-                    }
-                    int tx = full * cap2;
-                    rbs[j] += 2 * full; qq[j] -= tx; bits[j] += tx;
-                    if (left & 1) {                                         // last, single-PRB chunk
-                        tx = (int)min((long long)rate[j], qq[j]);
-                        rbs[j] += 1; qq[j] -= tx; bits[j] += tx;
-                    }
-                    break;
-                }
+            // phase 1: contended chunks (>= 2 backlogged UEs); one uniform loop body for all lanes still in it
+            while (n_backlog >= 2 && r < n_prbs) {
                 ++pf_iters;
-                if (RS_EXP & 8) { rbs[0] += n_prbs - r; break; }
+                if (RS_EXP & 8) break;
                 const int c = min(n_prbs - r, 2);
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 copy, exact when close
                 int idx = 0;
@@ -347,6 +331,29 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
                 else { metf[idx] = 0.0f; --n_backlog; }
                 r += 2;
             }
+            __syncwarp(sched_mask);
+            // phase 2: a single backlogged UE takes chunks until it is drained or the PRBs run out (closed form)
+            if (r < n_prbs && n_backlog == 1) {
+                int j = 0;
+                while (qq[j] <= 0) ++j;
+                const int left = n_prbs - r, full = left >> 1;
+                const int cap2 = 2 * rate[j];
+                if (qq[j] <= (long long)full * cap2) {                      // drained within the 2-PRB chunks
+                    const int q32 = (int)qq[j];
+                    const int need = (q32 + cap2 - 1) / cap2;
+                    rbs[j] += 2 * need; bits[j] += q32; qq[j] = 0; r += 2 * need;
+                } else {
+                    int tx = full * cap2;
+                    rbs[j] += 2 * full; qq[j] -= tx; bits[j] += tx;
+                    if (left & 1) {                                         // last, single-PRB chunk
+                        tx = (int)min((long long)rate[j], qq[j]);
+                        rbs[j] += 1; qq[j] -= tx; bits[j] += tx;
+                    }
+                    r = n_prbs;
+                }
+            }
+            // phase 3: every queue drained -> all metrics 0 -> argmax 0 with 0 bits for the remaining PRBs
+            if (r < n_prbs) rbs[0] += n_prbs - r;
             // ---- MI sums of the served sub-bands, flattened over (UE, quad): ~n_prbs/4 iterations per lane
             __syncwarp(sched_mask);
             {
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
     hdr.ctr[0] = c_ran; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
     st.hdr[u] = hdr;
-    st.hint[u] = pf_iters;
+    st.hint[u] = (pf_iters << 8) | (uint32_t)n_prbs;
 
     // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
     const double acc[10] = {(double)a_traffic[0], (double)a_th[0], (double)a_prb[0], a_queue[0], a_snr[0],

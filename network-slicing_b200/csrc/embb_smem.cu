@@ -296,27 +296,10 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
             for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= 0xFFFF0000; }   // ue_bits, ue_rbs
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
             int r = 0;
-            while (r < n_prbs) {
-                if (n_backlog == 0) { v.pe[SIX(0)] += n_prbs - r; break; }  // all metrics 0 -> argmax 0, tx 0
-                if (n_backlog == 1) {                                       // no competition: closed form
-                    int j = 0;
-                    while (v.queue[SIX(j)] - v.bits[SIX(j)] <= 0) ++j;
-                    const int left = n_prbs - r, full = left >> 1;
-                    const int rate = (int)(v.rm[SIX(j)] & 0xFFFFu), cap2 = 2 * rate;
-                    const int q32 = v.queue[SIX(j)] - v.bits[SIX(j)];
-                    if ((long long)q32 <= (long long)full * cap2) {         // drained within the 2-PRB chunks
-                        const int need = (q32 + cap2 - 1) / cap2;
-                        v.pe[SIX(j)] += 2 * need; v.bits[SIX(j)] += q32; r += 2 * need;
-                        n_backlog = 0;
-                        continue;
-                    }
-                    int tx = full * cap2;
-                    if (left & 1) tx += min(rate, q32 - tx);                // last, single-PRB chunk
-                    v.pe[SIX(j)] += left; v.bits[SIX(j)] += tx;
-                    break;
-                }
+            // phase 1: contended chunks (>= 2 backlogged UEs); one uniform loop body for all lanes still in it
+            while (n_backlog >= 2 && r < n_prbs) {
                 ++pf_iters;
-                if (RS_EXP & 8) { v.pe[SIX(0)] += n_prbs - r; break; }
+                if (RS_EXP & 8) break;
                 const int c = min(n_prbs - r, 2);
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 metric, exact when close
                 int idx = 0;
@@ -350,6 +333,26 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                 if (left_q - tx <= 0) --n_backlog;
                 r += 2;
             }
+            __syncwarp(sched_mask);
+            // phase 2: a single backlogged UE takes chunks until it is drained or the PRBs run out (closed form)
+            if (r < n_prbs && n_backlog == 1) {
+                int j = 0;
+                while (v.queue[SIX(j)] - v.bits[SIX(j)] <= 0) ++j;
+                const int left = n_prbs - r, full = left >> 1;
+                const int rate = (int)(v.rm[SIX(j)] & 0xFFFFu), cap2 = 2 * rate;
+                const int q32 = v.queue[SIX(j)] - v.bits[SIX(j)];
+                if ((long long)q32 <= (long long)full * cap2) {             // drained within the 2-PRB chunks
+                    const int need = (q32 + cap2 - 1) / cap2;
+                    v.pe[SIX(j)] += 2 * need; v.bits[SIX(j)] += q32; r += 2 * need;
+                } else {
+                    int tx = full * cap2;
+                    if (left & 1) tx += min(rate, q32 - tx);                // last, single-PRB chunk
+                    v.pe[SIX(j)] += left; v.bits[SIX(j)] += tx;
+                    r = n_prbs;
+                }
+            }
+            // phase 3: every queue drained -> all metrics 0 -> argmax 0 with 0 bits for the remaining PRBs
+            if (r < n_prbs) v.pe[SIX(0)] += n_prbs - r;
             // ---- MI sums of the served sub-bands, flattened over (UE, quad): ~n_prbs/4 iterations per lane
             __syncwarp(sched_mask);
             {
@@ -481,7 +484,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
     hdr.ctr[0] = c_ran; hdr.ctr[1] = r_chan.n; hdr.ctr[2] = r_rx.n; hdr.ctr[3] = r_vbr.n;
     st.hdr[u] = hdr;
-    st.hint[u] = pf_iters;
+    st.hint[u] = (pf_iters << 8) | (uint32_t)n_prbs;
 
     // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
     const double acc[10] = {(double)a_traffic[0], (double)a_th[0], (double)a_prb[0], a_queue[0], a_snr[0],

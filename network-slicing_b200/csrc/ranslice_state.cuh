@@ -55,11 +55,11 @@ struct EmbbState {
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
     int32_t *perm;         // [2U] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
     uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
-    uint32_t *hint;        // [U] PF-loop iterations of the previous step (sort hint only; never affects results)
+    uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
-constexpr int SORT_BINS = 16384;   // key = n_prbs << 6 | contention class << 4 | min(live UEs, 15)
+constexpr int SORT_BINS = 32768;   // key = n_prbs << 7 | contention class (3 bits) << 4 | min(live UEs, 15)
 
 struct MmtcState {
     int U, Q;              // units (env * n_mmtc + m), backlog cap
