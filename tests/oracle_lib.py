@@ -175,3 +175,71 @@ class OracleBatch:
         lib().orc_step_batch(self.handles, self.N, self.n_threads, _ptr(a), _ptr(obs), _ptr(rew), _ptr(lab),
                              _ptr(vio), _ptr(flags))
         return obs, rew, lab, vio, flags
+
+
+# ----------------------------------------------------------------------------- KBRL oracle (oracle/kbrl_oracle.c)
+def _kb_lib():
+    L = lib()
+    if not getattr(L, "_kb_ready", False):
+        L.orc_kb_create.restype = C.c_void_p
+        L.orc_kb_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                    C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.orc_kb_destroy.argtypes = [C.c_void_p]
+        L.orc_kb_update_control.argtypes = [C.c_void_p] * 5
+        L.orc_kb_select_action.argtypes = [C.c_void_p] * 4
+        L.orc_kb_get_control.argtypes = [C.c_void_p] * 6
+        L.orc_kb_get_learner.restype = C.c_int
+        L.orc_kb_get_learner.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_kb_predict.restype = C.c_double
+        L.orc_kb_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_kb_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        L._kb_ready = True
+    return L
+
+
+class OracleKBRL:
+    """One KBRL_Control (kbrl_control.py) with S Projectron learners, CPU oracle."""
+
+    def __init__(self, dims, n_prbs, init_action, init_sec, accuracy_range=(0.99, 0.999), alfa=0.05, gamma=1.0, eta=0.1):
+        self.S = len(dims)
+        self.dims = np.ascontiguousarray(dims, np.int32)
+        self.offsets = np.ascontiguousarray(np.concatenate([[0], np.cumsum(self.dims - 1)[:-1]]), np.int32)
+        self.n_prbs = n_prbs
+        ia = np.ascontiguousarray(init_action, np.int64)
+        isec = np.ascontiguousarray(init_sec, np.int64)
+        self.h = _kb_lib().orc_kb_create(self.S, _ptr(self.dims), _ptr(self.offsets), n_prbs, alfa, accuracy_range[0],
+                                         accuracy_range[1], _ptr(ia), _ptr(isec), gamma, eta)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _kb_lib().orc_kb_destroy(self.h)
+            self.h = None
+
+    def update_control(self, state, action, labels):
+        st = np.ascontiguousarray(state, np.float32)
+        a = np.ascontiguousarray(action, np.int64)
+        lab = np.ascontiguousarray(labels, np.int64)
+        hits = np.zeros(self.S, np.int64)
+        _kb_lib().orc_kb_update_control(self.h, _ptr(st), _ptr(a), _ptr(lab), _ptr(hits))
+        return hits
+
+    def select_action(self, state):
+        st = np.ascontiguousarray(state, np.float32)
+        a = np.zeros(self.S, np.int64)
+        adj = np.zeros(1, np.int32)
+        _kb_lib().orc_kb_select_action(self.h, _ptr(st), _ptr(a), _ptr(adj))
+        return a, int(adj[0])
+
+    def control(self):
+        sec = np.zeros(self.S, np.int64); mar = np.zeros(self.S, np.int64); sizes = np.zeros(self.S, np.int64)
+        acc = np.zeros((self.S, self.n_prbs), np.float64)
+        tb = C.c_long()
+        _kb_lib().orc_kb_get_control(self.h, _ptr(sec), _ptr(mar), _ptr(acc), _ptr(sizes), C.byref(tb))
+        return dict(security_factors=sec, margins=mar, accuracies=acc, sizes=sizes, tie_breaks=tb.value)
+
+    def learner(self, s):
+        D = int(self.control()["sizes"][s])
+        d = int(self.dims[s])
+        lm = np.zeros((max(D, 1), d)); cf = np.zeros(max(D, 1)); ki = np.zeros((max(D, 1), max(D, 1)))
+        _kb_lib().orc_kb_get_learner(self.h, s, _ptr(lm), _ptr(cf), _ptr(ki))
+        return lm[:D], cf[:D], ki[:D, :D]

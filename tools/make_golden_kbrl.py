@@ -1,0 +1,79 @@
+#!/usr/bin/env python3
+"""Golden fixtures for kernel #2 (KBRL: GaussianKernel + Projectron + KBRL_Control) from the UNMODIFIED
+reference.  Build-container tool.  For each case it runs the reference controller on the reference env
+(Philox-injected, tests/refharness.py) and records, per step, everything the controller saw and decided,
+so that the K3 tests can replay update_control / select_action without the env:
+  state[t], action[t], labels[t], new_state[t], next_action[t], adjusted[t], hits[t], sizes[t] (dictionary
+  size per learner after the step), security_factors[t], margins[t]; final landmarks/coeff/Kinv per learner.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {"K_scn0": (0, 9000, 400, [0.97, 0.99]), "K_scn1": (1, 9100, 300, [0.99, 0.999])}
+
+
+def gen(name):
+    import refharness as rh
+    scn, seed, steps, a_range = CASES[name]
+    ref = rh.load_reference()
+    tie_calls = []
+    ref.kernel.np = __import__("types").SimpleNamespace(
+        exp=np.exp, ndim=np.ndim, array=np.array, float32=np.float32, sign=np.sign,
+        random=__import__("types").SimpleNamespace(choice=lambda seq: tie_calls.append(1) or seq[0]))
+    env, _ = rh.make_env_philox(seed, scn)
+    agent = ref.scenario_creator.create_kbrl_agent(np.random.default_rng(seed), scn, accuracy_range=a_range)
+    S = agent.n_slices
+    init_action = agent.action.copy()
+    init_sec = agent.security_factors.copy()
+    rec = {k: [] for k in ("state", "action", "labels", "new_state", "next_action", "adjusted", "hits", "sizes",
+                           "security_factors", "margins", "reward", "violations")}
+    action = agent.action
+    state = env.reset()
+    for i in range(steps):
+        new_state, reward, _, info = env.step(action)
+        labels = info["SLA_labels"]
+        hits = agent.update_control(state, action, labels)
+        rec["state"].append(np.array(state, np.float32)); rec["action"].append(np.array(action, np.int64))
+        rec["labels"].append(np.array(labels, np.int64)); rec["new_state"].append(np.array(new_state, np.float32))
+        rec["hits"].append(np.array(hits, np.int64))
+        rec["sizes"].append(np.array([h.algorithm.counter for h in agent.learners], np.int64))
+        action, agent.adjusted = agent.select_action(new_state)
+        rec["next_action"].append(np.array(action, np.int64)); rec["adjusted"].append(int(agent.adjusted))
+        rec["security_factors"].append(agent.security_factors.astype(np.int64).copy())
+        rec["margins"].append(np.asarray(agent.margins, np.int64).copy())
+        rec["reward"].append(float(reward)); rec["violations"].append(int(info["total_violations"]))
+        state = new_state
+    out = {k: np.stack(v) if isinstance(v[0], np.ndarray) else np.array(v) for k, v in rec.items()}
+    Dmax = int(out["sizes"].max())
+    dims = [h.indexes.stop - h.indexes.start + 1 for h in agent.learners]
+    lm = np.zeros((S, Dmax, max(dims)))
+    cf = np.zeros((S, Dmax))
+    ki = np.zeros((S, Dmax, Dmax))
+    for s, h in enumerate(agent.learners):
+        D = h.algorithm.counter
+        if D == 0:
+            continue
+        L = np.atleast_2d(np.asarray(h.algorithm.sv.landmarks, np.float64))
+        lm[s, :D, :dims[s]] = L
+        cf[s, :D] = np.asarray(h.algorithm.sv.coeff, np.float64)
+        ki[s, :D, :D] = np.atleast_2d(np.asarray(h.algorithm.Kinv, np.float64))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), scenario=scn, seed=seed, accuracy_range=np.array(a_range),
+                        init_action=init_action.astype(np.int64), init_sec=init_sec.astype(np.int64), dims=np.array(dims),
+                        n_prbs=agent.n_prbs, alfa=agent.alfa, tie_calls=len(tie_calls), final_landmarks=lm,
+                        final_coeff=cf, final_kinv=ki, accuracies=agent.accuracies, numpy_version=np.__version__, **out)
+    return name, out["sizes"][-1].tolist(), int(out["violations"].sum()), len(tie_calls)
+
+
+if __name__ == "__main__":
+    from concurrent.futures import ProcessPoolExecutor
+    names = sys.argv[1:] or list(CASES)
+    with ProcessPoolExecutor(2) as ex:
+        for r in ex.map(gen, names):
+            print(r, flush=True)
