@@ -1,0 +1,67 @@
+/*
+ * kbrl_b200.h -- C ABI of kernel #2 (KBRL inner loop) in libranslice_b200.so.
+ *
+ * Batched replacement for the per-learner calls KBRL_Control makes into Projectron / GaussianKernel
+ * (reference: kbrl_control.py:41-114 -> algorithms/projectron.py:32-60 -> algorithms/kernel.py:8-28).
+ * One learner per (env, slice): L = n_envs * n_slices learners, each with its own growing dictionary
+ * (landmarks, coefficients, K^-1) resident in HBM, fp64 (with the reference's float32 stage while a
+ * dictionary holds a single landmark, kernel.py:15-16).
+ *
+ * x of a learner = [its slice's state variables (float32 -> float64), l1_prbs / n_prbs]
+ * (kbrl_control.py:56,88).  Same conventions as ranslice_b200.h (0 / negative error code, rs_last_error()).
+ */
+#ifndef KBRL_B200_H
+#define KBRL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { KB_FLAG_DICT_CAP = 1u /* dictionary full: a sample that should have been added was dropped */ };
+
+/* create_kbrl_agent(rng, n, accuracy_range) (scenario_creator.py:197-238): one
+ * Learner(Projectron(GaussianKernel(SVvariable(), gamma), eta)) per slice, here for n_envs envs. */
+typedef struct kb_config {
+    int32_t abi_version;   /* RS_ABI_VERSION */
+    int32_t device;
+    int32_t n_envs, n_slices, n_prbs;
+    int32_t n_variables;   /* V: row length of the state arrays */
+    int32_t dict_cap;      /* landmarks per learner (<= 1024); the reference is unbounded (flagged when hit) */
+    int32_t reserved;
+    double gamma, eta;     /* scenario_creator.py:218 (gamma = 1), projectron.py:25 (eta = 0.1) */
+} kb_config;
+
+typedef struct kb_handle kb_handle;
+
+/* dims[s] = len(x) of slice s (11 eMBB / 4 mMTC), offsets[s] = first state variable of slice s (Learner.indexes) */
+int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets, kb_handle **out);
+int kb_destroy(kb_handle *h);
+int kb_reset(kb_handle *h);                      /* empty dictionaries */
+
+/* Projectron part of KBRL_Control.update_control (kbrl_control.py:88-89,103-112), all learners:
+ *   y_pred[l] = predict([state_l, action_l / n_prbs])            (0 while the dictionary is empty)
+ *   then, with y = labels[l]: for a in (action_l .. n_prbs) if y == +1 else (0 .. action_l):
+ *        predict([state_l, a / n_prbs]); update(., y)
+ * state [N][V] float32, action / labels / y_pred [N][S] int32.  DEVICE pointers, async on stream. */
+int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels,
+                     int32_t *d_y_pred, void *stream);
+/* scan of KBRL_Control.select_action (kbrl_control.py:54-61): first_pos[l] = smallest l1_prbs in 0..n_prbs
+ * with predict([state_l, l1_prbs / n_prbs]) == +1, or -1 if none.  DEVICE pointers. */
+int kb_predict_device(kb_handle *h, const float *d_state, int32_t *d_first_pos, void *stream);
+
+/* HOST-buffer convenience wrappers (copy in, run, copy out, synchronise) */
+int kb_update(kb_handle *h, const float *state, const int32_t *action, const int32_t *labels, int32_t *y_pred);
+int kb_predict(kb_handle *h, const float *state, int32_t *first_pos);
+
+/* dictionary sizes [N][S] and KB_FLAG_* per learner (host buffers, either may be NULL) */
+int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags);
+/* dictionary of one learner, packed: landmarks [D][dims[s]], coeff [D], kinv [D][D]; returns D in *D_out */
+int kb_get_learner(kb_handle *h, int32_t learner, double *landmarks, double *coeff, double *kinv, int32_t *D_out);
+/* kernels launched so far; predict-mistakes (dictionary updates) applied in the last kb_update */
+int kb_get_counters(kb_handle *h, uint64_t *kernel_launches, uint64_t *updates_last_call);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,402 @@
+// K3: KBRL inner loop -- Gaussian-kernel evaluation and Projectron dictionary projection / update,
+// batched over L = n_envs * n_slices independent learners (C ABI: include/kbrl_b200.h).
+//
+//   GaussianKernel.k_eval / k / predict   algorithms/kernel.py:8-28
+//   Projectron.predict / update           algorithms/projectron.py:32-60
+//   callers restated: the select_action scan (kbrl_control.py:54-61) and the sample-augmentation loop of
+//   update_control (kbrl_control.py:103-112)
+//
+// One CTA per learner.  Both callers evaluate f(a) = sum_j coeff_j exp(-gamma ||l_j - [s, a/n]||^2) for
+// up to n_prbs + 1 candidate allocations a of one state s.  numpy's pairwise sum over the 11 (4)
+// squared differences adds the action coordinate LAST, so the distance is separable bit-exactly:
+// base_j (state part, once per landmark) + (l_j,last - a/n)^2.  Threads own candidates and walk the
+// landmarks (broadcast from shared memory) in index order; a dictionary update (rare: ~0.3 per
+// learner-step) is a block-cooperative K^-1 k mat-vec (columns are coalesced, K^-1 is exactly
+// symmetric) and, when the sample is not well approximated, a rank-1 extension of K^-1.
+// The Gram / K^-1 products stay warp-reduced fp64: a D x D mat-vec 1.4 times per env-step is far below
+// any tensor-core crossover.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/kbrl_b200.h"
+#include "../../include/ranslice_b200.h"
+
+namespace kb {
+
+constexpr int THREADS = 256;
+constexpr int MAX_CAND = 256;      // n_prbs + 1 <= 201
+constexpr int MAX_DIM = 16;
+
+struct State {
+    int L, S, V, n_prbs, cap;
+    double gamma, eta;
+    int dims[8], offs[8];
+    int *D;            // [L]
+    double *lm;        // [L][cap][MAX_DIM]
+    double *coeff;     // [L][cap]
+    double *kinv;      // [L][cap][cap] (exactly symmetric)
+    uint32_t *flags;   // [L]
+    unsigned long long *updates;   // [1]
+};
+
+// state part of ((l - x)**2).sum() in numpy's pairwise order (action coordinate excluded; it is added last)
+__device__ __forceinline__ double base_dist(const double *l, const double *x, int ns) {
+    if (ns < 8) {                                   // n = ns + 1 < 8 or exactly the sequential tail below
+        double r = 0.0;
+        for (int i = 0; i < ns; ++i) { const double t = l[i] - x[i]; r += t * t; }
+        return r;
+    }
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double t = l[i] - x[i]; a[i] = t * t; }
+    double r = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (int i = 8; i < ns; ++i) { const double t = l[i] - x[i]; r += t * t; }
+    return r;
+}
+
+__device__ __forceinline__ void carve(unsigned char *raw, int cap, double *&base, double *&cf, double *&ll, double *&kf,
+                                      double *&ds, double *&fval) {
+    double *p = reinterpret_cast<double *>(raw);
+    base = p; cf = base + cap; ll = cf + cap; kf = ll + cap; ds = kf + cap; fval = ds + cap;
+}
+
+// f(a) for candidate a with the dictionary staged in shared memory (kernel.py:13-25 incl. the D == 1 float32 stage)
+__device__ __forceinline__ double eval_f(int D, double gamma, const double *base, const double *cf, const double *ll, double xa) {
+    if (D == 0) return 0.0;
+    if (D == 1) {
+        const double t = ll[0] - xa;
+        const float k = (float)exp(-gamma * (base[0] + t * t));
+        return (double)(k * (float)cf[0]);
+    }
+    double f = 0.0;
+    for (int j = 0; j < D; ++j) {
+        const double t = ll[j] - xa;
+        f += exp(-gamma * (base[j] + t * t)) * cf[j];
+    }
+    return f;
+}
+
+__device__ void stage_dictionary(const State &kb, int l, int D, int d, const double *xs, double *base, double *cf, double *ll) {
+    const double *lm = kb.lm + (size_t)l * kb.cap * MAX_DIM;
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        base[j] = base_dist(lm + (size_t)j * MAX_DIM, xs, d - 1);
+        cf[j] = kb.coeff[(size_t)l * kb.cap + j];
+        ll[j] = lm[(size_t)j * MAX_DIM + d - 1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) predict_kernel(const State kb, const float *__restrict__ state, int32_t *first_pos) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    double *base, *cf, *ll, *kf, *ds, *fval;
+    carve(raw, kb.cap, base, cf, ll, kf, ds, fval);
+    __shared__ double xs[MAX_DIM];
+    __shared__ int s_first;
+    const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
+    if (threadIdx.x < d - 1) xs[threadIdx.x] = (double)state[(size_t)env * kb.V + kb.offs[s] + threadIdx.x];
+    if (threadIdx.x == 0) s_first = 1 << 30;
+    __syncthreads();
+    const int D = kb.D[l];
+    stage_dictionary(kb, l, D, d, xs, base, cf, ll);
+    __syncthreads();
+    for (int a = threadIdx.x; a <= kb.n_prbs; a += blockDim.x) {
+        const double f = eval_f(D, kb.gamma, base, cf, ll, (double)a / (double)kb.n_prbs);
+        if (f > 0.0) atomicMin(&s_first, a);                  // prediction == +1 (kernel.py:25)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) first_pos[l] = s_first == (1 << 30) ? -1 : s_first;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const float *__restrict__ state,
+                                                         const int32_t *__restrict__ action,
+                                                         const int32_t *__restrict__ labels, int32_t *y_pred) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    double *base, *cf, *ll, *kf, *ds, *fval;
+    carve(raw, kb.cap, base, cf, ll, kf, ds, fval);
+    __shared__ double xs[MAX_DIM];
+    __shared__ double s_delta;
+    __shared__ int s_first, s_D;
+    const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs, cap = kb.cap;
+    if (threadIdx.x < d - 1) xs[threadIdx.x] = (double)state[(size_t)env * kb.V + kb.offs[s] + threadIdx.x];
+    const int y = labels[l];
+    const int a0 = min(max(action[l], 0), n);
+    const int lo = y == 1 ? a0 : 0, hi = y == 1 ? n : a0;     // kbrl_control.py:103-112
+    double *lm = kb.lm + (size_t)l * cap * MAX_DIM;
+    double *coeff = kb.coeff + (size_t)l * cap;
+    double *kinv = kb.kinv + (size_t)l * cap * cap;
+    int D = kb.D[l];
+    int cur = lo;
+    bool first_round = true;
+    unsigned n_updates = 0;
+    __syncthreads();
+    while (cur <= hi) {
+        stage_dictionary(kb, l, D, d, xs, base, cf, ll);
+        if (threadIdx.x == 0) s_first = 1 << 30;
+        __syncthreads();
+        for (int a = cur + threadIdx.x; a <= hi; a += blockDim.x) {
+            const double f = eval_f(D, kb.gamma, base, cf, ll, (double)a / (double)n);
+            fval[a] = f;
+            if (f * (double)y <= 0.0) atomicMin(&s_first, a);  // Projectron.update acts only on mistakes (projectron.py:40)
+        }
+        __syncthreads();
+        if (first_round) {                                     // the predict of kbrl_control.py:89 (before any update)
+            if (threadIdx.x == 0) { const double f = fval[a0]; y_pred[l] = D == 0 ? 0 : (f > 0.0 ? 1 : -1); }
+            first_round = false;
+        }
+        const int astar = s_first;
+        if (astar == (1 << 30)) break;
+        // ---- Projectron.update at x = [s, astar / n] (projectron.py:41-60)
+        const double xa = (double)astar / (double)n;
+        ++n_updates;
+        if (D <= 1) {                                          // float32 stage: Kinv, K_f, coeff are float32 arrays of length 1
+            if (threadIdx.x == 0) {
+                float kfv = 0.f, ki = 0.f;
+                if (D == 1) { const double t = ll[0] - xa; kfv = (float)exp(-kb.gamma * (base[0] + t * t)); ki = (float)kinv[0]; }
+                const float dsv = ki * kfv;
+                const double dot = (double)(float)(dsv * kfv);
+                double delta = 1.0 - dot;
+                if (delta < 0.0) delta = 0.0;
+                if (delta <= kb.eta) coeff[0] = (double)(float)((float)coeff[0] + (float)y * dsv);
+                else {
+                    for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
+                    lm[(size_t)D * MAX_DIM + d - 1] = xa;
+                    coeff[D] = (double)y;
+                    if (D == 0) kinv[0] = (double)(float)(1.0 / 1.0);
+                    else {
+                        const double dse[2] = {(double)dsv, -1.0};
+                        kinv[1] = 0.0; kinv[cap] = 0.0; kinv[cap + 1] = 0.0;
+                        for (int i = 0; i < 2; ++i)
+                            for (int j = 0; j < 2; ++j) kinv[(size_t)i * cap + j] += dse[i] * dse[j] / delta;
+                    }
+                    s_D = D + 1;
+                }
+                if (delta <= kb.eta) s_D = D;
+            }
+            __syncthreads();
+            D = s_D;
+        } else {
+            for (int j = threadIdx.x; j < D; j += blockDim.x) { const double t = ll[j] - xa; kf[j] = exp(-kb.gamma * (base[j] + t * t)); }
+            __syncthreads();
+            for (int i = threadIdx.x; i < D; i += blockDim.x) {      // d* = K^-1 k; column i == row i (symmetric), coalesced
+                double acc = 0.0;
+                for (int j = 0; j < D; ++j) acc += kinv[(size_t)j * cap + i] * kf[j];
+                ds[i] = acc;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {                                   // delta = max(Kii - d* . k, 0), index order
+                double dot = 0.0;
+                for (int i = 0; i < D; ++i) dot += ds[i] * kf[i];
+                double delta = 1.0 - dot;
+                s_delta = delta < 0.0 ? 0.0 : delta;
+            }
+            __syncthreads();
+            const double delta = s_delta;
+            if (delta <= kb.eta) {                                    // sv.update(y * d_star)
+                for (int i = threadIdx.x; i < D; i += blockDim.x) coeff[i] += (double)y * ds[i];
+            } else if (D < cap) {                                     // sv.extend / insert + rank-1 extension of K^-1
+                if (threadIdx.x == 0) {
+                    for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
+                    lm[(size_t)D * MAX_DIM + d - 1] = xa;
+                    coeff[D] = (double)y;
+                    ds[D] = -1.0;
+                }
+                for (int i = threadIdx.x; i <= D; i += blockDim.x) { kinv[(size_t)i * cap + D] = 0.0; kinv[(size_t)D * cap + i] = 0.0; }
+                __syncthreads();
+                const int m = D + 1;
+                for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+                    const int i = idx / m, j = idx - i * m;
+                    kinv[(size_t)i * cap + j] += ds[i] * ds[j] / delta;
+                }
+                D = m;
+            } else if (threadIdx.x == 0) kb.flags[l] |= KB_FLAG_DICT_CAP;
+            __syncthreads();
+        }
+        cur = astar + 1;
+    }
+    if (threadIdx.x == 0) {
+        kb.D[l] = D;
+        if (n_updates) atomicAdd(kb.updates, (unsigned long long)n_updates);
+    }
+}
+
+}  // namespace kb
+
+// ================================================================================================= C ABI
+struct kb_handle {
+    kb_config cfg;
+    kb::State st;
+    size_t smem_bytes;
+    cudaStream_t stream;
+    float *d_state;
+    int32_t *d_action, *d_labels, *d_out;
+    uint64_t launches;
+};
+
+// error text is shared with ranslice_cabi.cu through rs_set_error
+extern "C" void rs_set_error(const char *msg);
+namespace {
+int kfail(int code, const std::string &m) { rs_set_error(m.c_str()); return code; }
+}
+#define KCU(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return kfail(RS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" {
+
+int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets, kb_handle **out) {
+    if (!cfg || !dims || !offsets || !out) return kfail(RS_E_ARG, "null argument");
+    if (cfg->abi_version != RS_ABI_VERSION) return kfail(RS_E_ARG, "abi_version mismatch");
+    if (cfg->n_envs <= 0 || cfg->n_slices <= 0 || cfg->n_slices > 8 || cfg->n_prbs <= 0 || cfg->n_prbs + 1 > kb::MAX_CAND)
+        return kfail(RS_E_ARG, "bad n_envs / n_slices / n_prbs");
+    const int cap = cfg->dict_cap ? cfg->dict_cap : 256;
+    if (cap < 2 || cap > 1024) return kfail(RS_E_ARG, "dict_cap must be in [2, 1024]");
+    for (int s = 0; s < cfg->n_slices; ++s) {
+        // separable distance needs the action coordinate to be added last by numpy's pairwise sum: len(x) != 8, < 16
+        if (dims[s] < 2 || dims[s] == 8 || dims[s] >= kb::MAX_DIM) return kfail(RS_E_ARG, "unsupported x dimension (need 2..15, != 8)");
+        if (offsets[s] < 0 || offsets[s] + dims[s] - 1 > cfg->n_variables) return kfail(RS_E_ARG, "state slice out of range");
+    }
+    int ndev = 0;
+    KCU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return kfail(RS_E_ARG, "bad device ordinal");
+    KCU(cudaSetDevice(cfg->device));
+    kb_handle *h = new kb_handle();
+    h->cfg = *cfg; h->cfg.dict_cap = cap; h->launches = 0;
+    kb::State &st = h->st;
+    st.L = cfg->n_envs * cfg->n_slices; st.S = cfg->n_slices; st.V = cfg->n_variables; st.n_prbs = cfg->n_prbs; st.cap = cap;
+    st.gamma = cfg->gamma; st.eta = cfg->eta;
+    for (int s = 0; s < 8; ++s) { st.dims[s] = s < cfg->n_slices ? dims[s] : 0; st.offs[s] = s < cfg->n_slices ? offsets[s] : 0; }
+    const size_t L = (size_t)st.L;
+    KCU(cudaMalloc(&st.D, L * sizeof(int)));
+    KCU(cudaMalloc(&st.lm, L * cap * kb::MAX_DIM * sizeof(double)));
+    KCU(cudaMalloc(&st.coeff, L * cap * sizeof(double)));
+    KCU(cudaMalloc(&st.kinv, L * cap * cap * sizeof(double)));
+    KCU(cudaMalloc(&st.flags, L * sizeof(uint32_t)));
+    KCU(cudaMalloc(&st.updates, sizeof(unsigned long long)));
+    KCU(cudaMalloc(&h->d_state, (size_t)cfg->n_envs * cfg->n_variables * sizeof(float)));
+    KCU(cudaMalloc(&h->d_action, L * sizeof(int32_t)));
+    KCU(cudaMalloc(&h->d_labels, L * sizeof(int32_t)));
+    KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
+    KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->smem_bytes = (size_t)(5 * cap + kb::MAX_CAND) * sizeof(double);
+    KCU(cudaFuncSetAttribute(kb::update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    KCU(cudaFuncSetAttribute(kb::predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    *out = h;
+    return kb_reset(h);
+}
+
+int kb_reset(kb_handle *h) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaMemset(h->st.D, 0, (size_t)h->st.L * sizeof(int)));
+    KCU(cudaMemset(h->st.flags, 0, (size_t)h->st.L * sizeof(uint32_t)));
+    KCU(cudaMemset(h->st.updates, 0, sizeof(unsigned long long)));
+    return RS_OK;
+}
+
+int kb_destroy(kb_handle *h) {
+    if (!h) return RS_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(h->st.D); cudaFree(h->st.lm); cudaFree(h->st.coeff); cudaFree(h->st.kinv); cudaFree(h->st.flags);
+    cudaFree(h->st.updates); cudaFree(h->d_state); cudaFree(h->d_action); cudaFree(h->d_labels); cudaFree(h->d_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return RS_OK;
+}
+
+int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels,
+                     int32_t *d_y_pred, void *stream) {
+    if (!h || !d_state || !d_action || !d_labels || !d_y_pred) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
+    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, d_y_pred);
+    h->launches += 1;
+    KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+int kb_predict_device(kb_handle *h, const float *d_state, int32_t *d_first_pos, void *stream) {
+    if (!h || !d_state || !d_first_pos) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    kb::predict_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, (cudaStream_t)stream>>>(h->st, d_state, d_first_pos);
+    h->launches += 1;
+    KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+int kb_update(kb_handle *h, const float *state, const int32_t *action, const int32_t *labels, int32_t *y_pred) {
+    if (!h || !state || !action || !labels || !y_pred) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    const size_t L = (size_t)h->st.L;
+    KCU(cudaMemcpyAsync(h->d_state, state, (size_t)h->cfg.n_envs * h->cfg.n_variables * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    KCU(cudaMemcpyAsync(h->d_action, action, L * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    KCU(cudaMemcpyAsync(h->d_labels, labels, L * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = kb_update_device(h, h->d_state, h->d_action, h->d_labels, h->d_out, h->stream);
+    if (rc) return rc;
+    KCU(cudaMemcpyAsync(y_pred, h->d_out, L * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    KCU(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int kb_predict(kb_handle *h, const float *state, int32_t *first_pos) {
+    if (!h || !state || !first_pos) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    const size_t L = (size_t)h->st.L;
+    KCU(cudaMemcpyAsync(h->d_state, state, (size_t)h->cfg.n_envs * h->cfg.n_variables * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    int rc = kb_predict_device(h, h->d_state, h->d_out, h->stream);
+    if (rc) return rc;
+    KCU(cudaMemcpyAsync(first_pos, h->d_out, L * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    KCU(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    if (sizes) KCU(cudaMemcpy(sizes, h->st.D, (size_t)h->st.L * sizeof(int), cudaMemcpyDeviceToHost));
+    if (flags) KCU(cudaMemcpy(flags, h->st.flags, (size_t)h->st.L * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+int kb_get_learner(kb_handle *h, int32_t l, double *landmarks, double *coeff, double *kinv, int32_t *D_out) {
+    if (!h || l < 0 || l >= h->st.L) return kfail(RS_E_ARG, "bad handle / learner");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    int D = 0;
+    KCU(cudaMemcpy(&D, h->st.D + l, sizeof(int), cudaMemcpyDeviceToHost));
+    const int cap = h->st.cap, d = h->st.dims[l % h->st.S];
+    if (landmarks && D) {
+        std::vector<double> tmp((size_t)D * kb::MAX_DIM);
+        KCU(cudaMemcpy(tmp.data(), h->st.lm + (size_t)l * cap * kb::MAX_DIM, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < D; ++i) for (int j = 0; j < d; ++j) landmarks[(size_t)i * d + j] = tmp[(size_t)i * kb::MAX_DIM + j];
+    }
+    if (coeff && D) KCU(cudaMemcpy(coeff, h->st.coeff + (size_t)l * cap, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost));
+    if (kinv && D)
+        KCU(cudaMemcpy2D(kinv, (size_t)D * sizeof(double), h->st.kinv + (size_t)l * cap * cap, (size_t)cap * sizeof(double),
+                         (size_t)D * sizeof(double), D, cudaMemcpyDeviceToHost));
+    if (D_out) *D_out = D;
+    return RS_OK;
+}
+
+int kb_get_counters(kb_handle *h, uint64_t *kernel_launches, uint64_t *updates_last_call) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    KCU(cudaSetDevice(h->cfg.device));
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (updates_last_call) {
+        KCU(cudaDeviceSynchronize());
+        unsigned long long v = 0;
+        KCU(cudaMemcpy(&v, h->st.updates, sizeof v, cudaMemcpyDeviceToHost));
+        *updates_last_call = v;
+    }
+    return RS_OK;
+}
+
+}  // extern "C"

@@ -118,6 +118,7 @@ void build_tables(const rs_tables *t, rs::Tables &tb) {
 extern "C" {
 
 const char *rs_last_error(void) { return g_err.c_str(); }
+void rs_set_error(const char *msg) { g_err = msg ? msg : ""; }   // shared with kbrl.cu (internal)
 
 int rs_n_variables(const rs_handle *h) { return h ? h->p.V : 0; }
 

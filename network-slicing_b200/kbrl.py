@@ -1,0 +1,224 @@
+"""Host-side mirror of the reference's KBRL controller on top of kernel #2 (include/kbrl_b200.h).
+
+* :class:`BatchedProjectron` -- L = n_envs * n_slices Projectron learners resident on the GPU; the two
+  batched calls replace the per-sample ``Projectron.predict / update`` loops of ``KBRL_Control``
+  (kbrl_control.py:54-61 and :88-89,103-112).
+* :class:`KBRLControl` -- ``KBRL_Control`` (kbrl_control.py:23-157) vectorised over the env axis with
+  numpy: E-learner accuracies, security factors, margins, ``adjust_action`` and the ``run`` loop keep the
+  reference's names, arithmetic and result keys (``reward, resources, hits, adjusted, SLA, violation``).
+* :func:`create_kbrl_agent` -- ``scenario_creator.create_kbrl_agent`` (scenario_creator.py:197-238).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .scenario_creator import scenarios, state_variables_embb, state_variables_mmtc
+
+alfa = 0.05                 # scenario_creator.py:187
+embb_sec, embb_a = (2, 8), (4, 20)        # :190-191
+mmtc_sec, mmtc_a = (1, 4), (2, 10)        # :192-193
+
+
+class KbConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_envs", C.c_int32), ("n_slices", C.c_int32),
+                ("n_prbs", C.c_int32), ("n_variables", C.c_int32), ("dict_cap", C.c_int32), ("reserved", C.c_int32),
+                ("gamma", C.c_double), ("eta", C.c_double)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _bind(L):
+    if getattr(L, "_kb_bound", False):
+        return L
+    vp = C.c_void_p
+    L.kb_create.argtypes = [C.POINTER(KbConfig), vp, vp, C.POINTER(vp)]
+    L.kb_destroy.argtypes = [vp]
+    L.kb_reset.argtypes = [vp]
+    L.kb_update.argtypes = [vp] * 5
+    L.kb_predict.argtypes = [vp] * 3
+    L.kb_update_device.argtypes = [vp] * 6
+    L.kb_predict_device.argtypes = [vp] * 4
+    L.kb_get_sizes.argtypes = [vp, vp, vp]
+    L.kb_get_learner.argtypes = [vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int32)]
+    L.kb_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    for n in ("kb_create", "kb_destroy", "kb_reset", "kb_update", "kb_predict", "kb_update_device", "kb_predict_device",
+              "kb_get_sizes", "kb_get_learner", "kb_get_counters"):
+        getattr(L, n).restype = C.c_int
+    L._kb_bound = True
+    return L
+
+
+class BatchedProjectron:
+    """One ``Projectron(GaussianKernel(SVvariable(), gamma), eta)`` per (env, slice), on the GPU."""
+
+    def __init__(self, scenario, n_envs, dict_cap=256, device=0, gamma=1.0, eta=0.1):
+        sc = scenarios[scenario] if isinstance(scenario, int) else scenario
+        self.n_envs, self.n_prbs = n_envs, sc['n_prbs']
+        n_embb, n_mmtc = sc['n_embb'], sc['n_mmtc']
+        self.n_slices = n_embb + n_mmtc
+        self.dims = np.array([len(state_variables_embb) + 1] * n_embb + [len(state_variables_mmtc) + 1] * n_mmtc, np.int32)
+        self.offsets = np.concatenate([[0], np.cumsum(self.dims - 1)[:-1]]).astype(np.int32)
+        self.n_variables = int((self.dims - 1).sum())
+        L = _bind(_lib.lib())
+        cfg = KbConfig(_lib.RS_ABI_VERSION, device, n_envs, self.n_slices, self.n_prbs, self.n_variables, dict_cap, 0,
+                       gamma, eta)
+        h = C.c_void_p()
+        _lib.check(L.kb_create(C.byref(cfg), _p(self.dims), _p(self.offsets), C.byref(h)))
+        self._h, self._L = h, L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.kb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def update(self, state, action, labels):
+        """-> y_pred int32 [N,S] (prediction at (state, action) before the augmentation updates)."""
+        st = np.ascontiguousarray(state, np.float32).reshape(self.n_envs, self.n_variables)
+        a = np.ascontiguousarray(action, np.int32).reshape(self.n_envs, self.n_slices)
+        lab = np.ascontiguousarray(labels, np.int32).reshape(self.n_envs, self.n_slices)
+        out = np.empty((self.n_envs, self.n_slices), np.int32)
+        _lib.check(self._L.kb_update(self._h, _p(st), _p(a), _p(lab), _p(out)))
+        return out
+
+    def predict(self, state):
+        """-> first_pos int32 [N,S]: smallest l1_prbs whose prediction is +1, -1 if none."""
+        st = np.ascontiguousarray(state, np.float32).reshape(self.n_envs, self.n_variables)
+        out = np.empty((self.n_envs, self.n_slices), np.int32)
+        _lib.check(self._L.kb_predict(self._h, _p(st), _p(out)))
+        return out
+
+    def update_device(self, state, action, labels, y_pred):
+        import torch
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        _lib.check(self._L.kb_update_device(self._h, C.c_void_p(state.data_ptr()), C.c_void_p(action.data_ptr()),
+                                            C.c_void_p(labels.data_ptr()), C.c_void_p(y_pred.data_ptr()), C.c_void_p(stream)))
+        return y_pred
+
+    def predict_device(self, state, first_pos):
+        import torch
+        stream = torch.cuda.current_stream(state.device).cuda_stream
+        _lib.check(self._L.kb_predict_device(self._h, C.c_void_p(state.data_ptr()), C.c_void_p(first_pos.data_ptr()),
+                                             C.c_void_p(stream)))
+        return first_pos
+
+    def sizes(self):
+        s = np.empty((self.n_envs, self.n_slices), np.int32)
+        f = np.empty((self.n_envs, self.n_slices), np.uint32)
+        _lib.check(self._L.kb_get_sizes(self._h, _p(s), _p(f)))
+        return s, f
+
+    def learner(self, env, s):
+        l = env * self.n_slices + s
+        D = int(self.sizes()[0][env, s])
+        d = int(self.dims[s])
+        lm = np.zeros((max(D, 1), d)); cf = np.zeros(max(D, 1)); ki = np.zeros((max(D, 1), max(D, 1)))
+        Dout = C.c_int32()
+        _lib.check(self._L.kb_get_learner(self._h, l, _p(lm), _p(cf), _p(ki), C.byref(Dout)))
+        return lm[:D], cf[:D], ki[:D, :D]
+
+    def counters(self):
+        k, u = C.c_uint64(), C.c_uint64()
+        _lib.check(self._L.kb_get_counters(self._h, C.byref(k), C.byref(u)))
+        return int(k.value), int(u.value)
+
+
+class KBRLControl:
+    """``KBRL_Control`` (kbrl_control.py:23-157) for N envs at once; learners = :class:`BatchedProjectron`."""
+
+    def __init__(self, learners, n_prbs, initial_action, security_factor, alfa=0.05, accuracy_range=(0.99, 0.999)):
+        self.learners = learners
+        self.accuracy_range = list(accuracy_range)
+        self.n_envs, self.n_slices, self.n_prbs, self.alfa = learners.n_envs, learners.n_slices, n_prbs, alfa
+        N, S = self.n_envs, self.n_slices
+        self.adjusted = np.zeros(N, np.int64)
+        self.action = np.broadcast_to(np.asarray(initial_action, np.int64), (N, S)).copy()
+        self.security_factors = np.broadcast_to(np.asarray(security_factor, np.int64), (N, S)).copy()
+        self.margins = np.zeros((N, S), np.int64)
+        self.accuracies = np.full((N, S, n_prbs), (self.accuracy_range[0] + self.accuracy_range[1]) / 2, float)   # :38-39
+
+    def select_action(self, state):
+        """kbrl_control.py:41-78 -> (action int64 [N,S], adjusted int64 [N])."""
+        n = self.n_prbs
+        first = self.learners.predict(state).astype(np.int64)
+        found = first >= 0
+        a = np.minimum(n, first + self.security_factors)                     # :58
+        action = np.where(found, a, n)                                       # loop ran out: l1_prbs = n_prbs
+        margins = np.where(found, a - first, 0)
+        assigned = action.sum(axis=1)
+        adjusted = assigned > n                                              # :65
+        rel = action / np.maximum(assigned, 1)[:, None]                      # adjust_action, :75-78
+        new_action = np.floor(n * rel).astype(np.int64)
+        self.margins = np.where(adjusted[:, None], margins - (action - new_action), margins)
+        self.action = np.where(adjusted[:, None], new_action, action)
+        return self.action.copy(), adjusted.astype(np.int64)
+
+    def update_control(self, state, action, reward):
+        """kbrl_control.py:80-114; ``reward`` = SLA labels (+1 / -1) [N,S] -> hits [N,S]."""
+        action = np.asarray(action, np.int64)
+        y = np.asarray(reward, np.int64)
+        y_pred = self.learners.update(state, action, y).astype(np.int64)      # predict + sample augmentation on the GPU
+        hit = y == y_pred
+        margin = np.maximum(0, self.margins)
+        idx = np.arange(self.n_prbs)[None, None, :]
+        pos = (y_pred == 1)[:, :, None]
+        miss_mask = pos & ~hit[:, :, None] & (idx <= margin[:, :, None])      # :93-94
+        hit_mask = pos & hit[:, :, None] & (idx >= margin[:, :, None])        # :95-96
+        acc = self.accuracies
+        acc = np.where(miss_mask, (1 - self.alfa) * acc, acc)
+        acc = np.where(hit_mask, (1 - self.alfa) * acc + self.alfa, acc)
+        self.accuracies = acc
+        sf = np.argmax(acc > self.accuracy_range[0], axis=2)                  # :98-99 (0 when none)
+        free = (self.adjusted == 0)[:, None]
+        self.security_factors = np.where(free, sf, self.security_factors)
+        return hit.astype(np.int64)
+
+    def run(self, system, steps, learning_time=-1):
+        """kbrl_control.py:116-157 against a :class:`BatchedRanSlice`; histories get a leading env axis."""
+        N, S = self.n_envs, self.n_slices
+        action = self.action
+        SLA_history = np.zeros((N, steps), np.int16)
+        reward_history = np.zeros((N, steps), float)
+        violation_history = np.zeros((N, steps), np.int16)
+        adjusted_actions = np.zeros((N, steps), np.int16)
+        resources_history = np.zeros((N, steps), np.int16)
+        hits_history = np.zeros((N, S, steps), np.int16)
+        state = system.reset()
+        for i in range(steps):
+            new_state, reward, _, info = system.step(action)
+            SLA_labels = info['SLA_labels']
+            hits = self.update_control(state, action, SLA_labels)
+            action, self.adjusted = self.select_action(new_state)
+            state = new_state
+            SLA_history[:, i] = SLA_labels.sum(axis=1)
+            reward_history[:, i] = reward
+            violation_history[:, i] = info['total_violations']
+            resources_history[:, i] = action.sum(axis=1)
+            adjusted_actions[:, i] = self.adjusted
+            hits_history[:, :, i] = hits
+        return {'reward': reward_history, 'resources': resources_history, 'hits': hits_history,
+                'adjusted': adjusted_actions, 'SLA': SLA_history, 'violation': violation_history}
+
+
+def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=256, device=0):
+    """``scenario_creator.create_kbrl_agent`` (scenario_creator.py:197-238): random initial action and security
+    factor per learner (drawn per env from ``rng`` in the reference's order), gamma = 1, eta = 0.1."""
+    sc = scenarios[n]
+    n_embb, n_mmtc = sc['n_embb'], sc['n_mmtc']
+    ia = np.zeros((n_envs, n_embb + n_mmtc), np.int64)
+    sec = np.zeros_like(ia)
+    for e in range(n_envs):
+        for s in range(n_embb):
+            ia[e, s] = rng.integers(embb_a[0], embb_a[1]); sec[e, s] = rng.integers(embb_sec[0], embb_sec[1])
+        for s in range(n_embb, n_embb + n_mmtc):
+            ia[e, s] = rng.integers(mmtc_a[0], mmtc_a[1]); sec[e, s] = rng.integers(mmtc_sec[0], mmtc_sec[1])
+    learners = BatchedProjectron(n, n_envs, dict_cap=dict_cap, device=device)
+    return KBRLControl(learners, sc['n_prbs'], ia, sec, alfa=alfa, accuracy_range=accuracy_range)

@@ -1,0 +1,92 @@
+"""Kernel #2 on the GPU (through the C ABI) against the reference fixtures and the pinned oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _control(g, n_envs=1, dict_cap=256):
+    from ranslice_b200.kbrl import BatchedProjectron, KBRLControl
+    lrn = BatchedProjectron(int(g["scenario"]), n_envs, dict_cap=dict_cap)
+    return KBRLControl(lrn, int(g["n_prbs"]), g["init_action"], g["init_sec"], alfa=float(g["alfa"]),
+                       accuracy_range=tuple(g["accuracy_range"]))
+
+
+@pytest.mark.parametrize("name", ["K_scn0", "K_scn1"])
+def test_controller_replays_reference_fixture(golden, name):
+    """CUDA Projectron + host mirror of KBRL_Control vs the unmodified reference controller, step by step."""
+    g = golden(name)
+    ctl = _control(g)
+    for t in range(len(g["state"])):
+        hits = ctl.update_control(g["state"][t][None], g["action"][t][None], g["labels"][t][None])
+        assert np.array_equal(hits[0], g["hits"][t]), t
+        assert np.array_equal(ctl.learners.sizes()[0][0], g["sizes"][t]), t
+        a, adj = ctl.select_action(g["new_state"][t][None])
+        ctl.adjusted = adj                       # run(): action, self.adjusted = self.select_action(new_state)
+        assert np.array_equal(a[0], g["next_action"][t]) and adj[0] == g["adjusted"][t], t
+        assert np.array_equal(ctl.security_factors[0], g["security_factors"][t]), t
+        assert np.array_equal(ctl.margins[0], g["margins"][t]), t
+    assert np.allclose(ctl.accuracies[0], g["accuracies"], rtol=0, atol=1e-15)
+    for s in range(len(g["dims"])):
+        lm, cf, ki = ctl.learners.learner(0, s)
+        D, d = len(cf), int(g["dims"][s])
+        assert np.array_equal(lm, g["final_landmarks"][s, :D, :d])
+        assert np.allclose(cf, g["final_coeff"][s, :D], rtol=1e-8, atol=1e-11)
+        assert np.allclose(ki, g["final_kinv"][s, :D, :D], rtol=1e-8, atol=1e-8)
+    assert not ctl.learners.sizes()[1].any()
+
+
+def test_batched_learners_match_oracle_on_synthetic_streams():
+    """64 envs x 5 learners driven by synthetic (state, action, label) streams: every env's decisions equal
+    the oracle's for that env (learners are independent; batching must not mix them)."""
+    from ranslice_b200.kbrl import BatchedProjectron, KBRLControl
+    N, S, n_prbs, T = 64, 5, 200, 60
+    rng = np.random.default_rng(11)
+    ia = rng.integers(4, 20, (N, S)); sec = rng.integers(2, 8, (N, S))
+    ctl = KBRLControl(BatchedProjectron(0, N, dict_cap=128), n_prbs, ia, sec, accuracy_range=(0.97, 0.99))
+    orcs = [ol.OracleKBRL([11] * S, n_prbs, ia[e], sec[e], (0.97, 0.99)) for e in range(N)]
+    state = rng.random((N, 50)).astype(np.float32)
+    action = ia.copy()
+    for t in range(T):
+        new_state = np.clip(state + rng.normal(0, 0.05, state.shape), 0, 1.5).astype(np.float32)
+        need = (new_state.reshape(N, S, 10)[:, :, 0] * 60).astype(np.int64)       # synthetic SLA rule
+        labels = np.where(action >= need, 1, -1)
+        hits = ctl.update_control(state, action, labels)
+        nxt, adj = ctl.select_action(new_state)
+        ctl.adjusted = adj
+        for e in range(N):
+            h = orcs[e].update_control(state[e], action[e], labels[e])
+            a, ad = orcs[e].select_action(new_state[e])
+            assert np.array_equal(h, hits[e]) and np.array_equal(a, nxt[e]) and ad == adj[e], (t, e)
+        action, state = nxt, new_state
+    sizes = ctl.learners.sizes()[0]
+    assert np.array_equal(sizes, np.array([o.control()["sizes"] for o in orcs]))
+    assert sizes.max() > 3
+
+
+def test_dictionary_cap_is_flagged():
+    from ranslice_b200.kbrl import BatchedProjectron
+    lrn = BatchedProjectron(0, 2, dict_cap=4)
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        st = (rng.random((2, 50)) * 3).astype(np.float32)
+        lrn.update(st, rng.integers(0, 200, (2, 5)), rng.choice([-1, 1], (2, 5)))
+    sizes, flags = lrn.sizes()
+    assert sizes.max() <= 4 and (flags & 1).any()
+
+
+def test_kbrl_in_the_loop_with_the_env():
+    """BASELINE config 3 shape: env step + KBRL update/select every step (small batch); dictionaries grow,
+    allocations respect sum(action) <= n_prbs, result keys match kbrl_control.py:148-155."""
+    from ranslice_b200 import create_batched_env
+    from ranslice_b200.kbrl import create_kbrl_agent
+    N = 32
+    env = create_batched_env(99, 0, N)
+    agent = create_kbrl_agent(np.random.default_rng(0), 0, accuracy_range=(0.97, 0.99), n_envs=N, dict_cap=128)
+    out = agent.run(env, 40)
+    assert set(out) == {"reward", "resources", "hits", "adjusted", "SLA", "violation"}
+    assert out["hits"].shape == (N, 5, 40) and (out["resources"] <= 200).all()
+    assert agent.learners.sizes()[0].max() > 2
+    env.close()
