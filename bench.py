@@ -149,10 +149,11 @@ def main():
     K = args.steps
 
     from ranslice_b200 import create_batched_env
+    from ranslice_b200.sharding import max_over_ranks, weak_shard
     scn = args.scenario
     S, n_prbs, V = SCN[scn]
-    E = args.envs_per_gpu
-    env = create_batched_env(BASE_SEED, scn, E, device=local, first_env_id=rank * E, kernel_variant=args.variant)
+    first_env, E = weak_shard(args.envs_per_gpu, rank)      # weak scaling: fixed envs per GPU, global env ids
+    env = create_batched_env(BASE_SEED, scn, E, device=local, first_env_id=first_env, kernel_variant=args.variant)
     env.reset()
 
     def barrier():
@@ -207,10 +208,7 @@ def main():
     prof = env.profile_steps([dev_act[warmup + (i % K)] for i in range(min(K, 10))], out)
     n_live = int(env.n_ues().sum())
 
-    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = float(t[0]), float(t[1])
+    t_dev, t_e2e = max_over_ranks(t_dev), max_over_ranks(t_e2e)      # slowest shard decides
     total_envs = E * world
 
     if rank == 0:
@@ -225,7 +223,15 @@ def main():
         b_state = S * 16 * E + 88 * n_live
         b_io = (4 * S + 4 * V + 4 + 8 * S) * E
         b_trace = 4 * trace_elems
-        b_alg = 2 * b_state + b_io + b_trace
+        b_mtc = 4200 * env.n_mmtc * E                         # one scan of the 1000 next-arrival words + backlog
+        b_alg = 2 * b_state + b_io + b_trace + b_mtc
+        traffic = None                                        # dram bytes per launch from the committed ncu capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if tr.get("envs_per_gpu") == E and tr.get("scenario") == scn:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         k_ms = prof["embb_ms"] if scn != 3 else prof["embb_ms"] + prof["mmtc_ms"]
         achieved = b_alg / (k_ms * 1e-3) / 1e9
         line = {
@@ -242,7 +248,7 @@ def main():
                     "d2h_bytes_per_step": (4 * V + 4 + 8 * S + 4) * E, "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": prof["kernel"],
+                         "traffic": traffic, "peak_source": peak_src, "kernel": prof["kernel"],
                          "kernel_ms": k_ms, "bytes_per_launch": b_alg,
                          "bytes_per_env_step": b_alg / E, "nominal_bytes_per_env_step": NOMINAL_BALG.get(scn),
                          "note": "issue/latency-bound path (serial PF loop, fp64 decisions); tables are L2-resident, "
