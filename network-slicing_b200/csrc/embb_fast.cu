@@ -53,10 +53,13 @@ __device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ue
 
 // ---------------------------------------------------------------------------------------------
 // Pre-pass 1: PRB windows of all eMBB units of a step (node_b.py:71-74) + histogram of sort keys.
-// Units whose live-UE count fits the shared-memory kernel (embb_smem.cu) are counting-sorted into the
-// front of perm[]; the others are appended from the back (list L) for the general kernel below.
+// Units whose live-UE count fits ONE lane's slots of the shared-memory kernel (embb_smem.cu) are counting-
+// sorted into the front list of perm[]; units that need TWO lanes' slots (heavy_min_ues <= n_ues <=
+// max_front_ues) are placed before them as (unit, -1) pairs -- the odd lane only lends its shared memory --;
+// the rest is appended from the back (list L) for the general kernel below.
 __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ StepParams p,
-                                                     const __grid_constant__ EmbbState st, const int max_front_ues) {
+                                                     const __grid_constant__ EmbbState st, const int max_front_ues,
+                                                     const int heavy_min_ues) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.N) return;
     const int32_t *a = p.action + (size_t)env * p.S;
@@ -70,8 +73,12 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         st.win[u] = (uint32_t)off | ((uint32_t)v << 16);
         st.cur_prbs[u] = v;
         const int n_ues = st.hdr[u].n_ues;
-        if (n_ues <= max_front_ues) {
+        if (n_ues < heavy_min_ues) {
             atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots)], 1u);
+        } else if (n_ues <= max_front_ues) {
+            const uint32_t pos = 2u * atomicAdd(&st.hist[2 * KEY_BINS + 3], 1u);
+            st.perm[pos] = u;
+            st.perm[pos + 1] = -1;
         } else {
             st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
         }
@@ -97,18 +104,19 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Embb
         s_tot[threadIdx.x] += v;
         __syncthreads();
     }
-    uint32_t run = s_tot[threadIdx.x] - sum;
+    const uint32_t head = 2u * st.hist[2 * KEY_BINS + 3];                    // (unit, pad) pairs come first
+    uint32_t run = head + s_tot[threadIdx.x] - sum;
 #pragma unroll
     for (int i = 0; i < PER; ++i) { st.hist[KEY_BINS + base + PER - 1 - i] = run; run += loc[i]; }
-    if (threadIdx.x == 1023) st.hist[2 * KEY_BINS + 0] = s_tot[1023];        // size of the sorted front list
+    if (threadIdx.x == 1023) st.hist[2 * KEY_BINS + 0] = head + s_tot[1023]; // entries of the front list
 }
 
 // Pre-pass 3: scatter.
 __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ StepParams p,
-                                                      const __grid_constant__ EmbbState st, const int max_front_ues) {
+                                                      const __grid_constant__ EmbbState st, const int heavy_min_ues) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
-    if (st.hdr[u].n_ues > max_front_ues) return;
+    if (st.hdr[u].n_ues >= heavy_min_ues) return;
     const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], st.hdr[u].n_ues, p.slots);
     const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], 1u);
     st.perm[pos] = u;
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     const int count = (int)st.hist[2 * KEY_BINS + back_list];           // front (sorted) list or back list L
     const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
     if (tix >= count) return;
-    const int u = st.perm[back_list ? 2 * st.U - 1 - tix : tix];
+    const int u = st.perm[back_list ? 2 * st.U - 1 - tix : tix];    // (variant 2 has no pair entries: heavy_min = inf)
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
     unpack_window(st.win[u], i_prb, n_prbs);
@@ -505,11 +513,11 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
     embb_reset_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(st);
 }
 
-void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, cudaStream_t stream) {
+void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream) {
     cudaMemsetAsync(st.hist, 0, (2 * KEY_BINS + 4) * sizeof(uint32_t), stream);
-    window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues);
+    window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);
     scan_kernel<<<1, 1024, 0, stream>>>(st);
-    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues);
+    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, heavy_min_ues);
 }
 
 // general kernel over the front list (back_list = 0) or over list L (back_list = 1)
@@ -521,7 +529,7 @@ void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables 
 
 // variant 2: every unit through the general kernel, sorted
 int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    launch_embb_sort(p, st, 1 << 30, stream);
+    launch_embb_sort(p, st, 1 << 30, 1 << 30, stream);
     launch_embb_general(p, st, tb, 0, stream);
     return 4;   // kernels launched
 }

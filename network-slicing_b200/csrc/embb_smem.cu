@@ -9,11 +9,13 @@
 // unit's records once, keeps them as conflict-free SoA words smem[(slot, word)][thread], runs the 50
 // TTIs out of shared memory, and writes the records back once.  L1 then only serves the trace lines.
 //
-// Capacity: KS = 8 slots of 17 words per thread (68 KB per 128-thread block, 3 blocks per SM).  Units
-// with more than KS - 2 live UEs at the start of the step go to the general kernel (list L of the
-// sort pre-pass); a unit that outgrows its slots during the step (or whose queue no longer fits 31
-// bits) ABORTS before writing anything and is appended to list L, i.e. it is replayed from its
-// untouched state by the general kernel.  Results are therefore independent of the routing.
+// Capacity: KS = 8 slots of 17 words per lane (68 KB per 128-thread block, 3 blocks per SM).  A unit with
+// up to 6 live UEs at the start of the step owns one lane; a unit with 7..14 owns a PAIR of lanes (the odd
+// lane idles and lends its 8 slots: slot k >= 8 lives in the neighbour's column), placed at the head of the
+// sorted list by the pre-pass.  Only units with more than 14 UEs go to the general kernel (list L).  A unit
+// that outgrows its slots during the step (or whose queue no longer fits 31 bits) ABORTS before writing
+// anything and is appended to list L, i.e. it is replayed from its untouched state by the general
+// kernel.  Results are therefore independent of the routing.
 #include "embb_device.cuh"
 #include "embb_fastmath.cuh"
 
@@ -22,7 +24,8 @@ namespace rs {
 constexpr int SM_THREADS = 128;
 constexpr int SM_KS = 8;          // UE slots per thread held in shared memory
 constexpr int SM_WORDS = 17;      // 32-bit words per slot
-constexpr int SM_MAX_START_UES = SM_KS - 2;
+constexpr int SM_MAX_START_UES = SM_KS - 2;            // single-lane units
+constexpr int SM_MAX_START_UES_PAIR = 2 * SM_KS - 2;   // units that own a pair of lanes
 constexpr int QUEUE_LIMIT = 1 << 30;
 
 // word offsets inside a slot (64-bit fields first so that they are 8-byte aligned in their own planes)
@@ -58,20 +61,23 @@ __device__ __forceinline__ SmemView carve_smem(unsigned char *base) {
 }
 static_assert(SM_WORDS == 3 * 2 + 7 + 4, "slot word budget");
 
-#define SIX(k) ((k) * SM_THREADS + tid)
+// element of slot k in a [KS][T] plane: slots 8.. of a pair-owning unit live in the neighbouring (idle) lane's column
+#define SIX(k) ((((k) & (SM_KS - 1)) * SM_THREADS) + tid + ((k) >> 3))
+#define TGX(j, k) ((((j) * SM_KS + ((k) & (SM_KS - 1))) * SM_THREADS) + tid + ((k) >> 3))
+static_assert(SM_KS == 8, "SIX/TGX assume 8 slots per lane");
 
 __device__ __forceinline__ void smem_move_slot(const SmemView &v, int tid, int from, int to) {
     v.th[SIX(to)] = v.th[SIX(from)]; v.nominal[SIX(to)] = v.nominal[SIX(from)];
     v.queue[SIX(to)] = v.queue[SIX(from)]; v.meta[SIX(to)] = v.meta[SIX(from)]; v.dep[SIX(to)] = v.dep[SIX(from)];
     v.vnext[SIX(to)] = v.vnext[SIX(from)]; v.bits[SIX(to)] = v.bits[SIX(from)]; v.pe[SIX(to)] = v.pe[SIX(from)];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + to) * SM_THREADS + tid] = v.togo[(j * SM_KS + from) * SM_THREADS + tid];
+    for (int j = 0; j < 4; ++j) v.togo[TGX(j, to)] = v.togo[TGX(j, from)];
 }
 
 // Rare RAN events of a slot on the shared-memory table; same order as ran_events in embb_fast.cu
 // (slice_ran.py:263-268, slice_l1.py:196-198).  Sets c.flags bit 31 when the unit must abort.
 __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, int tid, uint32_t k0, uint32_t k1,
-                                             uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, RanCtx &c) {
+                                             uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, int slots_cap, RanCtx &c) {
     struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran}, {k0, k1, s, STREAM_CHAN, c.c_chan},
                                                 {k0, k1, s, STREAM_VBR, c.c_vbr}};
     int n_ues = c.n_ues, cbr_next = c.cbr_next, vbr_next = c.vbr_next;
@@ -109,7 +115,7 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
     for (int a = 0; a < n_arr; ++a) {                                             // slice_l1.py:183-186
         const int rem = arr_rem[a] - 1;                          // this slot's departures() already ticked it
         if (rem == 0) { flags |= 8u; continue; }
-        if (n_ues >= SM_KS) { flags |= 0x80000000u; break; }     // out of slots: replay in the general kernel
+        if (n_ues >= slots_cap) { flags |= 0x80000000u; break; } // out of slots: replay in the general kernel
         const int fading = (int)rng.chan.integers(3);                             // channel_models.py:163-169
         const int index = (int)rng.chan.integers(N_SAMPLES);
         const int step = rng.chan.integers(2) ? 1 : -1;
@@ -120,7 +126,7 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
         v.dep[SIX(k)] = dep_at;
         v.vnext[SIX(k)] = arr_vnext[a]; v.bits[SIX(k)] = 0; v.th[SIX(k)] = 0.0; v.queue[SIX(k)] = 0; v.pe[SIX(k)] = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = 0u;
+        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = 0u;
         next_dep = min(next_dep, dep_at);
         ++n_ues;
     }
@@ -133,7 +139,7 @@ __device__ __forceinline__ int vbr_step_smem(const SmemView &v, int tid, int k, 
     uint32_t w[4];
     bool any = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { w[j] = v.togo[(j * SM_KS + k) * SM_THREADS + tid]; any |= w[j] != 0u; }
+    for (int j = 0; j < 4; ++j) { w[j] = v.togo[TGX(j, k)]; any |= w[j] != 0u; }
     int bits = 0;
     bool dirty = false;
     if (any) {
@@ -162,7 +168,7 @@ __device__ __forceinline__ int vbr_step_smem(const SmemView &v, int tid, int k, 
     } else v.vnext[SIX(k)] = vn;
     if (dirty) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = w[j];
+        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = w[j];
     }
     return bits;
 }
@@ -188,7 +194,10 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     const int count = (int)st.hist[2 * SORT_BINS + 0];
     const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
     if (tix >= count) return;
-    const int u = st.perm[tix];
+    const int u_raw = st.perm[tix];
+    const bool pad = u_raw < 0;                                  // idle lane lending its slots to the unit on its left
+    const int slots_cap = tix < 2 * (int)st.hist[2 * SORT_BINS + 3] ? 2 * SM_KS : SM_KS;
+    const int u = pad ? 0 : u_raw;
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
     unpack_window(st.win[u], i_prb, n_prbs);
@@ -203,9 +212,9 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1]}, r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2]},
         r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
 
-    int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
+    int n_ues = pad ? 0 : hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
     uint32_t clock = hdr.clock, next_dep = DEP_NEVER;
-    bool dead = false;                                           // aborted: replayed by the general kernel
+    bool dead = pad;                                             // aborted (replayed by the general kernel) or idle pad lane
 
     // ---- gather the unit's records into shared memory (once per step)
     for (int k = 0; k < n_ues; ++k) {
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         v.bits[SIX(k)] = r.bits; v.pe[SIX(k)] = r.pe;
         const uint32_t *tg = reinterpret_cast<const uint32_t *>(r.togo);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[(j * SM_KS + k) * SM_THREADS + tid] = tg[j];
+        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = tg[j];
         next_dep = min(next_dep, r.dep_at);
         dead |= r.queue >= QUEUE_LIMIT;
     }
@@ -235,7 +244,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         if (!dead) {
             if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
                 RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
-                ran_events_smem(p, v, tid, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], c);
+                ran_events_smem(p, v, tid, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], slots_cap, c);
                 c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
                 n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
                 if (flags & 0x80000000u) { dead = true; n_ues = 0; }
@@ -462,6 +471,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     }
 
     __syncwarp(warp_mask);
+    if (pad) return;
     if (dead) {                                                  // replay this unit in the general kernel (list L)
         st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * SORT_BINS + 1], 1u)] = u;
         return;
@@ -475,7 +485,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         int nb = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            tg[j] = v.togo[(j * SM_KS + k) * SM_THREADS + tid];
+            tg[j] = v.togo[TGX(j, k)];
             nb += ((tg[j] & 0xFFFFu) != 0u) + ((tg[j] >> 16) != 0u);
         }
         r.nb = nb;
@@ -495,7 +505,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
 }
 
-void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, cudaStream_t stream);
+void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream);
 void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream);
 
 // default variant: shared-memory kernel over the sorted front list, general kernel over list L
@@ -506,8 +516,8 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
         cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         configured = true;
     }
-    launch_embb_sort(p, st, SM_MAX_START_UES, stream);
-    const int blocks = (st.U + SM_THREADS - 1) / SM_THREADS;
+    launch_embb_sort(p, st, SM_MAX_START_UES_PAIR, SM_MAX_START_UES + 1, stream);
+    const int blocks = (2 * st.U + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
     embb_step_smem<<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     launch_embb_general(p, st, tb, 1, stream);
     return 5;   // kernels launched
