@@ -9,7 +9,7 @@
 // unit's records once, keeps them as conflict-free SoA words smem[(slot, word)][thread], runs the 50
 // TTIs out of shared memory, and writes the records back once.  L1 then only serves the trace lines.
 //
-// Capacity: KS = 8 slots of 17 words per lane (68 KB per 128-thread block, 3 blocks per SM).  A unit with
+// Capacity: KS = 8 slots of 18 words per lane (72 KB per 128-thread block, 3 blocks per SM).  A unit with
 // up to 6 live UEs at the start of the step owns one lane; a unit with 7..14 owns a PAIR of lanes (the odd
 // lane idles and lends its 8 slots: slot k >= 8 lives in the neighbour's column), placed at the head of the
 // sorted list by the pre-pass.  Only units with more than 14 UEs go to the general kernel (list L).  A unit
@@ -23,7 +23,7 @@ namespace rs {
 
 constexpr int SM_THREADS = 128;
 constexpr int SM_KS = 8;          // UE slots per thread held in shared memory
-constexpr int SM_WORDS = 17;      // 32-bit words per slot
+constexpr int SM_WORDS = 18;      // 32-bit words per slot
 constexpr int SM_MAX_START_UES = SM_KS - 2;            // single-lane units
 constexpr int SM_MAX_START_UES_PAIR = 2 * SM_KS - 2;   // units that own a pair of lanes
 constexpr int QUEUE_LIMIT = 1 << 30;
@@ -40,6 +40,7 @@ struct SmemView {
     int *bits;         // [KS][T] ue.bits; doubles as the scheduler's ue_bits while a TTI is scheduled
     int *pe;           // [KS][T] ue.prbs (bits 0-7) | ue.e_snr << 16; prbs doubles as ue_rbs
     uint32_t *rm;      // [KS][T] rate (low 16) | mcs << 16 of this TTI
+    float *metf;       // [KS][T] fp32 PF metric rate / th of a backlogged UE, 0 otherwise (schedulers.py:52)
     uint32_t *togo;    // [4][KS][T] 8 x int16 burst countdowns
 };
 
@@ -56,10 +57,11 @@ __device__ __forceinline__ SmemView carve_smem(unsigned char *base) {
     v.bits = v.vnext + P;
     v.pe = v.bits + P;
     v.rm = reinterpret_cast<uint32_t *>(v.pe + P);
-    v.togo = v.rm + P;
+    v.metf = reinterpret_cast<float *>(v.rm + P);
+    v.togo = reinterpret_cast<uint32_t *>(v.metf + P);
     return v;
 }
-static_assert(SM_WORDS == 3 * 2 + 7 + 4, "slot word budget");
+static_assert(SM_WORDS == 3 * 2 + 8 + 4, "slot word budget");
 
 // element of slot k in a [KS][T] plane: slots 8.. of a pair-owning unit live in the neighbouring (idle) lane's column
 #define SIX(k) ((((k) & (SM_KS - 1)) * SM_THREADS) + tid + ((k) >> 3))
@@ -173,8 +175,14 @@ __device__ __forceinline__ int vbr_step_smem(const SmemView &v, int tid, int k, 
     return bits;
 }
 
-// x / n for a small positive integer count n: skip the division for n == 1 (the common case)
-__device__ __forceinline__ double div_count(double x, int n) { return n <= 1 ? x : x / (double)n; }
+// x / n for a small positive integer count n, exactly rounded: q = RN(x * RN(1/n)), r = x - q n (exact, FMA),
+// q' = RN(q + r * RN(1/n)) (Markstein; rs_selftest samples the identity against IEEE division).
+__device__ __forceinline__ double div_count(double x, int n) {
+    if (n <= 1) return x;
+    const double dn = (double)n, rcp = __drcp_rn(dn);
+    const double q = __dmul_rn(x, rcp);
+    return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
+}
 
 __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_constant__ StepParams p,
                                                                 const __grid_constant__ EmbbState st,
@@ -184,9 +192,11 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     __shared__ int8_t s_mcs[256];
     __shared__ float s_ref[26];
     __shared__ int8_t s_mod[26];
+    __shared__ float s_inv[2 * TRACE_ROWS + 1];                  // 1 / n for the MI mean (fp32 fast path, inside the eps budget)
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += SM_THREADS) { s_rate[i] = tb.lut_rate[i]; s_mcs[i] = tb.lut_mcs[i]; }
     if (tid < 26) { s_ref[tid] = (float)tb.snr_ref[tid]; s_mod[tid] = tb.mod[tid]; }
+    for (int i = tid; i <= 2 * TRACE_ROWS; i += SM_THREADS) s_inv[i] = i ? __frcp_rn((float)i) : 0.f;
     __syncthreads();
     const SmemView v = carve_smem(smem_raw);
 
@@ -291,7 +301,9 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
             const int e = min(max(pe >> 16, -128), 127) + 128;
             v.rm[SIX(k)] = (uint32_t)(uint16_t)s_rate[e] | ((uint32_t)(uint8_t)s_mcs[e] << 16);
             const double th = v.th[SIX(k)];
-            v.thpf[SIX(k)] = th > 1.0 ? th : 1.0;
+            const double thp = th > 1.0 ? th : 1.0;
+            v.thpf[SIX(k)] = thp;
+            v.metf[SIX(k)] = queue > 0 ? (float)s_rate[e] * rcp_approx((float)thp) : 0.0f;
             n_backlog += queue > 0;
             sn[ty] += pe >> 16;
             cnt[ty] += 1;
@@ -312,10 +324,9 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                 const int c = min(n_prbs - r, 2);
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 metric, exact when close
                 int idx = 0;
-                float best = -1.0f, second = -1.0f;
-                for (int k = 0; k < n_ues; ++k) {
-                    const bool has = v.queue[SIX(k)] - v.bits[SIX(k)] > 0;
-                    const float m = has ? (float)(v.rm[SIX(k)] & 0xFFFFu) * rcp_approx((float)v.thpf[SIX(k)]) : 0.0f;
+                float best = v.metf[SIX(0)], second = -1.0f;
+                for (int k = 1; k < n_ues; ++k) {
+                    const float m = v.metf[SIX(k)];
                     if (m > best) { second = best; best = m; idx = k; }
                     else second = fmaxf(second, m);
                 }
@@ -323,11 +334,9 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                     const float lim = best * (1.0f - 1e-6f);
                     double best64 = -1.0;
                     for (int k = 0; k < n_ues; ++k) {
-                        if (v.queue[SIX(k)] - v.bits[SIX(k)] <= 0) continue;
-                        const double thk = v.thpf[SIX(k)];
-                        const float rate_f = (float)(v.rm[SIX(k)] & 0xFFFFu);
-                        if (rate_f * rcp_approx((float)thk) >= lim) {
-                            const double m64 = (double)(v.rm[SIX(k)] & 0xFFFFu) / thk;
+                        const float m = v.metf[SIX(k)];
+                        if (m >= lim && m > 0.0f) {
+                            const double m64 = (double)(v.rm[SIX(k)] & 0xFFFFu) / v.thpf[SIX(k)];
                             if (m64 > best64) { best64 = m64; idx = k; }
                         }
                     }
@@ -338,8 +347,10 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                 const int nbits = v.bits[SIX(idx)] + tx;
                 v.bits[SIX(idx)] = nbits;
                 v.pe[SIX(idx)] += c;
-                v.thpf[SIX(idx)] = __dadd_rn(__dmul_rn(PF_A, v.thpf[SIX(idx)]), b_bits_over_slot(nbits));
-                if (left_q - tx <= 0) --n_backlog;
+                const double thn = __dadd_rn(__dmul_rn(PF_A, v.thpf[SIX(idx)]), b_bits_over_slot(nbits));
+                v.thpf[SIX(idx)] = thn;
+                if (left_q - tx <= 0) { v.metf[SIX(idx)] = 0.0f; --n_backlog; }
+                else v.metf[SIX(idx)] = (float)rate * rcp_approx((float)thn);
                 r += 2;
             }
             __syncwarp(sched_mask);
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                 const int4 *col4 = nullptr;
                 for (; !(RS_EXP & 4);) {
                     if (left == 0) {
-                        if (k >= 0) v.thpf[SIX(k)] = msum / (double)rbs_k;   // mean MI; the PF copy of th is dead by now
+                        if (k >= 0) v.metf[SIX(k)] = (float)msum * s_inv[rbs_k];    // mean MI (the PF metric is dead by now)
                         do { ++k; if (k < n_ues) { rbs_k = v.pe[SIX(k)] & 0xFF; lo = o; o += rbs_k; } } while (k < n_ues && rbs_k < 2);
                         if (k >= n_ues) break;
                         hi = lo + rbs_k;
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                         float dbg_p32 = -1.f, dbg_eps = 0.f;
                         if (prbs == 1) need_exact = true;                    // single RB: no MI averaging, one fp64 sigmoid
                         else {
-                            const float m = (float)v.thpf[SIX(k)];
+                            const float m = v.metf[SIX(k)];
                             if (m >= 1.0f - 1e-4f) received = true;          // p == 1.0 exactly in fp64
                             else if (m <= 1e-4f) received = false;           // p < 2^-53
                             else {

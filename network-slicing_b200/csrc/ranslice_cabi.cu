@@ -372,6 +372,18 @@ int rs_selftest(void) {
         const double q2 = std::fma(r, 1000.0, q);
         if (q2 != y / slot) return fail(RS_E_STATE, "two-FMA division by slot_length is not exact for bits=" + std::to_string(bits));
     }
+    // (3) x / n by two FMAs (update_info means, slice_ran.py:290-291,304-305) for counts 2..32
+    unsigned long long lcg = 88172645463325252ull;
+    for (int n = 2; n <= 32; ++n) {
+        const double dn = (double)n, rcp = 1.0 / dn;
+        for (int it = 0; it < 200000; ++it) {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            const double x = (it & 1) ? (double)(long long)(lcg >> (16 + (it % 40))) : -(double)(long long)(lcg >> 40);
+            const double q = x * rcp;
+            const double q2 = std::fma(std::fma(-q, dn, x), rcp, q);
+            if (q2 != x / dn) return fail(RS_E_STATE, "two-FMA division by a count is not exact");
+        }
+    }
     return RS_OK;
 }
 
