@@ -47,8 +47,9 @@ __device__ __forceinline__ uint32_t contention_class(uint32_t hint, int n_now, i
     const uint32_t pred = (uint32_t)(((unsigned long long)iters_prev * (unsigned)n_now) / ((unsigned long long)n_prev * (unsigned)slots));
     return pred == 0 ? 0u : min(31u - (uint32_t)__clz(pred) + 1u, 7u);
 }
-__device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ues, int slots) {
-    return ((uint32_t)n_prbs << 7) | (contention_class(hint, n_prbs, slots) << 4) | (uint32_t)min(n_ues, 15);
+constexpr uint32_t HEAVY_BIT = 1u << 15;   // units that own a pair of lanes sort ahead of everything else
+__device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ues, int slots, bool heavy) {
+    return (heavy ? HEAVY_BIT : 0u) | ((uint32_t)n_prbs << 7) | (contention_class(hint, n_prbs, slots) << 4) | (uint32_t)min(n_ues, 15);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -74,11 +75,9 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         st.cur_prbs[u] = v;
         const int n_ues = st.hdr[u].n_ues;
         if (n_ues < heavy_min_ues) {
-            atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots)], 1u);
+            atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots, false)], 1u);
         } else if (n_ues <= max_front_ues) {
-            const uint32_t pos = 2u * atomicAdd(&st.hist[2 * KEY_BINS + 3], 1u);
-            st.perm[pos] = u;
-            st.perm[pos + 1] = -1;
+            atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots, true)], 2u);      // (unit, pad) pair
         } else {
             st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
         }
@@ -104,22 +103,30 @@ __global__ void __launch_bounds__(1024) scan_kernel(const __grid_constant__ Embb
         s_tot[threadIdx.x] += v;
         __syncthreads();
     }
-    const uint32_t head = 2u * st.hist[2 * KEY_BINS + 3];                    // (unit, pad) pairs come first
-    uint32_t run = head + s_tot[threadIdx.x] - sum;
+    uint32_t run = s_tot[threadIdx.x] - sum;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { st.hist[KEY_BINS + base + PER - 1 - i] = run; run += loc[i]; }
-    if (threadIdx.x == 1023) st.hist[2 * KEY_BINS + 0] = head + s_tot[1023]; // entries of the front list
+    for (int i = 0; i < PER; ++i) {
+        const int bin = base + PER - 1 - i;
+        st.hist[KEY_BINS + bin] = run;
+        if (bin == (int)HEAVY_BIT - 1) st.hist[2 * KEY_BINS + 3] = run >> 1;  // entries ahead of the first single-lane bin = 2 x pairs
+        run += loc[i];
+    }
+    if (threadIdx.x == 1023) st.hist[2 * KEY_BINS + 0] = s_tot[1023];        // entries of the front list
 }
 
 // Pre-pass 3: scatter.
 __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ StepParams p,
-                                                      const __grid_constant__ EmbbState st, const int heavy_min_ues) {
+                                                      const __grid_constant__ EmbbState st, const int max_front_ues,
+                                                      const int heavy_min_ues) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
-    if (st.hdr[u].n_ues >= heavy_min_ues) return;
-    const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], st.hdr[u].n_ues, p.slots);
-    const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], 1u);
+    const int n_ues = st.hdr[u].n_ues;
+    if (n_ues > max_front_ues) return;
+    const bool heavy = n_ues >= heavy_min_ues;
+    const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], n_ues, p.slots, heavy);
+    const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], heavy ? 2u : 1u);
     st.perm[pos] = u;
+    if (heavy) st.perm[pos + 1] = -1;                          // the odd lane only lends its shared-memory slots
 }
 
 // Rare RAN events of a slot, exactly in the reference's order (slice_ran.py:263-268, slice_l1.py:196-198):
@@ -517,7 +524,7 @@ void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ue
     cudaMemsetAsync(st.hist, 0, (2 * KEY_BINS + 4) * sizeof(uint32_t), stream);
     window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);
     scan_kernel<<<1, 1024, 0, stream>>>(st);
-    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, heavy_min_ues);
+    scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);
 }
 
 // general kernel over the front list (back_list = 0) or over list L (back_list = 1)

@@ -59,7 +59,7 @@ struct EmbbState {
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
-constexpr int SORT_BINS = 32768;   // key = n_prbs << 7 | contention class (3 bits) << 4 | min(live UEs, 15)
+constexpr int SORT_BINS = 65536;   // key = pair-of-lanes bit << 15 | n_prbs << 7 | contention class (3 bits) << 4 | min(live UEs, 15)
 
 struct MmtcState {
     int U, Q;              // units (env * n_mmtc + m), backlog cap
