@@ -9,7 +9,10 @@
 // unit's records once, keeps them as conflict-free SoA words smem[(slot, word)][thread], runs the 50
 // TTIs out of shared memory, and writes the records back once.  L1 then only serves the trace lines.
 //
-// Capacity: KS = 8 slots of 18 words per lane (72 KB per 128-thread block, 3 blocks per SM).  A unit with
+// Capacity: KS = 8 slots of 13 hot words per lane (52 KB per 128-thread block, 4 blocks per SM).  The cold part of
+// a UE (departure time, VBR countdowns) is only touched on events -- VBR traffic is evaluated lazily: between
+// events a source contributes 1000 bits per active burst -- and lives in a per-step global scratch copy, so an
+// aborted unit leaves the records untouched.  A unit with
 // up to 6 live UEs at the start of the step owns one lane; a unit with 7..14 owns a PAIR of lanes (the odd
 // lane idles and lends its 8 slots: slot k >= 8 lives in the neighbour's column), placed at the head of the
 // sorted list by the pre-pass.  Only units with more than 14 UEs go to the general kernel (list L).  A unit
@@ -23,7 +26,7 @@ namespace rs {
 
 constexpr int SM_THREADS = 128;
 constexpr int SM_KS = 8;          // UE slots per thread held in shared memory
-constexpr int SM_WORDS = 18;      // 32-bit words per slot
+constexpr int SM_WORDS = 13;      // 32-bit words per slot
 constexpr int SM_MAX_START_UES = SM_KS - 2;            // single-lane units
 constexpr int SM_MAX_START_UES_PAIR = 2 * SM_KS - 2;   // units that own a pair of lanes
 constexpr int QUEUE_LIMIT = 1 << 30;
@@ -35,13 +38,11 @@ struct SmemView {
     double *nominal;   // [KS][T]
     int *queue;        // [KS][T] ue.queue (bits, < 2^30 or the unit aborts)
     uint32_t *meta;    // [KS][T]
-    uint32_t *dep;     // [KS][T]
-    int *vnext;        // [KS][T]
+    uint32_t *vev;     // [KS][T] VBR: slots until this source's next event (burst end / burst arrival), VEV_NONE if none
     int *bits;         // [KS][T] ue.bits; doubles as the scheduler's ue_bits while a TTI is scheduled
-    int *pe;           // [KS][T] ue.prbs (bits 0-7) | ue.e_snr << 16; prbs doubles as ue_rbs
+    int *pe;           // [KS][T] ue.prbs (bits 0-7) | active bursts (bits 8-11) | ue.e_snr << 16; prbs doubles as ue_rbs
     uint32_t *rm;      // [KS][T] rate (low 16) | mcs << 16 of this TTI
     float *metf;       // [KS][T] fp32 PF metric rate / th of a backlogged UE, 0 otherwise (schedulers.py:52)
-    uint32_t *togo;    // [4][KS][T] 8 x int16 burst countdowns
 };
 
 __device__ __forceinline__ SmemView carve_smem(unsigned char *base) {
@@ -52,33 +53,58 @@ __device__ __forceinline__ SmemView carve_smem(unsigned char *base) {
     v.nominal = v.thpf + P;
     v.queue = reinterpret_cast<int *>(v.nominal + P);
     v.meta = reinterpret_cast<uint32_t *>(v.queue + P);
-    v.dep = v.meta + P;
-    v.vnext = reinterpret_cast<int *>(v.dep + P);
-    v.bits = v.vnext + P;
+    v.vev = v.meta + P;
+    v.bits = reinterpret_cast<int *>(v.vev + P);
     v.pe = v.bits + P;
     v.rm = reinterpret_cast<uint32_t *>(v.pe + P);
     v.metf = reinterpret_cast<float *>(v.rm + P);
-    v.togo = reinterpret_cast<uint32_t *>(v.metf + P);
     return v;
 }
-static_assert(SM_WORDS == 3 * 2 + 8 + 4, "slot word budget");
+static_assert(SM_WORDS == 3 * 2 + 7, "slot word budget");
 
 // element of slot k in a [KS][T] plane: slots 8.. of a pair-owning unit live in the neighbouring (idle) lane's column
 #define SIX(k) ((((k) & (SM_KS - 1)) * SM_THREADS) + tid + ((k) >> 3))
-#define TGX(j, k) ((((j) * SM_KS + ((k) & (SM_KS - 1))) * SM_THREADS) + tid + ((k) >> 3))
-static_assert(SM_KS == 8, "SIX/TGX assume 8 slots per lane");
+static_assert(SM_KS == 8, "SIX assumes 8 slots per lane");
 
-__device__ __forceinline__ void smem_move_slot(const SmemView &v, int tid, int from, int to) {
-    v.th[SIX(to)] = v.th[SIX(from)]; v.nominal[SIX(to)] = v.nominal[SIX(from)];
-    v.queue[SIX(to)] = v.queue[SIX(from)]; v.meta[SIX(to)] = v.meta[SIX(from)]; v.dep[SIX(to)] = v.dep[SIX(from)];
-    v.vnext[SIX(to)] = v.vnext[SIX(from)]; v.bits[SIX(to)] = v.bits[SIX(from)]; v.pe[SIX(to)] = v.pe[SIX(from)];
+constexpr uint32_t VEV_NONE = 0xFFFFu;
+
+// next VBR event of a source: the smallest positive countdown among its bursts and its next arrival
+__device__ __forceinline__ uint32_t next_vbr_event(const ColdRec &c) {
+    int ev = 0x7FFFFFFF;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v.togo[TGX(j, to)] = v.togo[TGX(j, from)];
+    for (int j = 0; j < MAX_BURSTS; ++j) if (c.togo[j] > 0) ev = min(ev, (int)c.togo[j]);
+    if (c.vnext > 0) ev = min(ev, c.vnext);
+    return ev == 0x7FFFFFFF ? VEV_NONE : (uint32_t)ev;
+}
+__device__ __forceinline__ int active_bursts(const ColdRec &c) {
+    int nb = 0;
+#pragma unroll
+    for (int j = 0; j < MAX_BURSTS; ++j) nb += c.togo[j] != 0;
+    return nb;
+}
+__device__ __forceinline__ void load_cold(const ColdRec *g, ColdRec &c) {
+    const int4 *s = reinterpret_cast<const int4 *>(g);
+    int4 *d = reinterpret_cast<int4 *>(&c);
+    d[0] = s[0]; d[1] = s[1];
+}
+__device__ __forceinline__ void store_cold(ColdRec *g, const ColdRec &c) {
+    const int4 *s = reinterpret_cast<const int4 *>(&c);
+    int4 *d = reinterpret_cast<int4 *>(g);
+    d[0] = s[0]; d[1] = s[1];
+}
+
+__device__ __forceinline__ void smem_move_slot(const SmemView &v, ColdRec *cold, int tid, int from, int to) {
+    v.th[SIX(to)] = v.th[SIX(from)]; v.nominal[SIX(to)] = v.nominal[SIX(from)];
+    v.queue[SIX(to)] = v.queue[SIX(from)]; v.meta[SIX(to)] = v.meta[SIX(from)]; v.vev[SIX(to)] = v.vev[SIX(from)];
+    v.bits[SIX(to)] = v.bits[SIX(from)]; v.pe[SIX(to)] = v.pe[SIX(from)];
+    ColdRec c;
+    load_cold(cold + from, c);
+    store_cold(cold + to, c);
 }
 
 // Rare RAN events of a slot on the shared-memory table; same order as ran_events in embb_fast.cu
 // (slice_ran.py:263-268, slice_l1.py:196-198).  Sets c.flags bit 31 when the unit must abort.
-__device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, int tid, uint32_t k0, uint32_t k1,
+__device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, ColdRec *cold, int tid, uint32_t k0, uint32_t k1,
                                              uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, int slots_cap, RanCtx &c) {
     struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran}, {k0, k1, s, STREAM_CHAN, c.c_chan},
                                                 {k0, k1, s, STREAM_VBR, c.c_vbr}};
@@ -104,9 +130,9 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
         int w = 0;
         uint32_t nd = DEP_NEVER;
         for (int k = 0; k < n_ues; ++k) {
-            const uint32_t d = v.dep[SIX(k)];
+            const uint32_t d = cold[k].dep_at;
             if (d != clock) {
-                if (w != k) smem_move_slot(v, tid, k, w);
+                if (w != k) smem_move_slot(v, cold, tid, k, w);
                 nd = min(nd, d);
                 ++w;
             }
@@ -125,10 +151,15 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
         v.nominal[SIX(k)] = draw_nominal_sinr(rng.chan, p.prop_A, p.prop_B);
         v.meta[SIX(k)] = pack_meta(arr_type[a], fading, step, index);
         const uint32_t dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem;
-        v.dep[SIX(k)] = dep_at;
-        v.vnext[SIX(k)] = arr_vnext[a]; v.bits[SIX(k)] = 0; v.th[SIX(k)] = 0.0; v.queue[SIX(k)] = 0; v.pe[SIX(k)] = 0;
+        ColdRec c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = 0u;
+        for (int j = 0; j < MAX_BURSTS; ++j) c.togo[j] = 0;
+        c.dep_at = dep_at; c.vnext = arr_vnext[a];
+        c.sync = clock - 1u;                                     // its first traffic step happens in this very slot
+        c.pad = 0u;
+        store_cold(cold + k, c);
+        v.vev[SIX(k)] = arr_vnext[a] > 0 ? (uint32_t)arr_vnext[a] : VEV_NONE;
+        v.bits[SIX(k)] = 0; v.th[SIX(k)] = 0.0; v.queue[SIX(k)] = 0; v.pe[SIX(k)] = 0;
         next_dep = min(next_dep, dep_at);
         ++n_ues;
     }
@@ -136,43 +167,39 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
     c.n_ues = n_ues; c.cbr_next = cbr_next; c.vbr_next = vbr_next; c.next_dep = next_dep; c.flags = flags;
 }
 
-// VbrSource.step on the packed burst words of slot k (same semantics as vbr_source_step in embb_device.cuh)
-__device__ __forceinline__ int vbr_step_smem(const SmemView &v, int tid, int k, PhiloxStream &r_vbr, uint32_t &flags) {
-    uint32_t w[4];
-    bool any = false;
+// A VBR source event (VbrSource.step, traffic_generators.py:70-99, evaluated lazily): bring the source's
+// countdowns up to `clock`, retire the bursts that end now (they contribute nothing this slot), then the burst
+// arrival if it is due (the new burst contributes from the next slot).  nb_now = bursts contributing THIS slot,
+// nb = bursts alive afterwards.  Returns the slots until the next event.
+__device__ __noinline__ uint32_t vbr_event(ColdRec *g, uint32_t clock, PhiloxStream &r_vbr, uint32_t &flags, int &nb_now, int &nb) {
+    ColdRec c;
+    load_cold(g, c);
+    const int elapsed = (int)(clock - c.sync);
+    c.sync = clock;
+    int alive = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { w[j] = v.togo[TGX(j, k)]; any |= w[j] != 0u; }
-    int bits = 0;
-    bool dirty = false;
-    if (any) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int lo = (int)(int16_t)(w[j] & 0xFFFFu), hi = (int)(int16_t)(w[j] >> 16);
-            if (lo != 0) { lo = max(lo - 1, -32768); bits += lo != 0 ? 1000 : 0; }
-            if (hi != 0) { hi = max(hi - 1, -32768); bits += hi != 0 ? 1000 : 0; }
-            w[j] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
-        }
-        dirty = true;
+    for (int j = 0; j < MAX_BURSTS; ++j) {
+        int tg = c.togo[j];
+        if (tg > 0) { tg -= elapsed; c.togo[j] = (int16_t)tg; }   // a burst whose length was drawn as 0 stays at -1: it never ends
+        alive += tg != 0;
     }
-    const int vn = v.vnext[SIX(k)] - 1;
-    if (vn == 0) {                                               // burst arrival (traffic_generators.py:92-97)
-        int len = exp_slots(r_vbr, 500.0);
-        if (len == 0) len = -1;                                  // never ends
-        bool placed = false;
+    nb_now = alive;
+    if (c.vnext > 0) {
+        c.vnext -= elapsed;
+        if (c.vnext == 0) {                                      // traffic_generators.py:92-97
+            int len = exp_slots(r_vbr, 500.0);
+            if (len == 0) len = -1;
+            bool placed = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (!placed && (w[j] & 0xFFFFu) == 0u) { w[j] |= (uint32_t)len & 0xFFFFu; placed = true; }
-            if (!placed && (w[j] >> 16) == 0u) { w[j] |= (uint32_t)len << 16; placed = true; }
+            for (int j = 0; j < MAX_BURSTS; ++j)
+                if (!placed && c.togo[j] == 0) { c.togo[j] = (int16_t)len; placed = true; }
+            if (placed) ++alive; else flags |= 2u;
+            c.vnext = exp_slots(r_vbr, 1000.0);                  // a draw of 0 never fires again
         }
-        if (!placed) flags |= 2u;
-        dirty = true;
-        v.vnext[SIX(k)] = exp_slots(r_vbr, 1000.0);
-    } else v.vnext[SIX(k)] = vn;
-    if (dirty) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = w[j];
     }
-    return bits;
+    nb = alive;
+    store_cold(g, c);
+    return next_vbr_event(c);
 }
 
 // x / n for a small positive integer count n, exactly rounded: q = RN(x * RN(1/n)), r = x - q n (exact, FMA),
@@ -184,7 +211,7 @@ __device__ __forceinline__ double div_count(double x, int n) {
     return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
 }
 
-__global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_constant__ StepParams p,
+__global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_constant__ StepParams p,
                                                                 const __grid_constant__ EmbbState st,
                                                                 const __grid_constant__ Tables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -206,7 +233,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     if (tix >= count) return;
     const int u_raw = st.perm[tix];
     const bool pad = u_raw < 0;                                  // idle lane lending its slots to the unit on its left
-    const int slots_cap = tix < 2 * (int)st.hist[2 * SORT_BINS + 3] ? 2 * SM_KS : SM_KS;
+    const int slots_cap = min(st.K, tix < 2 * (int)st.hist[2 * SORT_BINS + 3] ? 2 * SM_KS : SM_KS);
     const int u = pad ? 0 : u_raw;
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
@@ -216,6 +243,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
 
     UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
+    ColdRec *cold = st.cold + (size_t)u * st.K;                  // per-step scratch: committed only if the unit does not abort
     const uint64_t seed = p.seed0 + (uint64_t)env;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     uint32_t c_ran = hdr.ctr[0];
@@ -231,11 +259,14 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         UeRec r;
         load_rec(ue + k, r);
         v.th[SIX(k)] = r.th; v.nominal[SIX(k)] = r.nominal;
-        v.queue[SIX(k)] = (int)r.queue; v.meta[SIX(k)] = r.meta; v.dep[SIX(k)] = r.dep_at; v.vnext[SIX(k)] = r.vnext;
-        v.bits[SIX(k)] = r.bits; v.pe[SIX(k)] = r.pe;
-        const uint32_t *tg = reinterpret_cast<const uint32_t *>(r.togo);
+        v.queue[SIX(k)] = (int)r.queue; v.meta[SIX(k)] = r.meta; v.bits[SIX(k)] = r.bits;
+        ColdRec c;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v.togo[TGX(j, k)] = tg[j];
+        for (int j = 0; j < MAX_BURSTS; ++j) c.togo[j] = r.togo[j];
+        c.dep_at = r.dep_at; c.vnext = r.vnext; c.sync = clock; c.pad = 0u;
+        store_cold(cold + k, c);
+        v.vev[SIX(k)] = (r.meta & 1u) ? next_vbr_event(c) : VEV_NONE;
+        v.pe[SIX(k)] = (r.pe & (int)0xFFFF00FF) | (active_bursts(c) << 8);
         next_dep = min(next_dep, r.dep_at);
         dead |= r.queue >= QUEUE_LIMIT;
     }
@@ -254,7 +285,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         if (!dead) {
             if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
                 RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
-                ran_events_smem(p, v, tid, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], slots_cap, c);
+                ran_events_smem(p, v, cold, tid, k0, k1, (uint32_t)s, t, clock, a_prb[0], a_th[0], slots_cap, c);
                 c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
                 n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
                 if (flags & 0x80000000u) { dead = true; n_ues = 0; }
@@ -269,12 +300,25 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         for (int k = 0; k < n_ues; ++k) {
             uint32_t meta = v.meta[SIX(k)];
             const int ty = (int)(meta & 1u);
-            const int nb_bits = ty == 0 ? 500 : vbr_step_smem(v, tid, k, r_vbr, flags);   // CbrSource: 500 bits every slot
+            int pe = v.pe[SIX(k)];
+            int nb_bits = 500;                                   // CbrSource: 500000 b/s * 1e-3 every slot
+            if (ty) {                                            // VbrSource: 1000 bits per active burst; countdowns only on events
+                int nb_now = (pe >> 8) & 0xF;
+                uint32_t ev = v.vev[SIX(k)];
+                if (ev != VEV_NONE) {
+                    if (--ev == 0u) {
+                        int nb = nb_now;
+                        ev = vbr_event(cold + k, clock, r_vbr, flags, nb_now, nb);
+                        pe = (pe & (int)0xFFFFF0FF) | (nb << 8);
+                    }
+                    v.vev[SIX(k)] = ev;
+                }
+                nb_bits = 1000 * nb_now;
+            }
             a_traffic[ty] += nb_bits;
             const int queue = v.queue[SIX(k)] + nb_bits;
             v.queue[SIX(k)] = queue;
             if (queue >= QUEUE_LIMIT) dead = true;
-            int pe = v.pe[SIX(k)];
             if (n_prbs > 0) {
                 int index = (int)(meta >> 4), step = (meta & 8u) ? 1 : -1;
                 const int fading = (int)((meta >> 1) & 3u);
@@ -295,8 +339,8 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
                 pe = (pe & 0xFFFF) | (e_snr << 16);
-                v.pe[SIX(k)] = pe;
             }
+            v.pe[SIX(k)] = pe;
             // scheduler inputs (schedulers.py:37-45) + the update_info terms that are already final
             const int e = min(max(pe >> 16, -128), 127) + 128;
             v.rm[SIX(k)] = (uint32_t)(uint16_t)s_rate[e] | ((uint32_t)(uint8_t)s_mcs[e] << 16);
@@ -314,7 +358,7 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
         const bool scheduled = n_backlog > 0 && n_prbs > 0;      // queued_data > 0 <=> some queue > 0
         const unsigned sched_mask = __ballot_sync(warp_mask, scheduled);
         if (scheduled) {
-            for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= 0xFFFF0000; }   // ue_bits, ue_rbs
+            for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= (int)0xFFFFFF00; }   // ue_bits, ue_rbs
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
             int r = 0;
             // phase 1: contended chunks (>= 2 backlogged UEs); one uniform loop body for all lanes still in it
@@ -489,17 +533,22 @@ __global__ void __launch_bounds__(SM_THREADS, 3) embb_step_smem(const __grid_con
     }
     // ---- scatter the records back (once per step) and persist the slice scalars
     for (int k = 0; k < n_ues; ++k) {
+        ColdRec c;
+        load_cold(cold + k, c);
+        const int elapsed = (int)(clock - c.sync);               // bring the lazy VBR countdowns up to the end of the step
         UeRec r;
-        r.meta = v.meta[SIX(k)]; r.dep_at = v.dep[SIX(k)]; r.vnext = v.vnext[SIX(k)]; r.bits = v.bits[SIX(k)];
-        r.nominal = v.nominal[SIX(k)]; r.th = v.th[SIX(k)]; r.queue = v.queue[SIX(k)]; r.pe = v.pe[SIX(k)];
-        uint32_t *tg = reinterpret_cast<uint32_t *>(r.togo);
         int nb = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            tg[j] = v.togo[TGX(j, k)];
-            nb += ((tg[j] & 0xFFFFu) != 0u) + ((tg[j] >> 16) != 0u);
+        for (int j = 0; j < MAX_BURSTS; ++j) {
+            int tg = c.togo[j];
+            if (tg > 0) tg -= elapsed;
+            r.togo[j] = (int16_t)tg;
+            nb += tg != 0;
         }
-        r.nb = nb;
+        r.vnext = c.vnext > 0 ? c.vnext - elapsed : c.vnext;
+        r.meta = v.meta[SIX(k)]; r.dep_at = c.dep_at; r.bits = v.bits[SIX(k)];
+        r.nominal = v.nominal[SIX(k)]; r.th = v.th[SIX(k)]; r.queue = v.queue[SIX(k)];
+        r.pe = v.pe[SIX(k)] & (int)0xFFFF00FF; r.nb = nb;
         store_rec(ue + k, r);
     }
     hdr.n_ues = n_ues; hdr.cbr_next = cbr_next; hdr.vbr_next = vbr_next; hdr.clock = clock;
@@ -523,6 +572,7 @@ void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables 
 int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
     static bool configured = false;
     constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
+    static_assert(4 * (smem_bytes + 2048 + 1024) <= 227 * 1024, "4 blocks per SM must fit");
     if (!configured) {
         cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         configured = true;

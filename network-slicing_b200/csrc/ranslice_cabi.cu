@@ -193,12 +193,13 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
-        sc.take<uint32_t>(U); sc.take<int32_t>(2 * U); sc.take<uint32_t>(2 * rs::SORT_BINS + 4); sc.take<uint32_t>(U); sc.take<float>(8);
+        sc.take<uint32_t>(U); sc.take<int32_t>(2 * U); sc.take<uint32_t>(2 * rs::SORT_BINS + 4); sc.take<uint32_t>(U); sc.take<float>(8); sc.take<rs::ColdRec>(U * (size_t)h->embb.K);
         CU(cudaMalloc(&h->scratch, sc.off + 256));
         CU(cudaMemset(h->scratch, 0, sc.off + 256));
         Carver rc; rc.base = h->scratch;
         h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(2 * U);
         h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
+        h->embb.cold = rc.take<rs::ColdRec>(U * (size_t)h->embb.K);
     }
 
     const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;

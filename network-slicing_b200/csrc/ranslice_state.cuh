@@ -35,6 +35,16 @@ struct __align__(16) UeRec {
 };
 static_assert(sizeof(UeRec) == 64, "UeRec must be 64 bytes");
 
+// Cold part of a UE as the shared-memory kernel keeps it during a step (global scratch, embb_smem.cu)
+struct __align__(16) ColdRec {
+    int16_t togo[MAX_BURSTS]; // burst countdowns as of slot `sync`
+    uint32_t dep_at;
+    int32_t vnext;            // countdown to the next burst arrival as of slot `sync` (<= 0: never)
+    uint32_t sync;            // unit clock the countdowns refer to
+    uint32_t pad;
+};
+static_assert(sizeof(ColdRec) == 32, "ColdRec must be 32 bytes");
+
 constexpr uint32_t DEP_NEVER = 0xFFFFFFFFu;
 struct __align__(16) UnitHdr {
     int32_t n_ues;
@@ -56,6 +66,7 @@ struct EmbbState {
     int32_t *perm;         // [2U] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
     uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
     uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
+    ColdRec *cold;         // [U][K] per-step scratch of the shared-memory kernel
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
