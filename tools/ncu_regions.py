@@ -30,7 +30,7 @@ def find(s):
     raise KeyError(s)
 
 
-m = [("kernel prologue + gather", find("__global__ void __launch_bounds__(SM_THREADS, 3)")), ("RAN events check", find("arrivals / departures only on event slots")),
+m = [("kernel prologue + gather", find("__global__ void __launch_bounds__(SM_THREADS,")), ("RAN events check", find("arrivals / departures only on event slots")),
      ("per-UE pass (traffic, walk, mean)", find("per-UE traffic + SNR estimate")), ("PF allocate", find("// ================= scheduling + reception")),
      ("MI loop", find("// ---- MI sums of the served")), ("reception + tx step", find("// ---- per-UE reception")),
      ("unscheduled + update_info", find("nothing touched: stale bits") - 1), ("epilogue", find("if (pad) return;")), ("end", 10 ** 6)]
