@@ -50,6 +50,28 @@ int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action
  * with predict([state_l, l1_prbs / n_prbs]) == +1, or -1 if none.  DEVICE pointers. */
 int kb_predict_device(kb_handle *h, const float *d_state, int32_t *d_first_pos, void *stream);
 
+/* ---- device-resident KBRL_Control (kbrl_control.py:23-114): E-learner accuracies, security factors, margins, adjusted
+ * flag and the current action live in HBM next to the dictionaries, so that the control loop
+ *     new_state, _, _, info = system.step(action); update_control(state, action, info['SLA_labels']);
+ *     action, adjusted = select_action(new_state)                                   (kbrl_control.py:126-134)
+ * runs without a host round trip (rs_step_device -> kb_control_update_device -> kb_control_select_device on one stream).
+ * kb_control_init: KBRL_Control.__init__ (:28-39); initial_action / security_factor [N][S] HOST arrays
+ * (create_kbrl_agent draws them, scenario_creator.py:222-223), accuracies start at (lo + hi) / 2. */
+int kb_control_init(kb_handle *h, const int32_t *initial_action, const int32_t *security_factor, double alfa,
+                    double accuracy_lo, double accuracy_hi);
+/* update_control(state, action, reward = SLA labels) (:80-114) for all learners: prediction at the taken action,
+ * E-learner accuracy update, security factor (unless the last select_action adjusted that env), sample augmentation.
+ * hits [N][S] = (label == prediction), may be NULL.  DEVICE pointers, async on stream. */
+int kb_control_update_device(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels,
+                             int32_t *d_hits, void *stream);
+/* select_action(state) (:41-73) incl. adjust_action (:75-78): action [N][S] and adjusted [N] out (either may be NULL;
+ * both are also kept in the handle).  DEVICE pointers, async on stream. */
+int kb_control_select_device(kb_handle *h, const float *d_state, int32_t *d_action, int32_t *d_adjusted, void *stream);
+/* controller state to HOST buffers (any may be NULL): action / security_factors / margins [N][S], adjusted [N],
+ * accuracies [N][S][n_prbs] */
+int kb_control_get(kb_handle *h, int32_t *action, int32_t *security_factors, int32_t *margins, int32_t *adjusted,
+                   double *accuracies);
+
 /* HOST-buffer convenience wrappers (copy in, run, copy out, synchronise) */
 int kb_update(kb_handle *h, const float *state, const int32_t *action, const int32_t *labels, int32_t *y_pred);
 int kb_predict(kb_handle *h, const float *state, int32_t *first_pos);

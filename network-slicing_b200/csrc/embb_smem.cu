@@ -219,10 +219,15 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
     __shared__ int8_t s_mcs[256];
     __shared__ float s_ref[26];
     __shared__ int8_t s_mod[26];
+    __shared__ float s_mi[3][4];                                 // per modulation: k, x0, c1 = -k log2(e), c0 = k x0 log2(e)  (fp32 MI fast path)
     __shared__ float s_inv[2 * TRACE_ROWS + 1];                  // 1 / n for the MI mean (fp32 fast path, inside the eps budget)
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += SM_THREADS) { s_rate[i] = tb.lut_rate[i]; s_mcs[i] = tb.lut_mcs[i]; }
     if (tid < 26) { s_ref[tid] = (float)tb.snr_ref[tid]; s_mod[tid] = tb.mod[tid]; }
+    if (tid < 3) {
+        const float kf = (float)c_MI_K[tid], x0f = (float)c_MI_X0[tid];
+        s_mi[tid][0] = kf; s_mi[tid][1] = x0f; s_mi[tid][2] = -kf * LOG2E_F; s_mi[tid][3] = kf * x0f * LOG2E_F;
+    }
     for (int i = tid; i <= 2 * TRACE_ROWS; i += SM_THREADS) s_inv[i] = i ? __frcp_rn((float)i) : 0.f;
     __syncthreads();
     const SmemView v = carve_smem(smem_raw);
@@ -436,8 +441,7 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                         left = ((hi - 1) >> 2) - q + 1;
                         const uint32_t meta = v.meta[SIX(k)];
                         const int m = s_mod[v.rm[SIX(k)] >> 16];
-                        const float kf = (float)c_MI_K[m], x0f = (float)c_MI_X0[m];
-                        c1 = -kf * LOG2E_F; c0 = kf * x0f * LOG2E_F; nf = (float)v.nominal[SIX(k)];
+                        c1 = s_mi[m][2]; c0 = s_mi[m][3]; nf = (float)v.nominal[SIX(k)];
                         col4 = reinterpret_cast<const int4 *>(tb.trace_q24 + ((int)((meta >> 1) & 3u) * N_SAMPLES + (int)(meta >> 4)) * TRACE_ROWS);
                         msum = 0.0;
                     }
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                             else if (m <= 1e-4f) received = false;           // p < 2^-53
                             else {
                                 const int md = s_mod[mcs];
-                                const float kf = (float)c_MI_K[md], x0f = (float)c_MI_X0[md];
+                                const float kf = s_mi[md][0], x0f = s_mi[md][1];
                                 const float rr = rcp_approx(m) - 1.0f;
                                 const float seff = x0f - __logf(rr) / kf;   // inv_sigmoid, channel_models.py:39-41
                                 const float L = Af * (seff - s_ref[mcs]) - Bf;

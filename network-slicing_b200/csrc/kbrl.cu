@@ -42,6 +42,17 @@ struct State {
     unsigned long long *updates;   // [1]
 };
 
+// Device-resident KBRL_Control state (kbrl_control.py:28-39); acc == nullptr while kb_control_init has not been called
+struct Control {
+    double *acc;       // [L][n_prbs] E-learner accuracies
+    int32_t *sec;      // [L] security_factors
+    int32_t *margins;  // [L]
+    int32_t *adjusted; // [N] self.adjusted of the last select_action
+    int32_t *action;   // [L] self.action
+    int32_t *first;    // [L] scratch: first allocation predicted +1 (select_action scan)
+    double alfa, acc_lo;
+};
+
 // state part of ((l - x)**2).sum() in numpy's pairwise order (action coordinate excluded; it is added last)
 __device__ __forceinline__ double base_dist(const double *l, const double *x, int ns) {
     if (ns < 8) {                                   // n = ns + 1 < 8 or exactly the sequential tail below
@@ -113,13 +124,14 @@ __global__ void __launch_bounds__(THREADS) predict_kernel(const State kb, const 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const float *__restrict__ state,
                                                          const int32_t *__restrict__ action,
-                                                         const int32_t *__restrict__ labels, int32_t *y_pred) {
+                                                         const int32_t *__restrict__ labels, int32_t *y_pred,
+                                                         const Control ctl, int32_t *hits) {
     extern __shared__ __align__(16) unsigned char raw[];
     double *base, *cf, *ll, *kf, *ds, *fval;
     carve(raw, kb.cap, base, cf, ll, kf, ds, fval);
     __shared__ double xs[MAX_DIM];
     __shared__ double s_delta;
-    __shared__ int s_first, s_D;
+    __shared__ int s_first, s_D, s_sf;
     const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs, cap = kb.cap;
     if (threadIdx.x < d - 1) xs[threadIdx.x] = (double)state[(size_t)env * kb.V + kb.offs[s] + threadIdx.x];
     const int y = labels[l];
@@ -144,8 +156,30 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
         }
         __syncthreads();
         if (first_round) {                                     // the predict of kbrl_control.py:89 (before any update)
-            if (threadIdx.x == 0) { const double f = fval[a0]; y_pred[l] = D == 0 ? 0 : (f > 0.0 ? 1 : -1); }
+            const int yp = D == 0 ? 0 : (fval[a0] > 0.0 ? 1 : -1);
+            if (threadIdx.x == 0 && y_pred) y_pred[l] = yp;
             first_round = false;
+            if (ctl.acc) {                                     // E-learner part of update_control (kbrl_control.py:90-101)
+                const bool hit = y == yp;
+                const int margin = max(0, ctl.margins[l]);
+                const double om = 1.0 - ctl.alfa;
+                double *acc = ctl.acc + (size_t)l * n;
+                if (threadIdx.x == 0) s_sf = 1 << 30;
+                __syncthreads();
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    double v = acc[i];
+                    if (yp == 1) {
+                        if (!hit) { if (i <= margin) { v = om * v; acc[i] = v; } }            // same or less margin: same mistake
+                        else if (i >= margin) { v = om * v + ctl.alfa; acc[i] = v; }          // same or more margin: same success
+                    }
+                    if (v > ctl.acc_lo) atomicMin(&s_sf, i);   // np.argmax(accuracies > accuracy_range[0]): first True, 0 if none
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    if (!ctl.adjusted[env]) ctl.sec[l] = s_sf == (1 << 30) ? 0 : s_sf;
+                    if (hits) hits[l] = hit ? 1 : 0;
+                }
+            }
         }
         const int astar = s_first;
         if (astar == (1 << 30)) break;
@@ -223,12 +257,41 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
     }
 }
 
+// Tail of KBRL_Control.select_action (kbrl_control.py:57-73) + adjust_action (:75-78); one thread per env.
+__global__ void select_kernel(const State kb, const Control ctl, int32_t *action_out, int32_t *adjusted_out) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env * kb.S >= kb.L) return;
+    const int n = kb.n_prbs, S = kb.S;
+    int a[8], m[8], assigned = 0;
+    for (int s = 0; s < S; ++s) {
+        const int l = env * S + s, first = ctl.first[l];
+        if (first >= 0) { a[s] = min(n, first + ctl.sec[l]); m[s] = a[s] - first; }
+        else { a[s] = n; m[s] = 0; }                            // the scan ran out: l1_prbs = n_prbs, margin 0
+        assigned += a[s];
+    }
+    const int adj = assigned > n;
+    for (int s = 0; s < S; ++s) {
+        const int l = env * S + s;
+        int act = a[s], mar = m[s];
+        if (adj) {
+            const double p = (double)a[s] / (double)assigned;
+            act = (int)floor((double)n * p);
+            mar -= a[s] - act;
+        }
+        ctl.action[l] = act; ctl.margins[l] = mar;
+        if (action_out) action_out[l] = act;
+    }
+    ctl.adjusted[env] = adj;
+    if (adjusted_out) adjusted_out[env] = adj;
+}
+
 }  // namespace kb
 
 // ================================================================================================= C ABI
 struct kb_handle {
     kb_config cfg;
     kb::State st;
+    kb::Control ctl;
     size_t smem_bytes;
     cudaStream_t stream;
     float *d_state;
@@ -267,6 +330,7 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     KCU(cudaSetDevice(cfg->device));
     kb_handle *h = new kb_handle();
     h->cfg = *cfg; h->cfg.dict_cap = cap; h->launches = 0;
+    h->ctl = kb::Control{};
     kb::State &st = h->st;
     st.L = cfg->n_envs * cfg->n_slices; st.S = cfg->n_slices; st.V = cfg->n_variables; st.n_prbs = cfg->n_prbs; st.cap = cap;
     st.gamma = cfg->gamma; st.eta = cfg->eta;
@@ -304,6 +368,8 @@ int kb_destroy(kb_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(h->st.D); cudaFree(h->st.lm); cudaFree(h->st.coeff); cudaFree(h->st.kinv); cudaFree(h->st.flags);
+    cudaFree(h->ctl.acc); cudaFree(h->ctl.sec); cudaFree(h->ctl.margins); cudaFree(h->ctl.adjusted); cudaFree(h->ctl.action);
+    cudaFree(h->ctl.first);
     cudaFree(h->st.updates); cudaFree(h->d_state); cudaFree(h->d_action); cudaFree(h->d_labels); cudaFree(h->d_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -316,9 +382,73 @@ int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action
     KCU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, d_y_pred);
+    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, d_y_pred, kb::Control{}, nullptr);
     h->launches += 1;
     KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+int kb_control_init(kb_handle *h, const int32_t *initial_action, const int32_t *security_factor, double alfa,
+                    double accuracy_lo, double accuracy_hi) {
+    if (!h || !initial_action || !security_factor) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    const size_t L = (size_t)h->st.L, n = (size_t)h->st.n_prbs;
+    kb::Control &c = h->ctl;
+    if (!c.acc) {
+        KCU(cudaMalloc(&c.acc, L * n * sizeof(double)));
+        KCU(cudaMalloc(&c.sec, L * sizeof(int32_t)));
+        KCU(cudaMalloc(&c.margins, L * sizeof(int32_t)));
+        KCU(cudaMalloc(&c.adjusted, (size_t)h->cfg.n_envs * sizeof(int32_t)));
+        KCU(cudaMalloc(&c.action, L * sizeof(int32_t)));
+        KCU(cudaMalloc(&c.first, L * sizeof(int32_t)));
+    }
+    c.alfa = alfa; c.acc_lo = accuracy_lo;
+    std::vector<double> acc(L * n, (accuracy_lo + accuracy_hi) / 2);               // kbrl_control.py:38-39
+    KCU(cudaMemcpy(c.acc, acc.data(), acc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    KCU(cudaMemcpy(c.sec, security_factor, L * sizeof(int32_t), cudaMemcpyHostToDevice));
+    KCU(cudaMemcpy(c.action, initial_action, L * sizeof(int32_t), cudaMemcpyHostToDevice));
+    KCU(cudaMemset(c.margins, 0, L * sizeof(int32_t)));
+    KCU(cudaMemset(c.adjusted, 0, (size_t)h->cfg.n_envs * sizeof(int32_t)));
+    return RS_OK;
+}
+
+int kb_control_update_device(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels,
+                             int32_t *d_hits, void *stream) {
+    if (!h || !d_state || !d_action || !d_labels) return kfail(RS_E_ARG, "null argument");
+    if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
+    KCU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
+    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, nullptr, h->ctl, d_hits);
+    h->launches += 1;
+    KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+int kb_control_select_device(kb_handle *h, const float *d_state, int32_t *d_action, int32_t *d_adjusted, void *stream) {
+    if (!h || !d_state) return kfail(RS_E_ARG, "null argument");
+    if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
+    KCU(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    kb::predict_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, h->ctl.first);
+    kb::select_kernel<<<(h->cfg.n_envs + 127) / 128, 128, 0, st>>>(h->st, h->ctl, d_action, d_adjusted);
+    h->launches += 2;
+    KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+int kb_control_get(kb_handle *h, int32_t *action, int32_t *security_factors, int32_t *margins, int32_t *adjusted,
+                   double *accuracies) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    const size_t L = (size_t)h->st.L;
+    if (action) KCU(cudaMemcpy(action, h->ctl.action, L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (security_factors) KCU(cudaMemcpy(security_factors, h->ctl.sec, L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (margins) KCU(cudaMemcpy(margins, h->ctl.margins, L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (adjusted) KCU(cudaMemcpy(adjusted, h->ctl.adjusted, (size_t)h->cfg.n_envs * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (accuracies) KCU(cudaMemcpy(accuracies, h->ctl.acc, L * h->st.n_prbs * sizeof(double), cudaMemcpyDeviceToHost));
     return RS_OK;
 }
 

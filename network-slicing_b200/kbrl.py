@@ -41,11 +41,16 @@ def _bind(L):
     L.kb_predict.argtypes = [vp] * 3
     L.kb_update_device.argtypes = [vp] * 6
     L.kb_predict_device.argtypes = [vp] * 4
+    L.kb_control_init.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_double]
+    L.kb_control_update_device.argtypes = [vp] * 6
+    L.kb_control_select_device.argtypes = [vp] * 5
+    L.kb_control_get.argtypes = [vp] * 6
     L.kb_get_sizes.argtypes = [vp, vp, vp]
     L.kb_get_learner.argtypes = [vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.kb_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     for n in ("kb_create", "kb_destroy", "kb_reset", "kb_update", "kb_predict", "kb_update_device", "kb_predict_device",
-              "kb_get_sizes", "kb_get_learner", "kb_get_counters"):
+              "kb_get_sizes", "kb_get_learner", "kb_get_counters", "kb_control_init", "kb_control_update_device",
+              "kb_control_select_device", "kb_control_get"):
         getattr(L, n).restype = C.c_int
     L._kb_bound = True
     return L
@@ -56,7 +61,7 @@ class BatchedProjectron:
 
     def __init__(self, scenario, n_envs, dict_cap=256, device=0, gamma=1.0, eta=0.1):
         sc = scenarios[scenario] if isinstance(scenario, int) else scenario
-        self.n_envs, self.n_prbs = n_envs, sc['n_prbs']
+        self.n_envs, self.n_prbs, self.device = n_envs, sc['n_prbs'], device
         n_embb, n_mmtc = sc['n_embb'], sc['n_mmtc']
         self.n_slices = n_embb + n_mmtc
         self.dims = np.array([len(state_variables_embb) + 1] * n_embb + [len(state_variables_mmtc) + 1] * n_mmtc, np.int32)
@@ -208,7 +213,99 @@ class KBRLControl:
                 'adjusted': adjusted_actions, 'SLA': SLA_history, 'violation': violation_history}
 
 
-def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=256, device=0):
+class DeviceKBRLControl:
+    """``KBRL_Control`` with ALL controller state resident on the GPU (kb_control_* in include/kbrl_b200.h):
+    ``update_control`` / ``select_action`` take and return torch CUDA tensors and enqueue kernels on the current
+    stream; ``run`` drives a :class:`BatchedRanSlice` through ``step_device`` with no host round trip per step."""
+
+    def __init__(self, learners, n_prbs, initial_action, security_factor, alfa=0.05, accuracy_range=(0.99, 0.999)):
+        import torch
+        self.learners = learners
+        self.accuracy_range = list(accuracy_range)
+        self.n_envs, self.n_slices, self.n_prbs, self.alfa = learners.n_envs, learners.n_slices, n_prbs, alfa
+        N, S = self.n_envs, self.n_slices
+        ia = np.ascontiguousarray(np.broadcast_to(np.asarray(initial_action, np.int32), (N, S)))
+        sec = np.ascontiguousarray(np.broadcast_to(np.asarray(security_factor, np.int32), (N, S)))
+        self._L, self._h = learners._L, learners._h
+        _lib.check(self._L.kb_control_init(self._h, _p(ia), _p(sec), float(alfa), float(accuracy_range[0]),
+                                           float(accuracy_range[1])))
+        self.device = torch.device("cuda", learners.device)
+        self.action = torch.from_numpy(ia.copy()).to(self.device)
+        self.adjusted = torch.zeros(N, dtype=torch.int32, device=self.device)
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def select_action(self, state, action_out=None, adjusted_out=None):
+        """state float32 CUDA [N,V] -> (action int32 CUDA [N,S], adjusted int32 CUDA [N]) (kbrl_control.py:41-78)."""
+        import torch
+        assert state.is_cuda and state.dtype == torch.float32 and state.is_contiguous()
+        a = action_out if action_out is not None else torch.empty((self.n_envs, self.n_slices), dtype=torch.int32, device=self.device)
+        adj = adjusted_out if adjusted_out is not None else torch.empty(self.n_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self._L.kb_control_select_device(self._h, C.c_void_p(state.data_ptr()), C.c_void_p(a.data_ptr()),
+                                                    C.c_void_p(adj.data_ptr()), self._stream()))
+        self.action, self.adjusted = a, adj
+        return a, adj
+
+    def update_control(self, state, action, reward, hits_out=None):
+        """(state f32 [N,V], action i32 [N,S], SLA labels i32 [N,S]) CUDA -> hits int32 CUDA [N,S] (kbrl_control.py:80-114)."""
+        import torch
+        for t, dt in ((state, torch.float32), (action, torch.int32), (reward, torch.int32)):
+            assert t.is_cuda and t.dtype == dt and t.is_contiguous()
+        hits = hits_out if hits_out is not None else torch.empty((self.n_envs, self.n_slices), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.kb_control_update_device(self._h, C.c_void_p(state.data_ptr()), C.c_void_p(action.data_ptr()),
+                                                    C.c_void_p(reward.data_ptr()), C.c_void_p(hits.data_ptr()), self._stream()))
+        return hits
+
+    def control_state(self):
+        """Host copies: dict(action, security_factors, margins [N,S], adjusted [N], accuracies [N,S,n_prbs])."""
+        N, S = self.n_envs, self.n_slices
+        out = dict(action=np.empty((N, S), np.int32), security_factors=np.empty((N, S), np.int32),
+                   margins=np.empty((N, S), np.int32), adjusted=np.empty(N, np.int32),
+                   accuracies=np.empty((N, S, self.n_prbs), np.float64))
+        _lib.check(self._L.kb_control_get(self._h, _p(out["action"]), _p(out["security_factors"]), _p(out["margins"]),
+                                          _p(out["adjusted"]), _p(out["accuracies"])))
+        return out
+
+    def run(self, system, steps, learning_time=-1):
+        """kbrl_control.py:116-157 against a :class:`BatchedRanSlice`, everything on the device; the histories
+        (leading env axis) are accumulated in HBM and copied to the host once at the end."""
+        import torch
+        N, S, dev = self.n_envs, self.n_slices, self.device
+        i16 = dict(dtype=torch.int16, device=dev)
+        SLA_history = torch.zeros((steps, N), **i16)
+        reward_history = torch.zeros((steps, N), dtype=torch.float64, device=dev)
+        violation_history = torch.zeros((steps, N), **i16)
+        adjusted_actions = torch.zeros((steps, N), **i16)
+        resources_history = torch.zeros((steps, N), **i16)
+        hits_history = torch.zeros((steps, N, S), **i16)
+        system.reset()
+        state = torch.zeros((N, system.n_variables), dtype=torch.float32, device=dev)      # reset() returns zeros
+        bufs = [None, None]                                                                 # two output sets (state / new_state)
+        action = self.action
+        hits = torch.zeros((N, S), dtype=torch.int32, device=dev)
+        for i in range(steps):
+            out = system.step_device(action, bufs[i & 1])
+            bufs[i & 1] = out
+            if learning_time < steps:
+                self.update_control(state, action, out['labels'], hits_out=hits)
+            nxt = torch.empty_like(action)
+            action, _ = self.select_action(out['obs'], action_out=nxt, adjusted_out=self.adjusted)
+            state = out['obs']
+            SLA_history[i] = out['labels'].sum(dim=1)
+            reward_history[i] = out['reward']
+            violation_history[i] = out['violations'].sum(dim=1)
+            resources_history[i] = action.sum(dim=1)
+            adjusted_actions[i] = self.adjusted
+            hits_history[i] = hits
+        torch.cuda.synchronize(dev)
+        t = lambda x: x.transpose(0, 1).cpu().numpy()
+        return {'reward': t(reward_history), 'resources': t(resources_history), 'hits': hits_history.permute(1, 2, 0).cpu().numpy(),
+                'adjusted': t(adjusted_actions), 'SLA': t(SLA_history), 'violation': t(violation_history)}
+
+
+def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=256, device=0, resident=False):
     """``scenario_creator.create_kbrl_agent`` (scenario_creator.py:197-238): random initial action and security
     factor per learner (drawn per env from ``rng`` in the reference's order), gamma = 1, eta = 0.1."""
     sc = scenarios[n]
@@ -221,4 +318,6 @@ def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=2
         for s in range(n_embb, n_embb + n_mmtc):
             ia[e, s] = rng.integers(mmtc_a[0], mmtc_a[1]); sec[e, s] = rng.integers(mmtc_sec[0], mmtc_sec[1])
     learners = BatchedProjectron(n, n_envs, dict_cap=dict_cap, device=device)
+    if resident:        # controller state on the GPU, torch tensors in / out (no host round trip per step)
+        return DeviceKBRLControl(learners, sc['n_prbs'], ia, sec, alfa=alfa, accuracy_range=accuracy_range)
     return KBRLControl(learners, sc['n_prbs'], ia, sec, alfa=alfa, accuracy_range=accuracy_range)

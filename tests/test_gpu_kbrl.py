@@ -90,3 +90,52 @@ def test_kbrl_in_the_loop_with_the_env():
     assert out["hits"].shape == (N, 5, 40) and (out["resources"] <= 200).all()
     assert agent.learners.sizes()[0].max() > 2
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------ device-resident controller
+def _device_control(g, n_envs=1, dict_cap=256):
+    from ranslice_b200.kbrl import BatchedProjectron, DeviceKBRLControl
+    lrn = BatchedProjectron(int(g["scenario"]), n_envs, dict_cap=dict_cap)
+    return DeviceKBRLControl(lrn, int(g["n_prbs"]), g["init_action"], g["init_sec"], alfa=float(g["alfa"]),
+                             accuracy_range=tuple(g["accuracy_range"]))
+
+
+@pytest.mark.parametrize("name", ["K_scn0", "K_scn1"])
+def test_device_controller_replays_reference_fixture(golden, name):
+    """kb_control_update_device / kb_control_select_device (controller state in HBM) vs the unmodified reference
+    KBRL_Control, step by step: hits, next action, adjusted flag, security factors, margins, accuracies."""
+    import torch
+    g = golden(name)
+    ctl = _device_control(g)
+    dev = ctl.device
+    tt = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a[None]).astype(dt)).to(dev)
+    for t in range(len(g["state"])):
+        hits = ctl.update_control(tt(g["state"][t], np.float32), tt(g["action"][t], np.int32), tt(g["labels"][t], np.int32))
+        assert np.array_equal(hits.cpu().numpy()[0], g["hits"][t]), t
+        a, adj = ctl.select_action(tt(g["new_state"][t], np.float32))
+        assert np.array_equal(a.cpu().numpy()[0], g["next_action"][t]) and int(adj[0]) == g["adjusted"][t], t
+        if t % 25 == 0 or t == len(g["state"]) - 1:
+            cs = ctl.control_state()
+            assert np.array_equal(cs["security_factors"][0], g["security_factors"][t]), t
+            assert np.array_equal(cs["margins"][0], g["margins"][t]), t
+            assert np.array_equal(ctl.learners.sizes()[0][0], g["sizes"][t]), t
+    assert np.allclose(ctl.control_state()["accuracies"][0], g["accuracies"], rtol=0, atol=1e-15)
+
+
+def test_device_controller_matches_host_mirror_in_the_loop():
+    """run() of the device-resident controller == run() of the numpy mirror on the same envs and seeds
+    (the mirror is pinned to the oracle / reference above): every history array is identical."""
+    from ranslice_b200 import create_batched_env
+    from ranslice_b200.kbrl import create_kbrl_agent
+    N, T = 48, 60
+    outs = []
+    for resident in (False, True):
+        env = create_batched_env(123, 0, N)
+        agent = create_kbrl_agent(np.random.default_rng(5), 0, accuracy_range=(0.97, 0.99), n_envs=N, dict_cap=128,
+                                  resident=resident)
+        outs.append((agent.run(env, T), agent.learners.sizes()[0].copy()))
+        env.close()
+    (a, sa), (b, sb) = outs
+    for k in a:
+        assert np.array_equal(np.asarray(a[k], np.float64), np.asarray(b[k], np.float64)), k
+    assert np.array_equal(sa, sb) and sa.max() > 2
