@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libranslice_b200.so")
+SO_PATH = os.environ.get("RS_B200_LIB") or os.path.join(_PKG, "libranslice_b200.so")   # RS_B200_LIB: experiment builds (tools/sweep_variants.sh)
 
 RS_ABI_VERSION = 1
 FLAG_UE_CAP, FLAG_BURST_CAP, FLAG_ACTION_CLAMP, FLAG_SAME_SLOT_DEP, FLAG_MTC_QUEUE_CAP = 1, 2, 4, 8, 16

@@ -30,7 +30,9 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "ranslice_b200.h"))
     headers.append(os.path.join(os.path.dirname(PKG), "include", "kbrl_b200.h"))
-    objdir = os.path.join(PKG, "build")
+    tag = os.environ.get("RS_BUILD_TAG", "")                # experiment builds: separate objects, lib<tag>.so next to the real one
+    out = OUT if not tag else OUT.replace(".so", "_%s.so" % tag)
+    objdir = os.path.join(PKG, "build" + ("_" + tag if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = [os.path.join(objdir, s.replace(".cu", ".o")) for s in srcs]
@@ -48,8 +50,8 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(4) as ex:
         list(ex.map(compile_one, zip(srcs, objs)))
-    if force or _stale(OUT, objs):
-        cmd = [_nvcc(), "-shared", "-o", OUT] + objs + ["-lcudart"]
+    if force or _stale(out, objs):
+        cmd = [_nvcc(), "-shared", "-o", out] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
@@ -59,7 +61,7 @@ def build(force=False, verbose=False):
     with open(os.path.join(objdir, "ptxas.log"), "a") as f:
         for s, l in logs.items():
             f.write("== %s\n%s\n" % (s, l))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -14,8 +14,8 @@
 //    fp64 re-evaluation) are NOT re-merged by the hardware on their own (measured: lanes of one warp
 //    working on different TTIs).
 //  * the window mean behind round(np.mean(snr)) (slice_ran.py:43-45) is an exact int64 sum over a
-//    2^-24 fixed-point copy of the traces, read as aligned 128-bit quads with the two end quads
-//    masked; only when the mean lies within 1e-6 of a rounding boundary is it recomputed in fp64.
+//    2^-22 fixed-point copy of the traces, read as aligned 128-bit quads with the two end quads
+//    masked; only when the mean lies within SNR_ROUND_GUARD (2e-6) of a rounding boundary is it recomputed in fp64.
 //  * the MI-effective-SNR reception probability (channel_models.py:297-313) is evaluated in fp32
 //    (ex2/rcp/lg2 SFU ops) together with a bound eps on |p32 - p64|; the Bernoulli decision
 //    u < p (slice_l1.py:223) is taken from p32 unless |u - p32| <= eps, in which case p is
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
     unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
     const float Af = (float)tb.A, Bf = (float)tb.B;
-    const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * 16777216.0) : 0.0;
+    const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * FIX_ONE) : 0.0;
 
     // per-UE scratch of one TTI (local memory, only the first n_ues entries are touched)
     long long qq[K];
@@ -272,14 +272,14 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
                 r.meta = pack_meta((int)(r.meta & 1u), fading, step, index);
                 const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
                 coloff[k] = col_off;
-                const long long isum = window_sum_q24(tb.trace_q24 + col_off, row_base, n_prbs);
+                const long long isum = window_sum_fix(tb.trace_fix + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
                 double mean = (double)isum * inv_n + r.nominal;  // |mean - reference mean| < 2^-25 + few ulp
                 const double fr = mean - floor(mean);
-                const bool near = fabs(fr - 0.5) < 1e-6;         // within the guard of a rounding boundary
+                const bool near = fabs(fr - 0.5) < SNR_ROUND_GUARD;         // within the guard of a rounding boundary
                 if (near || p.debug_check) {
                     const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, r.nominal);
-                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / 1e-6));
+                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / SNR_ROUND_GUARD));
                     if (near) { mean = exact; ++slow_snr; }
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
                         const int m = s_mod[mcs[k]];
                         const float kf = (float)c_MI_K[m], x0f = (float)c_MI_X0[m];
                         c1 = -kf * LOG2E_F; c0 = kf * x0f * LOG2E_F; nf = nomf[k];
-                        col4 = reinterpret_cast<const int4 *>(tb.trace_q24 + coloff[k]);
+                        col4 = reinterpret_cast<const int4 *>(tb.trace_fix + coloff[k]);
                         msum = 0.0;
                     }
                     int qq4 = q;
@@ -396,10 +396,10 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
                     const int b = q << 2;
                     float part = 0.f;
                     {
-                        const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.x, Q24_SCALE, nf), c1, c0));
-                        const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.y, Q24_SCALE, nf), c1, c0));
-                        const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.z, Q24_SCALE, nf), c1, c0));
-                        const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.w, Q24_SCALE, nf), c1, c0));
+                        const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.x, FIX_SCALE, nf), c1, c0));
+                        const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.y, FIX_SCALE, nf), c1, c0));
+                        const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.z, FIX_SCALE, nf), c1, c0));
+                        const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)v.w, FIX_SCALE, nf), c1, c0));
                         const float m0 = rcp_approx(1.0f + e0), m1 = rcp_approx(1.0f + e1);
                         const float m2 = rcp_approx(1.0f + e2), m3 = rcp_approx(1.0f + e3);
                         part += (b + 0 >= lo && b + 0 < hi) ? m0 : 0.f;

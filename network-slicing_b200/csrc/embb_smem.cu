@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
     double a_queue_c = 0.0, a_queue_v = 0.0, a_snr_c = 0.0, a_snr_v = 0.0;
     unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
     const float Af = (float)tb.A, Bf = (float)tb.B;
-    const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * 16777216.0) : 0.0;
+    const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * FIX_ONE) : 0.0;
 
     for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
         __syncwarp(warp_mask);
@@ -333,15 +333,15 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                 meta = pack_meta(ty, fading, step, index);
                 v.meta[SIX(k)] = meta;
                 const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
-                const long long isum = window_sum_q24(tb.trace_q24 + col_off, row_base, n_prbs);
+                const long long isum = window_sum_fix(tb.trace_fix + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
                 const double nominal = v.nominal[SIX(k)];
                 double mean = (double)isum * inv_n + nominal;    // |mean - reference mean| < 2^-25 + few ulp
                 const double fr = mean - floor(mean);
-                const bool near = fabs(fr - 0.5) < 1e-6;         // within the guard of a rounding boundary
+                const bool near = fabs(fr - 0.5) < SNR_ROUND_GUARD;         // within the guard of a rounding boundary
                 if (near || p.debug_check) {
                     const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, nominal);
-                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / 1e-6));
+                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / SNR_ROUND_GUARD));
                     if (near) { mean = exact; ++slow_snr; }
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
@@ -442,23 +442,50 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                         const uint32_t meta = v.meta[SIX(k)];
                         const int m = s_mod[v.rm[SIX(k)] >> 16];
                         c1 = s_mi[m][2]; c0 = s_mi[m][3]; nf = (float)v.nominal[SIX(k)];
-                        col4 = reinterpret_cast<const int4 *>(tb.trace_q24 + ((int)((meta >> 1) & 3u) * N_SAMPLES + (int)(meta >> 4)) * TRACE_ROWS);
+                        col4 = reinterpret_cast<const int4 *>(tb.trace_fix + ((int)((meta >> 1) & 3u) * N_SAMPLES + (int)(meta >> 4)) * TRACE_ROWS);
                         msum = 0.0;
                     }
+#ifndef RS_MI_V1
+                    // two quads per iteration (independent load -> ex2 -> rcp chains); a second quad past the UE's last one
+                    // is masked out by the `< hi` tests below (its rows are >= hi) and its load wraps inside the column
+                    const int qa = wrap_quad(q), qb = qa + 1 == QUADS_PER_COL ? 0 : qa + 1;
+                    const int4 x = LDQ_D(col4 + qa), y = LDQ_D(col4 + qb);
+                    const int b = q << 2;
+                    const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, FIX_SCALE, nf), c1, c0));
+                    const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, FIX_SCALE, nf), c1, c0));
+                    const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, FIX_SCALE, nf), c1, c0));
+                    const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.w, FIX_SCALE, nf), c1, c0));
+                    const float e4 = ex2_approx(__fmaf_rn(__fmaf_rn((float)y.x, FIX_SCALE, nf), c1, c0));
+                    const float e5 = ex2_approx(__fmaf_rn(__fmaf_rn((float)y.y, FIX_SCALE, nf), c1, c0));
+                    const float e6 = ex2_approx(__fmaf_rn(__fmaf_rn((float)y.z, FIX_SCALE, nf), c1, c0));
+                    const float e7 = ex2_approx(__fmaf_rn(__fmaf_rn((float)y.w, FIX_SCALE, nf), c1, c0));
+                    float part = (b + 0 >= lo && b + 0 < hi) ? rcp_approx(1.0f + e0) : 0.f;
+                    part += (b + 1 >= lo && b + 1 < hi) ? rcp_approx(1.0f + e1) : 0.f;
+                    part += (b + 2 >= lo && b + 2 < hi) ? rcp_approx(1.0f + e2) : 0.f;
+                    part += (b + 3 >= lo && b + 3 < hi) ? rcp_approx(1.0f + e3) : 0.f;
+                    msum += (double)part;
+                    float part2 = (b + 4 < hi) ? rcp_approx(1.0f + e4) : 0.f;
+                    part2 += (b + 5 < hi) ? rcp_approx(1.0f + e5) : 0.f;
+                    part2 += (b + 6 < hi) ? rcp_approx(1.0f + e6) : 0.f;
+                    part2 += (b + 7 < hi) ? rcp_approx(1.0f + e7) : 0.f;
+                    msum += (double)part2;
+                    q += 2; left = max(left - 2, 0);
+#else
                     int qq4 = q;
                     while (qq4 >= QUADS_PER_COL) qq4 -= QUADS_PER_COL;
                     const int4 x = LDQ_D(col4 + qq4);
                     const int b = q << 2;
-                    const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, Q24_SCALE, nf), c1, c0));
-                    const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, Q24_SCALE, nf), c1, c0));
-                    const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, Q24_SCALE, nf), c1, c0));
-                    const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.w, Q24_SCALE, nf), c1, c0));
+                    const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, FIX_SCALE, nf), c1, c0));
+                    const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, FIX_SCALE, nf), c1, c0));
+                    const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, FIX_SCALE, nf), c1, c0));
+                    const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.w, FIX_SCALE, nf), c1, c0));
                     float part = (b + 0 >= lo && b + 0 < hi) ? rcp_approx(1.0f + e0) : 0.f;
                     part += (b + 1 >= lo && b + 1 < hi) ? rcp_approx(1.0f + e1) : 0.f;
                     part += (b + 2 >= lo && b + 2 < hi) ? rcp_approx(1.0f + e2) : 0.f;
                     part += (b + 3 >= lo && b + 3 < hi) ? rcp_approx(1.0f + e3) : 0.f;
                     msum += (double)part;
                     ++q; --left;
+#endif
                 }
             }
             // ---- per-UE reception (schedulers.py:66-76, slice_l1.py:219-224) + transmission_step (slice_ran.py:51-55)

@@ -42,7 +42,7 @@ struct rs_handle {
     size_t arena_bytes;
     // tables + I/O staging
     double *d_trace;
-    int32_t *d_trace_q24;
+    int32_t *d_trace_fix;
     char *scratch;
     unsigned long long *d_slow_paths;
     int32_t *d_action;
@@ -177,19 +177,19 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     const size_t n_trace = (size_t)3 * rs::N_SAMPLES * rs::TRACE_ROWS;
     CU(cudaMalloc(&h->d_trace, n_trace * sizeof(double)));
     CU(cudaMemcpy(h->d_trace, tables->trace, n_trace * sizeof(double), cudaMemcpyHostToDevice));
-    {   // 2^-24 fixed-point copy (|v| < 128 dB): exact integer window sums on the fast path
-        std::vector<int32_t> q24(n_trace);
+    {   // 2^-22 fixed-point copy (|v| < 127 dB, embb_fastmath.cuh FIX_BITS): exact integer window sums on the fast path
+        std::vector<int32_t> fix(n_trace);
         for (size_t i = 0; i < n_trace; ++i) {
             const double v = tables->trace[i];
-            if (std::isnan(v)) { q24[i] = 0; continue; }
+            if (std::isnan(v)) { fix[i] = 0; continue; }
             if (std::fabs(v) >= 127.0) { delete h; return fail(RS_E_ARG, "fading trace value out of the +-127 dB fixed-point range"); }
-            q24[i] = (int32_t)std::llrint(v * 16777216.0);
+            fix[i] = (int32_t)std::llrint(v * 4194304.0);
         }
-        CU(cudaMalloc(&h->d_trace_q24, n_trace * sizeof(int32_t)));
-        CU(cudaMemcpy(h->d_trace_q24, q24.data(), n_trace * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&h->d_trace_fix, n_trace * sizeof(int32_t)));
+        CU(cudaMemcpy(h->d_trace_fix, fix.data(), n_trace * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     build_tables(tables, h->tb);
-    h->tb.trace = h->d_trace; h->tb.trace_q24 = h->d_trace_q24;
+    h->tb.trace = h->d_trace; h->tb.trace_fix = h->d_trace_fix;
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
@@ -227,7 +227,7 @@ int rs_destroy(rs_handle *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_q24); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
+    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
     cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
     cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
     if (h->stream) cudaStreamDestroy(h->stream);

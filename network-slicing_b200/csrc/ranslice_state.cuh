@@ -88,7 +88,7 @@ struct MmtcState {
 
 struct Tables {
     const double *trace;   // [3][N_SAMPLES][TRACE_ROWS] fp64, time-major
-    const int32_t *trace_q24; // same, fixed point round(v * 2^24): exact integer window sums on the fast path
+    const int32_t *trace_fix; // same, fixed point round(v * 2^22): exact integer window sums on the fast path
     int8_t lut_mcs[256];   // e_snr + 128 -> mcs        (MCSCodeset.mcs_rate_vs_error, channel_models.py:288-295)
     int16_t lut_rate[256]; // e_snr + 128 -> int(158 * rate*order)  (schedulers.py:45)
     double snr_ref[26];    // mcs -> snr_ref
