@@ -80,6 +80,10 @@ int kb_predict(kb_handle *h, const float *state, int32_t *first_pos);
 int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags);
 /* dictionary of one learner, packed: landmarks [D][dims[s]], coeff [D], kinv [D][D]; returns D in *D_out */
 int kb_get_learner(kb_handle *h, int32_t learner, double *landmarks, double *coeff, double *kinv, int32_t *D_out);
+/* Validation switch: with on != 0 every kernel evaluation f(x) is done in fp64 in the reference's operation order;
+ * by default f is first summed in guarded fp32 and only re-evaluated in fp64 when its sign is not certain
+ * (csrc/kbrl.cu eval_f_guarded).  Decisions are identical either way (tests/test_gpu_kbrl.py). */
+int kb_set_exact(kb_handle *h, int on);
 /* kernels launched so far; predict-mistakes (dictionary updates) applied in the last kb_update */
 int kb_get_counters(kb_handle *h, uint64_t *kernel_launches, uint64_t *updates_last_call);
 

@@ -26,12 +26,16 @@
 
 namespace kb {
 
-constexpr int THREADS = 256;
+#ifndef KB_THREADS
+#define KB_THREADS 256
+#endif
+constexpr int THREADS = KB_THREADS;
 constexpr int MAX_CAND = 256;      // n_prbs + 1 <= 201
 constexpr int MAX_DIM = 16;
 
 struct State {
     int L, S, V, n_prbs, cap;
+    int exact_only;    // kb_set_exact: evaluate every f in fp64 like the reference (validation of the guarded fast path)
     double gamma, eta;
     int dims[8], offs[8];
     int *D;            // [L]
@@ -69,9 +73,10 @@ __device__ __forceinline__ double base_dist(const double *l, const double *x, in
 }
 
 __device__ __forceinline__ void carve(unsigned char *raw, int cap, double *&base, double *&cf, double *&ll, double *&kf,
-                                      double *&ds, double *&fval) {
+                                      double *&ds, double *&fval, float4 *&fast) {
     double *p = reinterpret_cast<double *>(raw);
     base = p; cf = base + cap; ll = cf + cap; kf = ll + cap; ds = kf + cap; fval = ds + cap;
+    fast = reinterpret_cast<float4 *>(fval + MAX_CAND);      // [cap] fp32 copy of the staged dictionary (guarded fast path)
 }
 
 // f(a) for candidate a with the dictionary staged in shared memory (kernel.py:13-25 incl. the D == 1 float32 stage)
@@ -90,20 +95,83 @@ __device__ __forceinline__ double eval_f(int D, double gamma, const double *base
     return f;
 }
 
-__device__ void stage_dictionary(const State &kb, int l, int D, int d, const double *xs, double *base, double *cf, double *ll) {
-    const double *lm = kb.lm + (size_t)l * kb.cap * MAX_DIM;
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-        base[j] = base_dist(lm + (size_t)j * MAX_DIM, xs, d - 1);
-        cf[j] = kb.coeff[(size_t)l * kb.cap + j];
-        ll[j] = lm[(size_t)j * MAX_DIM + d - 1];
+// Guarded fp32 evaluation of f(a).  Only the SIGN of f is ever used (kernel.py:25, projectron.py:40), so f is first
+// summed in fp32 with ex2.approx together with G = sum |coeff_j| k_j; the fp32 result differs from the reference's
+// fp64 sum by less than (1e-5 + 1.2e-7 D) G  (|arg| <= 126 before a term flushes to zero: argument error <= 5e-7 +
+// 1.2e-7 |arg|, ex2.approx 2^-22, D sequential fp32 additions); the guard (4e-5 + 3e-7 D) G leaves a factor 2.5-4.  Inside that band -- a candidate sitting on the decision boundary -- f is re-evaluated
+// exactly like the reference (eval_f).  Dictionaries of 0 or 1 landmarks (the reference's float32 stage) go straight
+// to eval_f.
+constexpr float LOG2E = 1.4426950408889634f;
+#ifdef KB_CHECK
+__device__ unsigned long long g_kb_dbg[4];   // [0] accepted fast results, [1] sign mismatches among them, [2] max |f32-f64|/G * 1e9, [3] guard hits
+#endif
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ double eval_f_guarded(int D, double gamma, const double *base, const double *cf, const double *ll,
+                                                 const float4 *fast, bool fast_ok, double xa, unsigned *slow) {
+#ifdef KB_NO_FAST
+    return eval_f(D, gamma, base, cf, ll, xa);
+#endif
+    if (D <= 1 || !fast_ok) return eval_f(D, gamma, base, cf, ll, xa);
+    const float xf = (float)xa, g2 = (float)gamma * LOG2E;
+    float f = 0.f, G = 0.f;
+    for (int j = 0; j < D; ++j) {
+        const float4 e = fast[j];                            // x: gamma log2(e) base_j, y: coeff_j, z: l_j[last]
+        const float t = e.z - xf;
+        const float term = e.y * ex2f(-fmaf(t * t, g2, e.x));
+        f += term;
+        G += fabsf(term);
     }
+#ifdef KB_CHECK
+    {
+        const double fx = eval_f(D, gamma, base, cf, ll, xa);
+        const bool acc = fabsf(f) > (4e-5f + 3e-7f * (float)D) * G;
+        if (acc) {
+            atomicAdd(&g_kb_dbg[0], 1ull);
+            if ((fx > 0.0) != (f > 0.f)) atomicAdd(&g_kb_dbg[1], 1ull);
+            if (G > 0.f) atomicMax(&g_kb_dbg[2], (unsigned long long)(fabs((double)f - fx) / (double)G * 1e9));
+        } else atomicAdd(&g_kb_dbg[3], 1ull);
+    }
+#endif
+    if (fabsf(f) > (4e-5f + 3e-7f * (float)D) * G) return (double)f;
+    if (slow) ++*slow;
+    return eval_f(D, gamma, base, cf, ll, xa);
+}
+
+// Stages the dictionary of learner l for state xs: exact fp64 (base, coeff, last coordinate) and the fp32 copy of the
+// fast path.  The fp32 exponents are taken RELATIVE to the closest landmark (min_j base_j): sign(f) does not change
+// when every term is scaled by exp(gamma min_j base_j), and without the shift a state far from all landmarks puts
+// every term below the fp32 normal range (measured: flushed terms flipped 140 of 1.1e9 decisions).
+// Block-wide; ends with the dictionary visible to all threads (callers need no further barrier for it).  Returns
+// whether the fp32 fast path may be used for this (dictionary, state).
+__device__ bool stage_dictionary(const State &kb, int l, int D, int d, const double *xs, double *base, double *cf, double *ll,
+                                 float4 *fast) {
+    __shared__ unsigned long long s_minb;
+    const double *lm = kb.lm + (size_t)l * kb.cap * MAX_DIM;
+    const double g2 = kb.gamma * 1.4426950408889634;
+    if (threadIdx.x == 0) s_minb = ~0ull;
+    __syncthreads();
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+        const double b = base_dist(lm + (size_t)j * MAX_DIM, xs, d - 1);
+        base[j] = b; cf[j] = kb.coeff[(size_t)l * kb.cap + j]; ll[j] = lm[(size_t)j * MAX_DIM + d - 1];
+        atomicMin(&s_minb, (unsigned long long)__double_as_longlong(b));       // b >= 0: the bit pattern orders like the value
+    }
+    __syncthreads();
+    const double minb = D > 0 ? __longlong_as_double((long long)s_minb) : 0.0;
+    for (int j = threadIdx.x; j < D; j += blockDim.x)
+        fast[j] = make_float4((float)(g2 * (base[j] - minb)), (float)cf[j], (float)ll[j], 0.f);
+    __syncthreads();
+    // Past exp(-600) the reference's own fp64 terms run into the denormal range / underflow to 0 (f == 0 is a decision
+    // of its own): such far-away states are evaluated exactly.  Below it, every term that fp32 flushes after the shift
+    // (< 2^-126 of the scale) is equally negligible in fp64.
+    return kb.gamma * minb <= 600.0 && !kb.exact_only;
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS) predict_kernel(const State kb, const float *__restrict__ state, int32_t *first_pos) {
     extern __shared__ __align__(16) unsigned char raw[];
     double *base, *cf, *ll, *kf, *ds, *fval;
-    carve(raw, kb.cap, base, cf, ll, kf, ds, fval);
+    float4 *fast;
+    carve(raw, kb.cap, base, cf, ll, kf, ds, fval, fast);
     __shared__ double xs[MAX_DIM];
     __shared__ int s_first;
     const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
@@ -111,10 +179,9 @@ __global__ void __launch_bounds__(THREADS) predict_kernel(const State kb, const 
     if (threadIdx.x == 0) s_first = 1 << 30;
     __syncthreads();
     const int D = kb.D[l];
-    stage_dictionary(kb, l, D, d, xs, base, cf, ll);
-    __syncthreads();
+    const bool fast_ok = stage_dictionary(kb, l, D, d, xs, base, cf, ll, fast);
     for (int a = threadIdx.x; a <= kb.n_prbs; a += blockDim.x) {
-        const double f = eval_f(D, kb.gamma, base, cf, ll, (double)a / (double)kb.n_prbs);
+        const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, nullptr);
         if (f > 0.0) atomicMin(&s_first, a);                  // prediction == +1 (kernel.py:25)
     }
     __syncthreads();
@@ -128,7 +195,8 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
                                                          const Control ctl, int32_t *hits) {
     extern __shared__ __align__(16) unsigned char raw[];
     double *base, *cf, *ll, *kf, *ds, *fval;
-    carve(raw, kb.cap, base, cf, ll, kf, ds, fval);
+    float4 *fast;
+    carve(raw, kb.cap, base, cf, ll, kf, ds, fval, fast);
     __shared__ double xs[MAX_DIM];
     __shared__ double s_delta;
     __shared__ int s_first, s_D, s_sf;
@@ -146,11 +214,11 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
     unsigned n_updates = 0;
     __syncthreads();
     while (cur <= hi) {
-        stage_dictionary(kb, l, D, d, xs, base, cf, ll);
+        const bool fast_ok = stage_dictionary(kb, l, D, d, xs, base, cf, ll, fast);
         if (threadIdx.x == 0) s_first = 1 << 30;
         __syncthreads();
         for (int a = cur + threadIdx.x; a <= hi; a += blockDim.x) {
-            const double f = eval_f(D, kb.gamma, base, cf, ll, (double)a / (double)n);
+            const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)n, nullptr);
             fval[a] = f;
             if (f * (double)y <= 0.0) atomicMin(&s_first, a);  // Projectron.update acts only on mistakes (projectron.py:40)
         }
@@ -333,7 +401,7 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     h->ctl = kb::Control{};
     kb::State &st = h->st;
     st.L = cfg->n_envs * cfg->n_slices; st.S = cfg->n_slices; st.V = cfg->n_variables; st.n_prbs = cfg->n_prbs; st.cap = cap;
-    st.gamma = cfg->gamma; st.eta = cfg->eta;
+    st.gamma = cfg->gamma; st.eta = cfg->eta; st.exact_only = 0;
     for (int s = 0; s < 8; ++s) { st.dims[s] = s < cfg->n_slices ? dims[s] : 0; st.offs[s] = s < cfg->n_slices ? offsets[s] : 0; }
     const size_t L = (size_t)st.L;
     KCU(cudaMalloc(&st.D, L * sizeof(int)));
@@ -347,7 +415,7 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     KCU(cudaMalloc(&h->d_labels, L * sizeof(int32_t)));
     KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
     KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    h->smem_bytes = (size_t)(5 * cap + kb::MAX_CAND) * sizeof(double);
+    h->smem_bytes = (size_t)(5 * cap + kb::MAX_CAND) * sizeof(double) + (size_t)cap * sizeof(float4);
     KCU(cudaFuncSetAttribute(kb::update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     KCU(cudaFuncSetAttribute(kb::predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     *out = h;
@@ -513,6 +581,19 @@ int kb_get_learner(kb_handle *h, int32_t l, double *landmarks, double *coeff, do
         KCU(cudaMemcpy2D(kinv, (size_t)D * sizeof(double), h->st.kinv + (size_t)l * cap * cap, (size_t)cap * sizeof(double),
                          (size_t)D * sizeof(double), D, cudaMemcpyDeviceToHost));
     if (D_out) *D_out = D;
+    return RS_OK;
+}
+
+#ifdef KB_CHECK
+int kb_debug_counters(unsigned long long *out4) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out4, kb::g_kb_dbg, 4 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+int kb_set_exact(kb_handle *h, int on) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    h->st.exact_only = on ? 1 : 0;
     return RS_OK;
 }
 

@@ -45,12 +45,13 @@ def _bind(L):
     L.kb_control_update_device.argtypes = [vp] * 6
     L.kb_control_select_device.argtypes = [vp] * 5
     L.kb_control_get.argtypes = [vp] * 6
+    L.kb_set_exact.argtypes = [vp, C.c_int32]
     L.kb_get_sizes.argtypes = [vp, vp, vp]
     L.kb_get_learner.argtypes = [vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.kb_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     for n in ("kb_create", "kb_destroy", "kb_reset", "kb_update", "kb_predict", "kb_update_device", "kb_predict_device",
               "kb_get_sizes", "kb_get_learner", "kb_get_counters", "kb_control_init", "kb_control_update_device",
-              "kb_control_select_device", "kb_control_get"):
+              "kb_control_select_device", "kb_control_get", "kb_set_exact"):
         getattr(L, n).restype = C.c_int
     L._kb_bound = True
     return L
@@ -114,6 +115,10 @@ class BatchedProjectron:
         _lib.check(self._L.kb_predict_device(self._h, C.c_void_p(state.data_ptr()), C.c_void_p(first_pos.data_ptr()),
                                              C.c_void_p(stream)))
         return first_pos
+
+    def set_exact(self, on=True):
+        """Validation: evaluate every f(x) in fp64 like the reference instead of the guarded fp32 fast path."""
+        _lib.check(self._L.kb_set_exact(self._h, int(bool(on))))
 
     def sizes(self):
         s = np.empty((self.n_envs, self.n_slices), np.int32)

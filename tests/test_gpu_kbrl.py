@@ -139,3 +139,28 @@ def test_device_controller_matches_host_mirror_in_the_loop():
     for k in a:
         assert np.array_equal(np.asarray(a[k], np.float64), np.asarray(b[k], np.float64)), k
     assert np.array_equal(sa, sb) and sa.max() > 2
+
+
+def test_guarded_fp32_evaluation_never_changes_a_decision():
+    """The fp32 fast path of f(x) (csrc/kbrl.cu eval_f_guarded) against all-fp64 evaluation (kb_set_exact) in the
+    closed loop with the env, 512 envs x 120 steps (~2.5e8 kernel evaluations): identical actions, hits and
+    dictionaries.  A single flipped sign would change a dictionary and diverge the two runs."""
+    import torch
+    from ranslice_b200 import create_batched_env
+    from ranslice_b200.kbrl import create_kbrl_agent
+    N, T = 512, 120
+    outs = []
+    for exact in (False, True):
+        env = create_batched_env(777, 0, N)
+        agent = create_kbrl_agent(np.random.default_rng(3), 0, accuracy_range=(0.97, 0.99), n_envs=N, dict_cap=128,
+                                  resident=True)
+        agent.learners.set_exact(exact)
+        out = agent.run(env, T)
+        lm, cf, _ = agent.learners.learner(7, 2)
+        outs.append((out, agent.learners.sizes()[0].copy(), lm.copy(), cf.copy()))
+        env.close()
+    (a, sa, la, ca), (b, sb, lb, cb) = outs
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(sa, sb) and np.array_equal(la, lb) and np.array_equal(ca, cb)
+    assert sa.max() >= 20

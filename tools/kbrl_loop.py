@@ -80,6 +80,16 @@ else:
     res.update({"env_steps_per_s": a.envs * a.steps / tot, "ms_env": 1e3 * t_env / a.steps,
                 "ms_update_control": 1e3 * t_upd / a.steps, "ms_select_action": 1e3 * t_sel / a.steps})
 sizes, flags = agent.learners.sizes()
+import hashlib
+res["digest_sizes"] = hashlib.sha1(np.ascontiguousarray(sizes).tobytes()).hexdigest()[:12]
 res.update({"dict_mean": float(sizes.mean()), "dict_max": int(sizes.max()), "cap_hits": int((flags & 1).sum()),
             "updates_last_step": agent.learners.counters()[1], "after_steps": a.warm + a.steps})
+try:                                    # KB_CHECK builds only: fast-path validation counters
+    import ctypes
+    from ranslice_b200 import _lib
+    dbg = (ctypes.c_ulonglong * 4)()
+    if _lib.lib().kb_debug_counters(dbg) == 0:
+        res["kb_check"] = {"accepted": dbg[0], "sign_mismatch": dbg[1], "max_err_over_G": dbg[2] * 1e-9, "guard_hits": dbg[3]}
+except AttributeError:
+    pass
 print(json.dumps(res))
