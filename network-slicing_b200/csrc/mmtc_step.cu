@@ -5,8 +5,13 @@
 //   RanSlice.step reward    ran_slice.py:45-54
 //
 // The reference decrements 1000 countdowns per slot (slice_ran.py:107); here every device stores the
-// ABSOLUTE slot of its next arrival, so one step scans the 1000 words once (coalesced across units)
-// and only arriving devices are rewritten.  All arithmetic is integer except the per-slot means.
+// ABSOLUTE slot of its next arrival, so one step scans the 1000 words once and only arriving devices
+// are rewritten.  The scan is the HBM-bound part (4 KB per unit-step) and runs as its own kernel,
+// mmtc_scan_kernel, with (unit, device strip) threads -- coalesced across units, 8 strips per unit so that
+// 65 536 units put half a million threads in flight -- appending the arrivals of the period to a small
+// per-unit list; mmtc_step_kernel (thread per unit) orders the list by (slot, device) -- the order in which
+// the reference's np.where finds them -- and runs the 50 slots of FIFO processing.
+// All arithmetic is integer except the per-slot means.
 #include <cuda_runtime.h>
 
 #include "philox.cuh"
@@ -17,7 +22,7 @@ namespace rs {
 __device__ __constant__ int c_REP_SET[7] = {2, 4, 8, 16, 32, 64, 128};                     // scenario_creator.py:88
 __device__ __constant__ int c_PERIOD_SET[8] = {1000, 50000, 10000, 15000, 20000, 25000, 50000, 100000};  // :89 (50000 twice)
 
-constexpr int MTC_MAX_ARR = 96;   // arrivals buffered per unit per step (mean 8.2, Poisson-like)
+constexpr int MTC_STRIPS = 8;      // device strips per unit in the scan kernel (1000 / 8 = 125 devices each)
 
 // SliceRANmMTC.reset (slice_ran.py:91-101) + SliceL1mMTC.reset (slice_l1.py:29-39)
 __global__ void __launch_bounds__(128) mmtc_reset_kernel(const __grid_constant__ StepParams p,
@@ -41,6 +46,30 @@ __global__ void __launch_bounds__(128) mmtc_reset_kernel(const __grid_constant__
     st.acc[(size_t)u * 3 + 0] = st.acc[(size_t)u * 3 + 1] = st.acc[(size_t)u * 3 + 2] = 0.0;
 }
 
+// Phase 1: which devices fire in (t0, t0 + slots]?  Thread = (unit, strip of 125 devices).
+__global__ void __launch_bounds__(128) mmtc_scan_kernel(const __grid_constant__ StepParams p,
+                                                        const __grid_constant__ MmtcState st) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int U = st.U;
+    if (u >= U) return;
+    constexpr int PER = (N_MTC_DEV + MTC_STRIPS - 1) / MTC_STRIPS;
+    const int i0 = blockIdx.y * PER, i1 = min(i0 + PER, N_MTC_DEV);
+    const uint32_t t0 = st.time[u];
+    bool overflow = false;
+#pragma unroll 5
+    for (int i = i0; i < i1; ++i) {
+        const uint32_t d = st.next_abs[(size_t)i * U + u] - t0;     // wrap-safe: periods << 2^31
+        if (d >= 1u && d <= (uint32_t)p.slots) {
+            const uint32_t k = atomicAdd(&st.arr_n[u], 1u);
+            if (k < (uint32_t)MTC_MAX_ARR) st.arr[(size_t)k * U + u] = (d << 16) | (uint32_t)i;
+            else overflow = true;
+            st.next_abs[(size_t)i * U + u] += (uint32_t)c_PERIOD_SET[st.period_ix[(size_t)i * U + u]];  // period >= 1000 > slots
+        }
+    }
+    if (overflow) atomicOr(p.flags_acc + u / p.n_mmtc, 16u);
+}
+
+// Phase 2: the 50 slots of one mMTC slice.  Thread per unit.
 __global__ void __launch_bounds__(128) mmtc_step_kernel(const __grid_constant__ StepParams p,
                                                         const __grid_constant__ MmtcState st) {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,31 +93,36 @@ __global__ void __launch_bounds__(128) mmtc_step_kernel(const __grid_constant__ 
     st.cur_prbs[u] = n_prbs;
 
     const uint32_t t0 = st.time[u];
-    // ---- arrivals of this period: devices whose next arrival falls in (t0, t0+slots], in (slot, device) order
-    uint16_t arr_dev[MTC_MAX_ARR];
-    uint8_t arr_slot[MTC_MAX_ARR];
-    int n_arr = 0;
-    for (int i = 0; i < N_MTC_DEV; ++i) {
-        const uint32_t d = st.next_abs[(size_t)i * U + u] - t0;     // wrap-safe: periods << 2^31
-        if (d >= 1u && d <= (uint32_t)p.slots) {
-            if (n_arr < MTC_MAX_ARR) { arr_dev[n_arr] = (uint16_t)i; arr_slot[n_arr] = (uint8_t)d; ++n_arr; }
-            else flags |= 16u;
-            st.next_abs[(size_t)i * U + u] += (uint32_t)c_PERIOD_SET[st.period_ix[(size_t)i * U + u]];  // period >= 1000 > slots
+    // ---- arrivals of this period in (slot, device) order: insertion sort of the scan kernel's list (in place, coalesced)
+    const int n_arr = (int)min(st.arr_n[u], (uint32_t)MTC_MAX_ARR);
+    st.arr_n[u] = 0u;                                            // ready for the next step's scan
+    for (int a = 1; a < n_arr; ++a) {
+        const uint32_t key = st.arr[(size_t)a * U + u];
+        int b = a - 1;
+        while (b >= 0) {
+            const uint32_t kb = st.arr[(size_t)b * U + u];
+            if (kb <= key) break;
+            st.arr[(size_t)(b + 1) * U + u] = kb;
+            --b;
         }
+        st.arr[(size_t)(b + 1) * U + u] = key;
     }
+    int next_arr = 0;                                            // cursor into the ordered list
+    uint32_t next_key = n_arr > 0 ? st.arr[u] : 0xFFFFFFFFu;
     int q_n = st.q_n[u];
     double a_delay = 0.0, a_rep = 0.0;
     long long a_dev = 0;
     for (int t = 1; t <= p.slots; ++t) {
         const uint32_t now = t0 + (uint32_t)t;                     // self.time += 1
-        for (int k = 0; k < n_arr; ++k)                            // add_users, ascending device index (np.where)
-            if (arr_slot[k] == t) {
-                if (q_n < st.Q) {
-                    st.q_rep[(size_t)q_n * U + u] = c_REP_SET[st.rep_ix[(size_t)arr_dev[k] * U + u]];
-                    st.q_t0[(size_t)q_n * U + u] = now;
-                    ++q_n;
-                } else flags |= 16u;
-            }
+        while ((next_key >> 16) == (uint32_t)t) {                  // add_users, ascending device index (np.where)
+            if (q_n < st.Q) {
+                st.q_rep[(size_t)q_n * U + u] = c_REP_SET[st.rep_ix[(size_t)(next_key & 0xFFFFu) * U + u]];
+                st.q_t0[(size_t)q_n * U + u] = now;
+                ++q_n;
+            } else flags |= 16u;
+            ++next_arr;
+            next_key = next_arr < n_arr ? st.arr[(size_t)next_arr * U + u] : 0xFFFFFFFFu;
+        }
         const int n_tx = min(n_prbs, q_n);                         // one carrier (PRB) per device
         int w = 0;
         long long sd = 0, sr = 0;
@@ -143,8 +177,10 @@ __global__ void __launch_bounds__(256) reward_kernel(const __grid_constant__ Ste
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
     mmtc_reset_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
 }
-void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
+int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
+    mmtc_scan_kernel<<<dim3((st.U + 127) / 128, MTC_STRIPS), 128, 0, stream>>>(p, st);
     mmtc_step_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
+    return 2;   // kernels launched
 }
 void launch_reward(const StepParams &p, cudaStream_t stream) {
     reward_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p);

@@ -17,7 +17,7 @@ int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb,
 int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
-void launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
+int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 void launch_reward(const StepParams &p, cudaStream_t stream);
 }  // namespace rs
 
@@ -51,6 +51,8 @@ struct rs_handle {
     uint32_t *d_flags, *d_flags_acc;
     unsigned long long *d_trace_elems;
     cudaStream_t stream;
+    cudaStream_t side_stream;                // mMTC kernels run here, concurrently with the eMBB kernels of the same step
+    cudaEvent_t ev_fork, ev_join;
     uint64_t launches;
     bool was_reset;
     bool profiling;
@@ -201,6 +203,12 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
         h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
         h->embb.cold = rc.take<rs::ColdRec>(U * (size_t)h->embb.K);
     }
+    if (h->mmtc.U) {   // arrival scratch of the mMTC scan kernel
+        const size_t UM = (size_t)h->mmtc.U;
+        CU(cudaMalloc(&h->mmtc.arr_n, UM * sizeof(uint32_t)));
+        CU(cudaMemset(h->mmtc.arr_n, 0, UM * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->mmtc.arr, UM * rs::MTC_MAX_ARR * sizeof(uint32_t)));
+    }
 
     const size_t N = (size_t)p.N, S = (size_t)p.S, V = (size_t)p.V;
     CU(cudaMalloc(&h->d_action, N * S * sizeof(int32_t)));
@@ -215,6 +223,9 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     CU(cudaMemset(h->d_trace_elems, 0, 4 * sizeof(unsigned long long)));
     h->d_slow_paths = h->d_trace_elems + 1;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     p.flags_acc = h->d_flags_acc;
     p.trace_elems = h->d_trace_elems;
     p.slow_paths = h->d_slow_paths;
@@ -230,7 +241,11 @@ int rs_destroy(rs_handle *h) {
     cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
     cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
     cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
+    if (h->mmtc.U) { cudaFree(h->mmtc.arr_n); cudaFree(h->mmtc.arr); }
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->prof_events) { for (auto e : *h->prof_events) cudaEventDestroy(e); delete h->prof_events; }
     delete h;
     return RS_OK;
@@ -272,13 +287,24 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
         for (auto &e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], st));
     }
+    // eMBB and mMTC slices of a step are independent (disjoint state, disjoint output columns): when both exist the
+    // mMTC kernels run on a side stream next to the eMBB kernels and join before the reward reduction.  With
+    // per-kernel profiling on, everything stays on one stream so that the events bracket single kernels.
+    const bool fork = h->embb.U && h->mmtc.U && !h->profiling;
+    if (fork) {
+        CU(cudaEventRecord(h->ev_fork, st));
+        CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        h->launches += rs::launch_mmtc_step(p, h->mmtc, h->side_stream);
+        CU(cudaEventRecord(h->ev_join, h->side_stream));
+    }
     if (h->embb.U) {
         if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->cfg.kernel_variant == 2 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
         else h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st);
     }
     if (h->profiling) CU(cudaEventRecord(ev[1], st));
-    if (h->mmtc.U) { rs::launch_mmtc_step(p, h->mmtc, st); h->launches += 1; }
+    if (fork) CU(cudaStreamWaitEvent(st, h->ev_join, 0));
+    else if (h->mmtc.U) h->launches += rs::launch_mmtc_step(p, h->mmtc, st);
     if (h->profiling) CU(cudaEventRecord(ev[2], st));
     rs::launch_reward(p, st);
     h->launches += 1;

@@ -84,7 +84,11 @@ struct MmtcState {
     uint32_t *ctr;         // [U] Philox counter (STREAM_MTC)
     double *acc;           // [U][3] devices, avg_rep, delay
     int32_t *cur_prbs;     // [U]
+    // per-step scratch (rebuilt every step, not part of the checkpoint): arrivals found by the scan kernel
+    uint32_t *arr_n;       // [U] arrivals of this period (may exceed MTC_MAX_ARR: the excess is flagged and dropped)
+    uint32_t *arr;         // [MTC_MAX_ARR][U] slot-in-period << 16 | device index, unordered
 };
+constexpr int MTC_MAX_ARR = 96;    // arrivals buffered per unit per step (mean 8.2, Poisson-like)
 
 struct Tables {
     const double *trace;   // [3][N_SAMPLES][TRACE_ROWS] fp64, time-major
