@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         } else if (n_ues <= max_front_ues) {
             atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots, true)], 2u);      // (unit, pad) pair
         } else {
-            st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
+            st.perm[st.perm_len - 1 - (int)atomicAdd(&st.hist[2 * KEY_BINS + 1], 1u)] = u;  // list L
         }
         off += v;
     }
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ St
     const bool heavy = n_ues >= heavy_min_ues;
     const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], n_ues, p.slots, heavy);
     const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], heavy ? 2u : 1u);
-    st.perm[pos] = u;
-    if (heavy) st.perm[pos + 1] = -1;                          // the odd lane only lends its shared-memory slots
+    st.perm[pos << st.dil] = u;                                // diluted list: the lanes in between stay -1 (launch_embb_sort)
+    if (heavy) st.perm[(pos << st.dil) + 1] = -1;                          // the odd lane only lends its shared-memory slots
 }
 
 // Rare RAN events of a slot, exactly in the reference's order (slice_ran.py:263-268, slice_l1.py:196-198):
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     const int count = (int)st.hist[2 * KEY_BINS + back_list];           // front (sorted) list or back list L
     const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
     if (tix >= count) return;
-    const int u = st.perm[back_list ? 2 * st.U - 1 - tix : tix];    // (variant 2 has no pair entries: heavy_min = inf)
+    const int u = st.perm[back_list ? st.perm_len - 1 - tix : tix];    // (variant 2 has no pair entries: heavy_min = inf)
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
     unpack_window(st.win[u], i_prb, n_prbs);
@@ -522,6 +522,7 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
 
 void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream) {
     cudaMemsetAsync(st.hist, 0, (2 * KEY_BINS + 4) * sizeof(uint32_t), stream);
+    if (st.dil) cudaMemsetAsync(st.perm, 0xFF, (size_t)st.perm_len * sizeof(int32_t), stream);   // idle lanes of the diluted list
     window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);
     scan_kernel<<<1, 1024, 0, stream>>>(st);
     scatter_kernel<<<(st.U + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);

@@ -233,12 +233,12 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
     const SmemView v = carve_smem(smem_raw);
 
     const int tix = blockIdx.x * SM_THREADS + tid;
-    const int count = (int)st.hist[2 * SORT_BINS + 0];
+    const int count = (int)st.hist[2 * SORT_BINS + 0] << st.dil;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, tix < count);
     if (tix >= count) return;
     const int u_raw = st.perm[tix];
     const bool pad = u_raw < 0;                                  // idle lane lending its slots to the unit on its left
-    const int slots_cap = min(st.K, tix < 2 * (int)st.hist[2 * SORT_BINS + 3] ? 2 * SM_KS : SM_KS);
+    const int slots_cap = min(st.K, tix < (2 * (int)st.hist[2 * SORT_BINS + 3]) << st.dil ? 2 * SM_KS : SM_KS);
     const int u = pad ? 0 : u_raw;
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
     __syncwarp(warp_mask);
     if (pad) return;
     if (dead) {                                                  // replay this unit in the general kernel (list L)
-        st.perm[2 * st.U - 1 - (int)atomicAdd(&st.hist[2 * SORT_BINS + 1], 1u)] = u;
+        st.perm[st.perm_len - 1 - (int)atomicAdd(&st.hist[2 * SORT_BINS + 1], 1u)] = u;
         return;
     }
     // ---- scatter the records back (once per step) and persist the slice scalars
@@ -613,7 +613,7 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
         configured = true;
     }
     launch_embb_sort(p, st, SM_MAX_START_UES_PAIR, SM_MAX_START_UES + 1, stream);
-    const int blocks = (2 * st.U + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
+    const int blocks = (st.perm_len + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
     embb_step_smem<<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     launch_embb_general(p, st, tb, 1, stream);
     return 5;   // kernels launched

@@ -57,13 +57,16 @@ static_assert(sizeof(UnitHdr) == 32, "UnitHdr must be 32 bytes");
 
 struct EmbbState {
     int U, K, MB;          // units, UE records per unit, burst slots per UE (== MAX_BURSTS)
+    int dil, perm_len;     // lane dilution (log2) of the shared-memory kernel's front list and the length of perm[]: when a batch
+                           // cannot fill the GPU, every 2^dil-th lane carries a unit and the rest idle -- fewer divergent units
+                           // per warp shorten the slowest warp, which is what a step of a small batch waits for
     UnitHdr *hdr;          // [U]
     UeRec *ue;             // [U][K], live UEs first, in arrival order (order decides PF ties and RNG draw order)
     double *acc;           // [U][10] raw accumulators of the last step (info['l1_info'])
     int32_t *cur_prbs;     // [U] PRBs in force (after clamping)
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
-    int32_t *perm;         // [2U] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
+    int32_t *perm;         // [perm_len = 2U << dil] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
     uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
     uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
     ColdRec *cold;         // [U][K] per-step scratch of the shared-memory kernel
