@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libranslice_b200.so")
-SOURCES = ["ranslice_cabi.cu", "embb_step.cu", "embb_fast.cu", "embb_smem.cu", "mmtc_step.cu", "kbrl.cu"]
+SOURCES = ["ranslice_cabi.cu", "embb_step.cu", "embb_fast.cu", "embb_smem.cu", "mmtc_step.cu", "kbrl.cu", "wrappers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=false",           # fp64 decision arithmetic must not be contracted (parity with NumPy)
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -30,6 +30,7 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG), "include", "ranslice_b200.h"))
     headers.append(os.path.join(os.path.dirname(PKG), "include", "kbrl_b200.h"))
+    headers.append(os.path.join(os.path.dirname(PKG), "include", "wrapper_b200.h"))
     tag = os.environ.get("RS_BUILD_TAG", "")                # experiment builds: separate objects, lib<tag>.so next to the real one
     out = OUT if not tag else OUT.replace(".so", "_%s.so" % tag)
     objdir = os.path.join(PKG, "build" + ("_" + tag if tag else ""))
