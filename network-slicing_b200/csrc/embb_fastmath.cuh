@@ -12,11 +12,15 @@ namespace rs {
 #endif
 #if RS_EXP & 1
 #define LDQ_B(p) make_int4(1 << 22, 2 << 22, 3 << 22, 4 << 22)
+#elif defined(RS_LD_CG)
+#define LDQ_B(p) __ldcg(p)
 #else
 #define LDQ_B(p) __ldg(p)
 #endif
 #if RS_EXP & 2
 #define LDQ_D(p) make_int4(1 << 22, 2 << 22, 3 << 22, 4 << 22)
+#elif defined(RS_LD_CG)
+#define LDQ_D(p) __ldcg(p)
 #else
 #define LDQ_D(p) __ldg(p)
 #endif

@@ -211,7 +211,19 @@ __device__ __forceinline__ double div_count(double x, int n) {
     return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
 }
 
-__global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_constant__ StepParams p,
+#ifdef RS_STATS
+// Workload statistics of the PF loop (experiment builds only; read with rs_debug_stats)
+__device__ unsigned long long g_stats[64];
+#define STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+__device__ __forceinline__ int log2_bucket(int x) { return x <= 0 ? 0 : min(1 + (31 - __clz(x)), 7); }
+#else
+#define STAT(i, v)
+#endif
+
+#ifndef RS_SM_BLOCKS
+#define RS_SM_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const __grid_constant__ StepParams p,
                                                                 const __grid_constant__ EmbbState st,
                                                                 const __grid_constant__ Tables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -364,6 +376,10 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
         __syncwarp(warp_mask);
         const bool scheduled = n_backlog > 0 && n_prbs > 0;      // queued_data > 0 <=> some queue > 0
         const unsigned sched_mask = __ballot_sync(warp_mask, scheduled);
+#ifdef RS_STATS
+        if (!pad && !dead) { STAT(0, 1); STAT(1, scheduled); STAT(8 + min(n_backlog, 7), 1); STAT(16 + min(n_ues, 15), 1); }
+        int st_iters = 0, st_prev = -1, st_same = 0;
+#endif
         if (scheduled) {
             for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= (int)0xFFFFFF00; }   // ue_bits, ue_rbs
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
@@ -381,6 +397,9 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                     if (m > best) { second = best; best = m; idx = k; }
                     else second = fmaxf(second, m);
                 }
+#ifdef RS_STATS
+                if (second >= best * (1.0f - 1e-6f)) STAT(2, 1);
+#endif
                 if (second >= best * (1.0f - 1e-6f)) {                      // too close for fp32: exact quotients
                     const float lim = best * (1.0f - 1e-6f);
                     double best64 = -1.0;
@@ -403,7 +422,16 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
                 if (left_q - tx <= 0) { v.metf[SIX(idx)] = 0.0f; --n_backlog; }
                 else v.metf[SIX(idx)] = (float)rate * rcp_approx((float)thn);
                 r += 2;
+#ifdef RS_STATS
+                ++st_iters; st_same += idx == st_prev; st_prev = idx;
+                STAT(3, n_ues);
+                if (left_q - tx <= 0) STAT(4, 1);
+#endif
             }
+#ifdef RS_STATS
+            STAT(5, st_iters); STAT(6, st_same); STAT(32 + log2_bucket(st_iters), 1); STAT(40 + log2_bucket(st_iters), st_iters);
+            STAT(7, (r < n_prbs && n_backlog == 1));
+#endif
             __syncwarp(sched_mask);
             // phase 2: a single backlogged UE takes chunks until it is drained or the PRBs run out (closed form)
             if (r < n_prbs && n_backlog == 1) {
@@ -600,6 +628,15 @@ __global__ void __launch_bounds__(SM_THREADS, 4) embb_step_smem(const __grid_con
     if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
 }
 
+#ifdef RS_STATS
+extern "C" int rs_debug_stats(unsigned long long *out64, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out64, g_stats, sizeof(g_stats)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_stats, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream);
 void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream);
 
@@ -607,9 +644,12 @@ void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables 
 int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
     static bool configured = false;
     constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
-    static_assert(4 * (smem_bytes + 2048 + 1024) <= 227 * 1024, "4 blocks per SM must fit");
+    static_assert(RS_SM_BLOCKS * (smem_bytes + 2048 + 1024) <= 227 * 1024, "RS_SM_BLOCKS blocks per SM must fit");
     if (!configured) {
         cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+#ifdef RS_CARVEOUT
+        cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributePreferredSharedMemoryCarveout, RS_CARVEOUT);   // experiment: percent of the 228 KB
+#endif
         configured = true;
     }
     launch_embb_sort(p, st, SM_MAX_START_UES_PAIR, SM_MAX_START_UES + 1, stream);
