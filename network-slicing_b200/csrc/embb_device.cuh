@@ -68,16 +68,22 @@ static __device__ __noinline__ double draw_nominal_sinr(PhiloxStream &r, double 
     return rx - (-110) - 9;
 }
 
-// SINRSelectiveFading.get_snr index walk (channel_models.py:171-191)
-__device__ __forceinline__ void walk_trace(PhiloxStream &r, int &index, int &step) {
+// SINRSelectiveFading.get_snr index walk (channel_models.py:171-191).  The re-draw at a trace end happens once per
+// ~10 000 TTIs of a UE: it is kept out of line so that its two Philox evaluations (~200 instructions) do not sit in
+// the middle of the per-TTI instruction stream (the hot loop is instruction-fetch sensitive).
+static __device__ __noinline__ void walk_trace_redraw(PhiloxStream &r, int &index, int &step) {
     for (;;) {
-        index += step;
         if (index >= N_SAMPLES || index < 0) {
             index = (int)r.integers(N_SAMPLES);
             step = r.integers(2) ? 1 : -1;
         }
         if (index != N_SAMPLES - 1) break;       // column 10000 is all-NaN
+        index += step;
     }
+}
+__device__ __forceinline__ void walk_trace(PhiloxStream &r, int &index, int &step) {
+    index += step;
+    if (index >= N_SAMPLES - 1 || index < 0) walk_trace_redraw(r, index, step);
 }
 
 // VbrSource.step (traffic_generators.py:70-99) on a UE record held in registers; returns this slot's bits.

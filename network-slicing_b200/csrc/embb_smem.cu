@@ -211,6 +211,22 @@ __device__ __forceinline__ double div_count(double x, int n) {
     return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
 }
 
+// PF argmax among the candidates within 1e-6 (relative) of the fp32 maximum: exact fp64 quotients, first maximum
+// (np.argmax, schedulers.py:52).  Taken by 0.6 % of the chunks; out of line to keep the RB loop compact.
+__device__ __noinline__ int pf_exact_argmax(const SmemView &v, int tid, int n_ues, float best) {
+    const float lim = best * (1.0f - 1e-6f);
+    double best64 = -1.0;
+    int idx = 0;
+    for (int k = 0; k < n_ues; ++k) {
+        const float m = v.metf[SIX(k)];
+        if (m >= lim && m > 0.0f) {
+            const double m64 = (double)(v.rm[SIX(k)] & 0xFFFFu) / v.thpf[SIX(k)];
+            if (m64 > best64) { best64 = m64; idx = k; }
+        }
+    }
+    return idx;
+}
+
 #ifdef RS_STATS
 // Workload statistics of the PF loop (experiment builds only; read with rs_debug_stats)
 __device__ unsigned long long g_stats[64];
@@ -400,17 +416,7 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
 #ifdef RS_STATS
                 if (second >= best * (1.0f - 1e-6f)) STAT(2, 1);
 #endif
-                if (second >= best * (1.0f - 1e-6f)) {                      // too close for fp32: exact quotients
-                    const float lim = best * (1.0f - 1e-6f);
-                    double best64 = -1.0;
-                    for (int k = 0; k < n_ues; ++k) {
-                        const float m = v.metf[SIX(k)];
-                        if (m >= lim && m > 0.0f) {
-                            const double m64 = (double)(v.rm[SIX(k)] & 0xFFFFu) / v.thpf[SIX(k)];
-                            if (m64 > best64) { best64 = m64; idx = k; }
-                        }
-                    }
-                }
+                if (second >= best * (1.0f - 1e-6f)) idx = pf_exact_argmax(v, tid, n_ues, best);   // too close for fp32
                 const int rate = (int)(v.rm[SIX(idx)] & 0xFFFFu);
                 const int left_q = v.queue[SIX(idx)] - v.bits[SIX(idx)];
                 const int tx = min(c * rate, left_q);
