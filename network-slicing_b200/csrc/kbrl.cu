@@ -6,7 +6,11 @@
 //   callers restated: the select_action scan (kbrl_control.py:54-61) and the sample-augmentation loop of
 //   update_control (kbrl_control.py:103-112)
 //
-// One CTA per learner.  Both callers evaluate f(a) = sum_j coeff_j exp(-gamma ||l_j - [s, a/n]||^2) for
+// One thread GROUP per learner (KB_GROUP = 32 threads = one warp by default, 4 groups per 128-thread block): a
+// learner-step is a chain of short phases (stage the dictionary, evaluate <= 201 candidates, find the first mistake,
+// project / extend) separated by barriers, so what matters is how many learners an SM keeps in flight and how cheap
+// the barriers are -- with one 256-thread CTA per learner the kernels spent 9.8 barrier-stall cycles per issued
+// instruction (profiles/r01f_kb_update_16384_full.txt).  Both callers evaluate f(a) = sum_j coeff_j exp(-gamma ||l_j - [s, a/n]||^2) for
 // up to n_prbs + 1 candidate allocations a of one state s.  numpy's pairwise sum over the 11 (4)
 // squared differences adds the action coordinate LAST, so the distance is separable bit-exactly:
 // base_j (state part, once per landmark) + (l_j,last - a/n)^2.  Threads own candidates and walk the
@@ -26,10 +30,29 @@
 
 namespace kb {
 
-#ifndef KB_THREADS
-#define KB_THREADS 256
+// Threads per learner.  Measured in the config-3 loop (16 384 envs, D mean 27, cap 128; tools/gpu_kb_sweep.sh):
+//   update_kernel   32: 8.9 ms   64: 5.4 ms   128: 3.9 ms   256: 3.4 ms   -- work-bound per learner (K^-1 mat-vec and rank-1
+//                   extension over D^2 elements, <= 201 candidates x D terms per round): wide groups win
+//   predict_kernel  32: 0.44 ms  128: 0.54 ms  256: 0.62 ms               -- one short pass: more learners in flight win
+#ifndef KB_GROUP_UPDATE
+#define KB_GROUP_UPDATE 256
 #endif
-constexpr int THREADS = KB_THREADS;
+#ifndef KB_GROUP_PREDICT
+#define KB_GROUP_PREDICT 32
+#endif
+constexpr size_t GROUP_SMEM_PER_LANDMARK = 5 * sizeof(double) + sizeof(float4);   // base, coeff, last coord, k, d*, fp32 copy
+template <int G> struct Cfg {
+    static_assert(G == 32 || G == 64 || G == 128 || G == 256, "threads per learner: 32, 64, 128 or 256");
+    static constexpr int THREADS = G < 128 ? 128 : G;        // threads per block
+    static constexpr int GROUPS = THREADS / G;               // learners per block
+};
+// barrier among the G threads that work on one learner
+template <int G> __device__ __forceinline__ void gsync(int group) {
+    if (G == 32) __syncwarp();
+    else if (Cfg<G>::GROUPS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(G) : "memory");
+}
+
 constexpr int MAX_CAND = 256;      // n_prbs + 1 <= 201
 constexpr int MAX_DIM = 16;
 
@@ -72,12 +95,15 @@ __device__ __forceinline__ double base_dist(const double *l, const double *x, in
     return r;
 }
 
-__device__ __forceinline__ void carve(unsigned char *raw, int cap, double *&base, double *&cf, double *&ll, double *&kf,
-                                      double *&ds, double *&fval, float4 *&fast) {
-    double *p = reinterpret_cast<double *>(raw);
-    base = p; cf = base + cap; ll = cf + cap; kf = ll + cap; ds = kf + cap; fval = ds + cap;
-    fast = reinterpret_cast<float4 *>(fval + MAX_CAND);      // [cap] fp32 copy of the staged dictionary (guarded fast path)
+// shared-memory slice of one group
+__device__ __forceinline__ void carve(unsigned char *raw, int cap, int group, double *&base, double *&cf, double *&ll, double *&kf,
+                                      double *&ds, float4 *&fast) {
+    double *p = reinterpret_cast<double *>(raw + (size_t)group * cap * GROUP_SMEM_PER_LANDMARK);
+    base = p; cf = base + cap; ll = cf + cap; kf = ll + cap; ds = kf + cap;
+    fast = reinterpret_cast<float4 *>(ds + cap);             // [cap] fp32 copy of the staged dictionary (guarded fast path)
 }
+// per-group scalars
+struct GroupVars { double xs[MAX_DIM]; double delta, fa0; unsigned long long minb; int first, D, sf, pad; };
 
 // f(a) for candidate a with the dictionary staged in shared memory (kernel.py:13-25 incl. the D == 1 float32 stage)
 __device__ __forceinline__ double eval_f(int D, double gamma, const double *base, const double *cf, const double *ll, double xa) {
@@ -141,25 +167,25 @@ __device__ __forceinline__ double eval_f_guarded(int D, double gamma, const doub
 // fast path.  The fp32 exponents are taken RELATIVE to the closest landmark (min_j base_j): sign(f) does not change
 // when every term is scaled by exp(gamma min_j base_j), and without the shift a state far from all landmarks puts
 // every term below the fp32 normal range (measured: flushed terms flipped 140 of 1.1e9 decisions).
-// Block-wide; ends with the dictionary visible to all threads (callers need no further barrier for it).  Returns
-// whether the fp32 fast path may be used for this (dictionary, state).
-__device__ bool stage_dictionary(const State &kb, int l, int D, int d, const double *xs, double *base, double *cf, double *ll,
-                                 float4 *fast) {
-    __shared__ unsigned long long s_minb;
+// Group-wide; ends with the dictionary visible to all threads of the group (callers need no further barrier for it).
+// Returns whether the fp32 fast path may be used for this (dictionary, state).
+template <int GROUP>
+__device__ bool stage_dictionary(const State &kb, int l, int D, int d, GroupVars &g, int group, int gt, double *base, double *cf,
+                                 double *ll, float4 *fast) {
     const double *lm = kb.lm + (size_t)l * kb.cap * MAX_DIM;
     const double g2 = kb.gamma * 1.4426950408889634;
-    if (threadIdx.x == 0) s_minb = ~0ull;
-    __syncthreads();
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-        const double b = base_dist(lm + (size_t)j * MAX_DIM, xs, d - 1);
+    if (gt == 0) g.minb = ~0ull;
+    gsync<GROUP>(group);
+    for (int j = gt; j < D; j += GROUP) {
+        const double b = base_dist(lm + (size_t)j * MAX_DIM, g.xs, d - 1);
         base[j] = b; cf[j] = kb.coeff[(size_t)l * kb.cap + j]; ll[j] = lm[(size_t)j * MAX_DIM + d - 1];
-        atomicMin(&s_minb, (unsigned long long)__double_as_longlong(b));       // b >= 0: the bit pattern orders like the value
+        atomicMin(&g.minb, (unsigned long long)__double_as_longlong(b));       // b >= 0: the bit pattern orders like the value
     }
-    __syncthreads();
-    const double minb = D > 0 ? __longlong_as_double((long long)s_minb) : 0.0;
-    for (int j = threadIdx.x; j < D; j += blockDim.x)
+    gsync<GROUP>(group);
+    const double minb = D > 0 ? __longlong_as_double((long long)g.minb) : 0.0;
+    for (int j = gt; j < D; j += GROUP)
         fast[j] = make_float4((float)(g2 * (base[j] - minb)), (float)cf[j], (float)ll[j], 0.f);
-    __syncthreads();
+    gsync<GROUP>(group);
     // Past exp(-600) the reference's own fp64 terms run into the denormal range / underflow to 0 (f == 0 is a decision
     // of its own): such far-away states are evaluated exactly.  Below it, every term that fp32 flushes after the shift
     // (< 2^-126 of the scale) is equally negligible in fp64.
@@ -167,41 +193,53 @@ __device__ bool stage_dictionary(const State &kb, int l, int D, int d, const dou
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) predict_kernel(const State kb, const float *__restrict__ state, int32_t *first_pos) {
+template <int GROUP>
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const State kb, const float *__restrict__ state, int32_t *first_pos) {
     extern __shared__ __align__(16) unsigned char raw[];
-    double *base, *cf, *ll, *kf, *ds, *fval;
+    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
+    __shared__ GroupVars gv[GROUPS];
+    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+    const int l = blockIdx.x * GROUPS + group;
+    if (l >= kb.L) return;                                    // whole group
+    double *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, kb.cap, base, cf, ll, kf, ds, fval, fast);
-    __shared__ double xs[MAX_DIM];
-    __shared__ int s_first;
-    const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
-    if (threadIdx.x < d - 1) xs[threadIdx.x] = (double)state[(size_t)env * kb.V + kb.offs[s] + threadIdx.x];
-    if (threadIdx.x == 0) s_first = 1 << 30;
-    __syncthreads();
+    carve(raw, kb.cap, group, base, cf, ll, kf, ds, fast);
+    GroupVars &g = gv[group];
+    const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
+    if (gt < d - 1) g.xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
+    if (gt == 0) g.first = 1 << 30;
+    gsync<GROUP>(group);
     const int D = kb.D[l];
-    const bool fast_ok = stage_dictionary(kb, l, D, d, xs, base, cf, ll, fast);
-    for (int a = threadIdx.x; a <= kb.n_prbs; a += blockDim.x) {
+    const bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
+    int first = 1 << 30;
+    for (int a = gt; a <= kb.n_prbs; a += GROUP) {
         const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, nullptr);
-        if (f > 0.0) atomicMin(&s_first, a);                  // prediction == +1 (kernel.py:25)
+        if (f > 0.0) first = min(first, a);                   // prediction == +1 (kernel.py:25)
     }
-    __syncthreads();
-    if (threadIdx.x == 0) first_pos[l] = s_first == (1 << 30) ? -1 : s_first;
+    if (first != (1 << 30)) atomicMin(&g.first, first);
+    gsync<GROUP>(group);
+    if (gt == 0) first_pos[l] = g.first == (1 << 30) ? -1 : g.first;
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const float *__restrict__ state,
+template <int GROUP>
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) update_kernel(const State kb, const float *__restrict__ state,
                                                          const int32_t *__restrict__ action,
                                                          const int32_t *__restrict__ labels, int32_t *y_pred,
                                                          const Control ctl, int32_t *hits) {
     extern __shared__ __align__(16) unsigned char raw[];
-    double *base, *cf, *ll, *kf, *ds, *fval;
+    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
+    __shared__ GroupVars gv[GROUPS];
+    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+    const int l = blockIdx.x * GROUPS + group;
+    if (l >= kb.L) return;                                    // whole group
+    double *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, kb.cap, base, cf, ll, kf, ds, fval, fast);
-    __shared__ double xs[MAX_DIM];
-    __shared__ double s_delta;
-    __shared__ int s_first, s_D, s_sf;
-    const int l = blockIdx.x, env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs, cap = kb.cap;
-    if (threadIdx.x < d - 1) xs[threadIdx.x] = (double)state[(size_t)env * kb.V + kb.offs[s] + threadIdx.x];
+    carve(raw, kb.cap, group, base, cf, ll, kf, ds, fast);
+    GroupVars &g = gv[group];
+    double *xs = g.xs;
+    const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs, cap = kb.cap;
+    if (gt < d - 1) xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
     const int y = labels[l];
     const int a0 = min(max(action[l], 0), n);
     const int lo = y == 1 ? a0 : 0, hi = y == 1 ? n : a0;     // kbrl_control.py:103-112
@@ -212,50 +250,52 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
     int cur = lo;
     bool first_round = true;
     unsigned n_updates = 0;
-    __syncthreads();
+    gsync<GROUP>(group);
     while (cur <= hi) {
-        const bool fast_ok = stage_dictionary(kb, l, D, d, xs, base, cf, ll, fast);
-        if (threadIdx.x == 0) s_first = 1 << 30;
-        __syncthreads();
-        for (int a = cur + threadIdx.x; a <= hi; a += blockDim.x) {
+        const bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
+        if (gt == 0) g.first = 1 << 30;
+        gsync<GROUP>(group);
+        int first = 1 << 30;
+        for (int a = cur + gt; a <= hi; a += GROUP) {
             const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)n, nullptr);
-            fval[a] = f;
-            if (f * (double)y <= 0.0) atomicMin(&s_first, a);  // Projectron.update acts only on mistakes (projectron.py:40)
+            if (first_round && a == a0) g.fa0 = f;
+            if (f * (double)y <= 0.0) first = min(first, a);   // Projectron.update acts only on mistakes (projectron.py:40)
         }
-        __syncthreads();
+        if (first != (1 << 30)) atomicMin(&g.first, first);
+        gsync<GROUP>(group);
         if (first_round) {                                     // the predict of kbrl_control.py:89 (before any update)
-            const int yp = D == 0 ? 0 : (fval[a0] > 0.0 ? 1 : -1);
-            if (threadIdx.x == 0 && y_pred) y_pred[l] = yp;
+            const int yp = D == 0 ? 0 : (g.fa0 > 0.0 ? 1 : -1);
+            if (gt == 0 && y_pred) y_pred[l] = yp;
             first_round = false;
             if (ctl.acc) {                                     // E-learner part of update_control (kbrl_control.py:90-101)
                 const bool hit = y == yp;
                 const int margin = max(0, ctl.margins[l]);
                 const double om = 1.0 - ctl.alfa;
                 double *acc = ctl.acc + (size_t)l * n;
-                if (threadIdx.x == 0) s_sf = 1 << 30;
-                __syncthreads();
-                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                if (gt == 0) g.sf = 1 << 30;
+                gsync<GROUP>(group);
+                for (int i = gt; i < n; i += GROUP) {
                     double v = acc[i];
                     if (yp == 1) {
                         if (!hit) { if (i <= margin) { v = om * v; acc[i] = v; } }            // same or less margin: same mistake
                         else if (i >= margin) { v = om * v + ctl.alfa; acc[i] = v; }          // same or more margin: same success
                     }
-                    if (v > ctl.acc_lo) atomicMin(&s_sf, i);   // np.argmax(accuracies > accuracy_range[0]): first True, 0 if none
+                    if (v > ctl.acc_lo) atomicMin(&g.sf, i);   // np.argmax(accuracies > accuracy_range[0]): first True, 0 if none
                 }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    if (!ctl.adjusted[env]) ctl.sec[l] = s_sf == (1 << 30) ? 0 : s_sf;
+                gsync<GROUP>(group);
+                if (gt == 0) {
+                    if (!ctl.adjusted[env]) ctl.sec[l] = g.sf == (1 << 30) ? 0 : g.sf;
                     if (hits) hits[l] = hit ? 1 : 0;
                 }
             }
         }
-        const int astar = s_first;
+        const int astar = g.first;
         if (astar == (1 << 30)) break;
         // ---- Projectron.update at x = [s, astar / n] (projectron.py:41-60)
         const double xa = (double)astar / (double)n;
         ++n_updates;
         if (D <= 1) {                                          // float32 stage: Kinv, K_f, coeff are float32 arrays of length 1
-            if (threadIdx.x == 0) {
+            if (gt == 0) {
                 float kfv = 0.f, ki = 0.f;
                 if (D == 1) { const double t = ll[0] - xa; kfv = (float)exp(-kb.gamma * (base[0] + t * t)); ki = (float)kinv[0]; }
                 const float dsv = ki * kfv;
@@ -274,52 +314,52 @@ __global__ void __launch_bounds__(THREADS) update_kernel(const State kb, const f
                         for (int i = 0; i < 2; ++i)
                             for (int j = 0; j < 2; ++j) kinv[(size_t)i * cap + j] += dse[i] * dse[j] / delta;
                     }
-                    s_D = D + 1;
+                    g.D = D + 1;
                 }
-                if (delta <= kb.eta) s_D = D;
+                if (delta <= kb.eta) g.D = D;
             }
-            __syncthreads();
-            D = s_D;
+            gsync<GROUP>(group);
+            D = g.D;
         } else {
-            for (int j = threadIdx.x; j < D; j += blockDim.x) { const double t = ll[j] - xa; kf[j] = exp(-kb.gamma * (base[j] + t * t)); }
-            __syncthreads();
-            for (int i = threadIdx.x; i < D; i += blockDim.x) {      // d* = K^-1 k; column i == row i (symmetric), coalesced
+            for (int j = gt; j < D; j += GROUP) { const double t = ll[j] - xa; kf[j] = exp(-kb.gamma * (base[j] + t * t)); }
+            gsync<GROUP>(group);
+            for (int i = gt; i < D; i += GROUP) {      // d* = K^-1 k; column i == row i (symmetric), coalesced
                 double acc = 0.0;
                 for (int j = 0; j < D; ++j) acc += kinv[(size_t)j * cap + i] * kf[j];
                 ds[i] = acc;
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {                                   // delta = max(Kii - d* . k, 0), index order
+            gsync<GROUP>(group);
+            if (gt == 0) {                                   // delta = max(Kii - d* . k, 0), index order
                 double dot = 0.0;
                 for (int i = 0; i < D; ++i) dot += ds[i] * kf[i];
                 double delta = 1.0 - dot;
-                s_delta = delta < 0.0 ? 0.0 : delta;
+                g.delta = delta < 0.0 ? 0.0 : delta;
             }
-            __syncthreads();
-            const double delta = s_delta;
+            gsync<GROUP>(group);
+            const double delta = g.delta;
             if (delta <= kb.eta) {                                    // sv.update(y * d_star)
-                for (int i = threadIdx.x; i < D; i += blockDim.x) coeff[i] += (double)y * ds[i];
+                for (int i = gt; i < D; i += GROUP) coeff[i] += (double)y * ds[i];
             } else if (D < cap) {                                     // sv.extend / insert + rank-1 extension of K^-1
-                if (threadIdx.x == 0) {
+                if (gt == 0) {
                     for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
                     lm[(size_t)D * MAX_DIM + d - 1] = xa;
                     coeff[D] = (double)y;
                     ds[D] = -1.0;
                 }
-                for (int i = threadIdx.x; i <= D; i += blockDim.x) { kinv[(size_t)i * cap + D] = 0.0; kinv[(size_t)D * cap + i] = 0.0; }
-                __syncthreads();
+                for (int i = gt; i <= D; i += GROUP) { kinv[(size_t)i * cap + D] = 0.0; kinv[(size_t)D * cap + i] = 0.0; }
+                gsync<GROUP>(group);
                 const int m = D + 1;
-                for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+                for (int idx = gt; idx < m * m; idx += GROUP) {
                     const int i = idx / m, j = idx - i * m;
                     kinv[(size_t)i * cap + j] += ds[i] * ds[j] / delta;
                 }
                 D = m;
-            } else if (threadIdx.x == 0) kb.flags[l] |= KB_FLAG_DICT_CAP;
-            __syncthreads();
+            } else if (gt == 0) kb.flags[l] |= KB_FLAG_DICT_CAP;
+            gsync<GROUP>(group);
         }
         cur = astar + 1;
     }
-    if (threadIdx.x == 0) {
+    if (gt == 0) {
         kb.D[l] = D;
         if (n_updates) atomicAdd(kb.updates, (unsigned long long)n_updates);
     }
@@ -360,7 +400,7 @@ struct kb_handle {
     kb_config cfg;
     kb::State st;
     kb::Control ctl;
-    size_t smem_bytes;
+    size_t smem_update, smem_predict;
     cudaStream_t stream;
     float *d_state;
     int32_t *d_action, *d_labels, *d_out;
@@ -370,6 +410,7 @@ struct kb_handle {
 // error text is shared with ranslice_cabi.cu through rs_set_error
 extern "C" void rs_set_error(const char *msg);
 namespace {
+constexpr int UG = kb::Cfg<KB_GROUP_UPDATE>::GROUPS, PG = kb::Cfg<KB_GROUP_PREDICT>::GROUPS;
 int kfail(int code, const std::string &m) { rs_set_error(m.c_str()); return code; }
 }
 #define KCU(call)                                                                                  \
@@ -415,9 +456,10 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     KCU(cudaMalloc(&h->d_labels, L * sizeof(int32_t)));
     KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
     KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    h->smem_bytes = (size_t)(5 * cap + kb::MAX_CAND) * sizeof(double) + (size_t)cap * sizeof(float4);
-    KCU(cudaFuncSetAttribute(kb::update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    KCU(cudaFuncSetAttribute(kb::predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    h->smem_update = (size_t)kb::Cfg<KB_GROUP_UPDATE>::GROUPS * cap * kb::GROUP_SMEM_PER_LANDMARK;
+    h->smem_predict = (size_t)kb::Cfg<KB_GROUP_PREDICT>::GROUPS * cap * kb::GROUP_SMEM_PER_LANDMARK;
+    KCU(cudaFuncSetAttribute(kb::update_kernel<KB_GROUP_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update));
+    KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict));
     *out = h;
     return kb_reset(h);
 }
@@ -450,7 +492,7 @@ int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action
     KCU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, d_y_pred, kb::Control{}, nullptr);
+    kb::update_kernel<KB_GROUP_UPDATE><<<(h->st.L + UG - 1) / UG, kb::Cfg<KB_GROUP_UPDATE>::THREADS, h->smem_update, st>>>(h->st, d_state, d_action, d_labels, d_y_pred, kb::Control{}, nullptr);
     h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
@@ -487,7 +529,7 @@ int kb_control_update_device(kb_handle *h, const float *d_state, const int32_t *
     KCU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    kb::update_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, d_action, d_labels, nullptr, h->ctl, d_hits);
+    kb::update_kernel<KB_GROUP_UPDATE><<<(h->st.L + UG - 1) / UG, kb::Cfg<KB_GROUP_UPDATE>::THREADS, h->smem_update, st>>>(h->st, d_state, d_action, d_labels, nullptr, h->ctl, d_hits);
     h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
@@ -498,7 +540,7 @@ int kb_control_select_device(kb_handle *h, const float *d_state, int32_t *d_acti
     if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
     KCU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    kb::predict_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, st>>>(h->st, d_state, h->ctl.first);
+    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict, st>>>(h->st, d_state, h->ctl.first);
     kb::select_kernel<<<(h->cfg.n_envs + 127) / 128, 128, 0, st>>>(h->st, h->ctl, d_action, d_adjusted);
     h->launches += 2;
     KCU(cudaGetLastError());
@@ -523,7 +565,7 @@ int kb_control_get(kb_handle *h, int32_t *action, int32_t *security_factors, int
 int kb_predict_device(kb_handle *h, const float *d_state, int32_t *d_first_pos, void *stream) {
     if (!h || !d_state || !d_first_pos) return kfail(RS_E_ARG, "null argument");
     KCU(cudaSetDevice(h->cfg.device));
-    kb::predict_kernel<<<h->st.L, kb::THREADS, h->smem_bytes, (cudaStream_t)stream>>>(h->st, d_state, d_first_pos);
+    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict, (cudaStream_t)stream>>>(h->st, d_state, d_first_pos);
     h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
