@@ -86,6 +86,9 @@ __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0
     }
     int qq = q;
     while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
     for (; q + 4 <= q_last; q += 4) {                        // interior quads, 4 independent loads in flight
         int i0 = qq, i1 = qq + 1, i2 = qq + 2, i3 = qq + 3;
         if (i1 >= QUADS_PER_COL) i1 -= QUADS_PER_COL;
@@ -96,6 +99,9 @@ __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0
         qq += 4;
         if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
     }
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
     for (; q < q_last; ++q) {                                // remaining interior quads: no masks
         const int4 v = LDQ_B(col4 + qq);
         sum += (long long)quad_total(v);

@@ -129,6 +129,9 @@ __device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView
     if (clock == next_dep) {                                                      // departures, :251-261 (order kept)
         int w = 0;
         uint32_t nd = DEP_NEVER;
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
         for (int k = 0; k < n_ues; ++k) {
             const uint32_t d = cold[k].dep_at;
             if (d != clock) {
@@ -217,6 +220,9 @@ __device__ __noinline__ int pf_exact_argmax(const SmemView &v, int tid, int n_ue
     const float lim = best * (1.0f - 1e-6f);
     double best64 = -1.0;
     int idx = 0;
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
     for (int k = 0; k < n_ues; ++k) {
         const float m = v.metf[SIX(k)];
         if (m >= lim && m > 0.0f) {
@@ -288,6 +294,9 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
     bool dead = pad;                                             // aborted (replayed by the general kernel) or idle pad lane
 
     // ---- gather the unit's records into shared memory (once per step)
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
     for (int k = 0; k < n_ues; ++k) {
         UeRec r;
         load_rec(ue + k, r);
@@ -332,6 +341,9 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
         int n_backlog = 0;
         int sn_all = 0, sn_v = 0, cnt_all = 0, cnt_v = 0;
         long long qsum_all = 0, qsum_v = 0;
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
         for (int k = 0; k < n_ues; ++k) {
             uint32_t meta = v.meta[SIX(k)];
             const int ty = (int)(meta & 1u);
@@ -397,6 +409,7 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
         int st_iters = 0, st_prev = -1, st_same = 0;
 #endif
         if (scheduled) {
+#pragma unroll 1
             for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= (int)0xFFFFFF00; }   // ue_bits, ue_rbs
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
             int r = 0;
@@ -408,6 +421,7 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 metric, exact when close
                 int idx = 0;
                 float best = v.metf[SIX(0)], second = -1.0f;
+#pragma unroll 1
                 for (int k = 1; k < n_ues; ++k) {
                     const float m = v.metf[SIX(k)];
                     if (m > best) { second = best; best = m; idx = k; }
@@ -525,6 +539,9 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
             // ---- per-UE reception (schedulers.py:66-76, slice_l1.py:219-224) + transmission_step (slice_ran.py:51-55)
             __syncwarp(sched_mask);
             int o = 0;
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
             for (int k = 0; k < n_ues; ++k) {
                 {
                     const int pe = v.pe[SIX(k)];
@@ -580,6 +597,7 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
                 }
             }
         } else {
+#pragma unroll 1
             for (int k = 0; k < n_ues; ++k) {                    // nothing touched: stale bits / prbs accumulate
                 const int ty = (int)(v.meta[SIX(k)] & 1u);
                 const int b = v.bits[SIX(k)], prbs = v.pe[SIX(k)] & 0xFF, queue = v.queue[SIX(k)];
@@ -601,6 +619,9 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
         return;
     }
     // ---- scatter the records back (once per step) and persist the slice scalars
+#ifndef RS_NO_UNROLL2
+#pragma unroll 1
+#endif
     for (int k = 0; k < n_ues; ++k) {
         ColdRec c;
         load_cold(cold + k, c);
