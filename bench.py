@@ -32,6 +32,25 @@ BASE_SEED = 20260000
 METRIC = "batched env-steps/sec (scenario_0)"
 
 
+# stdout carries exactly ONE line (the JSON): everything else a library prints at C level (NCCL's version banner ...)
+# is diverted to stderr by pointing fd 1 at fd 2 for the duration of the run.
+_REAL_STDOUT = None
+
+
+def _divert_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def simplex_actions(rng, N, S, n_prbs):
     w = rng.random((N, S + 1), dtype=np.float32)
     return np.floor(n_prbs * w[:, :S] / w.sum(axis=1, keepdims=True)).astype(np.int32)
@@ -116,7 +135,7 @@ def run_reference_arm(args):
                                "reference itself measured 8.5 env-steps/s/core in the build container (BASELINE.md)"},
             "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -132,6 +151,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _divert_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -142,8 +162,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"           # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -264,7 +282,7 @@ def main():
             line["cpu_baseline"] = {"value": val, "unit": "env-steps/s", "cores": threads, "kind": "port",
                                     "sample": "%d envs x 20 steps after %d burn-in steps, %d pthreads (oracle C port; "
                                               "Python reference: 8.5 env-steps/s/core, BASELINE.md)" % (n_cpu, burn, threads)}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()
