@@ -67,6 +67,7 @@ __device__ __forceinline__ int wrap_quad(int q) {             // q < 3 * QUADS_P
     q -= q >= QUADS_PER_COL ? QUADS_PER_COL : 0;
     return q;
 }
+template <int WIDE = 0>
 __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0, int n) {
     const int4 *col4 = reinterpret_cast<const int4 *>(col);
     const int lo = row0, hi = row0 + n;                      // absolute rows, may run past 100 (wrap)
@@ -86,6 +87,20 @@ __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0
     }
     int qq = q;
     while (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    if (WIDE) {                                              // latency variant (small batches): 16 independent loads in flight
+#pragma unroll 1
+        for (; q + 16 <= q_last; q += 16) {
+            int4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { int i = qq + j; if (i >= QUADS_PER_COL) i -= QUADS_PER_COL; v[j] = LDQ_B(col4 + i); }
+            long long part = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) part += (long long)quad_total(v[j]) + (long long)quad_total(v[j + 1]);
+            sum += part;
+            qq += 16;
+            if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+        }
+    }
 #ifndef RS_NO_UNROLL2
 #pragma unroll 1
 #endif

@@ -245,7 +245,12 @@ __device__ __forceinline__ int log2_bucket(int x) { return x <= 0 ? 0 : min(1 + 
 #ifndef RS_SM_BLOCKS
 #define RS_SM_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const __grid_constant__ StepParams p,
+#ifndef RS_WIDE_BLOCKS
+#define RS_WIDE_BLOCKS 2
+#endif
+// WIDE = 1: latency variant for batches that cannot fill the GPU (more registers per thread, deeper load batches)
+template <int WIDE>
+__global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOCKS) embb_step_smem(const __grid_constant__ StepParams p,
                                                                 const __grid_constant__ EmbbState st,
                                                                 const __grid_constant__ Tables tb) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(SM_THREADS, RS_SM_BLOCKS) embb_step_smem(const
                 meta = pack_meta(ty, fading, step, index);
                 v.meta[SIX(k)] = meta;
                 const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
-                const long long isum = window_sum_fix(tb.trace_fix + col_off, row_base, n_prbs);
+                const long long isum = window_sum_fix<WIDE>(tb.trace_fix + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
                 const double nominal = v.nominal[SIX(k)];
                 double mean = (double)isum * inv_n + nominal;    // |mean - reference mean| < 2^-25 + few ulp
@@ -673,15 +678,17 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
     constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
     static_assert(RS_SM_BLOCKS * (smem_bytes + 2048 + 1024) <= 227 * 1024, "RS_SM_BLOCKS blocks per SM must fit");
     if (!configured) {
-        cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaFuncSetAttribute(embb_step_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaFuncSetAttribute(embb_step_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 #ifdef RS_CARVEOUT
-        cudaFuncSetAttribute(embb_step_smem, cudaFuncAttributePreferredSharedMemoryCarveout, RS_CARVEOUT);   // experiment: percent of the 228 KB
+        cudaFuncSetAttribute(embb_step_smem<0>, cudaFuncAttributePreferredSharedMemoryCarveout, RS_CARVEOUT);   // experiment: percent of the 228 KB
 #endif
         configured = true;
     }
     launch_embb_sort(p, st, SM_MAX_START_UES_PAIR, SM_MAX_START_UES + 1, stream);
     const int blocks = (st.perm_len + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
-    embb_step_smem<<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
+    if (st.wide) embb_step_smem<1><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
+    else embb_step_smem<0><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     launch_embb_general(p, st, tb, 1, stream);
     return 5;   // kernels launched
 }

@@ -57,6 +57,7 @@ static_assert(sizeof(UnitHdr) == 32, "UnitHdr must be 32 bytes");
 
 struct EmbbState {
     int U, K, MB;          // units, UE records per unit, burst slots per UE (== MAX_BURSTS)
+    int wide;              // 1: launch the latency variant of the shared-memory kernel (small batches)
     int dil, perm_len;     // lane dilution (log2) of the shared-memory kernel's front list and the length of perm[]: when a batch
                            // cannot fill the GPU, every 2^dil-th lane carries a unit and the rest idle -- fewer divergent units
                            // per warp shorten the slowest warp, which is what a step of a small batch waits for
