@@ -414,8 +414,14 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
         int st_iters = 0, st_prev = -1, st_same = 0;
 #endif
         if (scheduled) {
+            {   // ue_bits = 0, ue_rbs = 0 (stepped slot address, see the scan below)
+                int *bp = v.bits + tid, *pp = v.pe + tid;
+                const int n_own = min(n_ues, SM_KS);
 #pragma unroll 1
-            for (int k = 0; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= (int)0xFFFFFF00; }   // ue_bits, ue_rbs
+                for (int k = 0; k < n_own; ++k) { *bp = 0; *pp &= (int)0xFFFFFF00; bp += SM_THREADS; pp += SM_THREADS; }
+#pragma unroll 1
+                for (int k = SM_KS; k < n_ues; ++k) { v.bits[SIX(k)] = 0; v.pe[SIX(k)] &= (int)0xFFFFFF00; }
+            }
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63); queue left = queue - ue_bits
             int r = 0;
             // phase 1: contended chunks (>= 2 backlogged UEs); one uniform loop body for all lanes still in it
@@ -424,13 +430,28 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
                 if (RS_EXP & 8) break;
                 const int c = min(n_prbs - r, 2);
                 // argmax of rate * (queue > 0) / th, first maximum (np.argmax): fp32 metric, exact when close
+                // (the slot address is stepped instead of recomputed: SIX(k) is 6 of the 15 instructions of a scan step;
+                //  slots 8.. of a pair-owning unit sit in the neighbouring lane's column)
                 int idx = 0;
-                float best = v.metf[SIX(0)], second = -1.0f;
+                const float *mp = v.metf + tid;
+                float best = *mp, second = -1.0f;
+                const int n_own = min(n_ues, SM_KS);
 #pragma unroll 1
-                for (int k = 1; k < n_ues; ++k) {
-                    const float m = v.metf[SIX(k)];
+                for (int k = 1; k < n_own; ++k) {
+                    mp += SM_THREADS;
+                    const float m = *mp;
                     if (m > best) { second = best; best = m; idx = k; }
                     else second = fmaxf(second, m);
+                }
+                if (n_ues > SM_KS) {
+                    mp = v.metf + tid + 1 - SM_THREADS;
+#pragma unroll 1
+                    for (int k = SM_KS; k < n_ues; ++k) {
+                        mp += SM_THREADS;
+                        const float m = *mp;
+                        if (m > best) { second = best; best = m; idx = k; }
+                        else second = fmaxf(second, m);
+                    }
                 }
 #ifdef RS_STATS
                 if (second >= best * (1.0f - 1e-6f)) STAT(2, 1);
