@@ -32,7 +32,8 @@ namespace kb {
 
 // Threads per learner.  Measured in the config-3 loop (16 384 envs, D mean 27, cap 128; tools/gpu_kb_sweep.sh):
 //   update_kernel   32: 8.9 ms   64: 5.4 ms   128: 3.9 ms   256: 3.4 ms   -- work-bound per learner (K^-1 mat-vec and rank-1
-//                   extension over D^2 elements, <= 201 candidates x D terms per round): wide groups win
+//                   extension over D^2 elements, <= 201 candidates x D terms per round): wide groups win; routing
+//                   learners with D <= 16/32/64 to a warp each and the rest to a CTA each: 3.9-4.0 vs 3.8 ms (no gain)
 //   predict_kernel  32: 0.44 ms  128: 0.54 ms  256: 0.62 ms               -- one short pass: more learners in flight win
 #ifndef KB_GROUP_UPDATE
 #define KB_GROUP_UPDATE 256
@@ -251,8 +252,16 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
     bool first_round = true;
     unsigned n_updates = 0;
     gsync<GROUP>(group);
+    // The dictionary is staged from HBM once; a round's update is mirrored into the staged copy (the state part of
+    // a new landmark equals the current state exactly, so its base distance is 0 and becomes the new minimum).
+    bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
+    const double g2 = kb.gamma * 1.4426950408889634;
+    // E-learner inputs, loaded early so that their latency hides behind the first evaluation round
+    const int ctl_margin = ctl.acc ? max(0, ctl.margins[l]) : 0;
+    const int ctl_adjusted = ctl.acc ? ctl.adjusted[env] : 0;
+    double acc_v = 0.0;
+    if (ctl.acc && gt < n) acc_v = ctl.acc[(size_t)l * n + gt];
     while (cur <= hi) {
-        const bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
         if (gt == 0) g.first = 1 << 30;
         gsync<GROUP>(group);
         int first = 1 << 30;
@@ -269,13 +278,13 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
             first_round = false;
             if (ctl.acc) {                                     // E-learner part of update_control (kbrl_control.py:90-101)
                 const bool hit = y == yp;
-                const int margin = max(0, ctl.margins[l]);
+                const int margin = ctl_margin;
                 const double om = 1.0 - ctl.alfa;
                 double *acc = ctl.acc + (size_t)l * n;
                 if (gt == 0) g.sf = 1 << 30;
                 gsync<GROUP>(group);
                 for (int i = gt; i < n; i += GROUP) {
-                    double v = acc[i];
+                    double v = i == gt ? acc_v : acc[i];
                     if (yp == 1) {
                         if (!hit) { if (i <= margin) { v = om * v; acc[i] = v; } }            // same or less margin: same mistake
                         else if (i >= margin) { v = om * v + ctl.alfa; acc[i] = v; }          // same or more margin: same success
@@ -284,7 +293,7 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
                 }
                 gsync<GROUP>(group);
                 if (gt == 0) {
-                    if (!ctl.adjusted[env]) ctl.sec[l] = g.sf == (1 << 30) ? 0 : g.sf;
+                    if (!ctl_adjusted) ctl.sec[l] = g.sf == (1 << 30) ? 0 : g.sf;
                     if (hits) hits[l] = hit ? 1 : 0;
                 }
             }
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
             }
             gsync<GROUP>(group);
             D = g.D;
+            fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);   // float32 stage: tiny, re-staged
         } else {
             for (int j = gt; j < D; j += GROUP) { const double t = ll[j] - xa; kf[j] = exp(-kb.gamma * (base[j] + t * t)); }
             gsync<GROUP>(group);
@@ -338,13 +348,17 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
             gsync<GROUP>(group);
             const double delta = g.delta;
             if (delta <= kb.eta) {                                    // sv.update(y * d_star)
-                for (int i = gt; i < D; i += GROUP) coeff[i] += (double)y * ds[i];
+                for (int i = gt; i < D; i += GROUP) {
+                    const double c = coeff[i] + (double)y * ds[i];
+                    coeff[i] = c; cf[i] = c; fast[i].y = (float)c;
+                }
             } else if (D < cap) {                                     // sv.extend / insert + rank-1 extension of K^-1
                 if (gt == 0) {
                     for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
                     lm[(size_t)D * MAX_DIM + d - 1] = xa;
                     coeff[D] = (double)y;
                     ds[D] = -1.0;
+                    base[D] = 0.0; cf[D] = (double)y; ll[D] = xa;          // staged copy of the new landmark
                 }
                 for (int i = gt; i <= D; i += GROUP) { kinv[(size_t)i * cap + D] = 0.0; kinv[(size_t)D * cap + i] = 0.0; }
                 gsync<GROUP>(group);
@@ -354,6 +368,9 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
                     kinv[(size_t)i * cap + j] += ds[i] * ds[j] / delta;
                 }
                 D = m;
+                for (int j = gt; j < D; j += GROUP)                      // fp32 copy relative to the new minimum (0)
+                    fast[j] = make_float4((float)(g2 * base[j]), (float)cf[j], (float)ll[j], 0.f);
+                fast_ok = !kb.exact_only;
             } else if (gt == 0) kb.flags[l] |= KB_FLAG_DICT_CAP;
             gsync<GROUP>(group);
         }
