@@ -49,7 +49,10 @@ __device__ __forceinline__ uint32_t contention_class(uint32_t hint, int n_now, i
 }
 constexpr uint32_t HEAVY_BIT = 1u << 15;   // units that own a pair of lanes sort ahead of everything else
 __device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ues, int slots, bool heavy) {
-    return (heavy ? HEAVY_BIT : 0u) | ((uint32_t)n_prbs << 7) | (contention_class(hint, n_prbs, slots) << 4) | (uint32_t)min(n_ues, 15);
+    // Key order measured on B200 (65 536 envs, M env-steps/s): (n_prbs, class, UEs) 12.43 | (n_prbs, UEs, class) 12.85 |
+    // (n_prbs/4, UEs, class) 13.04 | (class, n_prbs, UEs) 12.32 | (UEs, class, n_prbs) 13.26 | (UEs, n_prbs, class) 13.41;
+    // a second hint (UEs served per TTI in the previous step) on top of the last one: 13.35 (no gain)
+    return (heavy ? HEAVY_BIT : 0u) | ((uint32_t)min(n_ues, 15) << 11) | ((uint32_t)n_prbs << 3) | contention_class(hint, n_prbs, slots);
 }
 
 // ---------------------------------------------------------------------------------------------

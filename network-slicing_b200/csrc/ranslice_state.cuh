@@ -67,14 +67,14 @@ struct EmbbState {
     int32_t *cur_prbs;     // [U] PRBs in force (after clamping)
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
-    int32_t *perm;         // [perm_len = 2U << dil] front: unit ids sorted by descending (n_prbs, contention class, live UEs); list L grows down from the end
+    int32_t *perm;         // [perm_len = 2U << dil] front: unit ids sorted by descending (live UEs, n_prbs, contention class); list L grows down from the end
     uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
     uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
     ColdRec *cold;         // [U][K] per-step scratch of the shared-memory kernel
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
-constexpr int SORT_BINS = 65536;   // key = pair-of-lanes bit << 15 | n_prbs << 7 | contention class (3 bits) << 4 | min(live UEs, 15)
+constexpr int SORT_BINS = 65536;   // key = pair-of-lanes bit << 15 | min(live UEs, 15) << 11 | n_prbs << 3 | contention class (3 bits)
 
 struct MmtcState {
     int U, Q;              // units (env * n_mmtc + m), backlog cap
