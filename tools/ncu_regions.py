@@ -50,8 +50,15 @@ for (name, lo), (_, hi) in zip(m[:-1], m[1:]):
     i, t, s = agg("embb_smem.cu", lo, hi)
     print("%-36s inst %5.1f%% lanes %5.1f samp %5.1f%%" % (name, 100 * i / tot, t / max(i, 1), 100 * s / tots))
 first = m[0][1]
-for name, (f, lo, hi) in [("ran_events_smem + vbr_step (helpers)", ("embb_smem.cu", 1, first)), ("window_sum_q24", ("embb_fastmath.cuh", 50, 101)),
-                          ("fastmath exact paths", ("embb_fastmath.cuh", 101, 400)), ("philox", ("philox.cuh", 1, 200)), ("embb_device.cuh", ("embb_device.cuh", 1, 400)),
+fm = open(os.path.join(root, "network-slicing_b200", "csrc", "embb_fastmath.cuh")).read().split("\n")
+def fm_find(t):
+    for i, l in enumerate(fm):
+        if t in l:
+            return i + 1
+    raise KeyError(t)
+ws_lo, ws_hi = fm_find("// Exact integer sum of the window"), fm_find("// exact fp64 window mean")
+for name, (f, lo, hi) in [("ran_events_smem + vbr_step (helpers)", ("embb_smem.cu", 1, first)), ("window_sum_fix", ("embb_fastmath.cuh", ws_lo, ws_hi)),
+                          ("fastmath exact paths", ("embb_fastmath.cuh", ws_hi, 400)), ("philox", ("philox.cuh", 1, 200)), ("embb_device.cuh", ("embb_device.cuh", 1, 400)),
                           ("__syncwarp", ("sm_30_intrinsics.hpp", 1, 1000))]:
     i, t, s = agg(f, lo, hi)
     print("%-36s inst %5.1f%% lanes %5.1f samp %5.1f%%" % (name, 100 * i / tot, t / max(i, 1), 100 * s / tots))
