@@ -67,6 +67,7 @@ __device__ __forceinline__ int wrap_quad(int q) {             // q < 3 * QUADS_P
     q -= q >= QUADS_PER_COL ? QUADS_PER_COL : 0;
     return q;
 }
+#ifdef RS_WSUM_V1
 template <int WIDE = 0>
 __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0, int n) {
     const int4 *col4 = reinterpret_cast<const int4 *>(col);
@@ -133,6 +134,68 @@ __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0
     }
     return sum;
 }
+#else
+// Every wait on a load below is an L2 round trip (each lane reads its own column), and those waits are a third of the
+// kernel's stall samples; so the first quad, the last quad and the 1..3 interior quads that do not fill a batch of four
+// are all issued together, and only the full batches wait once each: a 33-PRB window costs 2 round trips instead of 6.
+template <int WIDE = 0>
+__device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0, int n) {
+    const int4 *col4 = reinterpret_cast<const int4 *>(col);
+    const int lo = row0, hi = row0 + n;                      // absolute rows, may run past 100 (wrap)
+    const int qf = lo >> 2, ql = (hi - 1) >> 2;              // first / last quad (qf <= 24: no wrap)
+    const int n_int = ql - qf - 1;                           // interior quads (-1: the window sits in one quad)
+    const int rem = n_int > 0 ? (n_int & 3) : 0;             // taken from the END of the interior: quads ql-rem .. ql-1
+    const int4 zero = make_int4(0, 0, 0, 0);
+    const int4 vf = LDQ_B(col4 + qf);
+    int4 vl = zero, r0 = zero, r1 = zero, r2 = zero;
+    if (ql != qf) vl = LDQ_B(col4 + wrap_quad(ql));
+    if (rem > 0) r0 = LDQ_B(col4 + wrap_quad(ql - 1));
+    if (rem > 1) r1 = LDQ_B(col4 + wrap_quad(ql - 2));
+    if (rem > 2) r2 = LDQ_B(col4 + wrap_quad(ql - 3));
+    long long sum;
+    {   // first quad (masked below lo and at/after hi), last quad (masked at/after hi; all zero when ql == qf)
+        const int bf = qf << 2, bl = ql << 2;
+        int s = (bf + 0 >= lo && bf + 0 < hi) ? vf.x : 0;
+        s += (bf + 1 >= lo && bf + 1 < hi) ? vf.y : 0;
+        s += (bf + 2 >= lo && bf + 2 < hi) ? vf.z : 0;
+        s += (bf + 3 >= lo && bf + 3 < hi) ? vf.w : 0;
+        int t = (bl + 0 < hi) ? vl.x : 0;
+        t += (bl + 1 < hi) ? vl.y : 0;
+        t += (bl + 2 < hi) ? vl.z : 0;
+        t += (bl + 3 < hi) ? vl.w : 0;
+        sum = ((long long)s + (long long)t) + (((long long)quad_total(r0) + (long long)quad_total(r1)) + (long long)quad_total(r2));
+    }
+    int qq = qf + 1;                                         // wrapped index of the next interior quad
+    qq -= qq >= QUADS_PER_COL ? QUADS_PER_COL : 0;
+    int batches = n_int > 0 ? (n_int >> 2) : 0;
+    if (WIDE) {                                              // latency variant (small batches): 16 independent loads in flight
+#pragma unroll 1
+        for (; batches >= 4; batches -= 4) {
+            int4 v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { int i = qq + j; if (i >= QUADS_PER_COL) i -= QUADS_PER_COL; v[j] = LDQ_B(col4 + i); }
+            long long part = 0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) part += (long long)quad_total(v[j]) + (long long)quad_total(v[j + 1]);
+            sum += part;
+            qq += 16;
+            if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+        }
+    }
+#pragma unroll 1
+    for (; batches > 0; --batches) {                         // interior quads, 4 independent loads in flight
+        int i1 = qq + 1, i2 = qq + 2, i3 = qq + 3;
+        if (i1 >= QUADS_PER_COL) i1 -= QUADS_PER_COL;
+        if (i2 >= QUADS_PER_COL) i2 -= QUADS_PER_COL;
+        if (i3 >= QUADS_PER_COL) i3 -= QUADS_PER_COL;
+        const int4 v0 = LDQ_B(col4 + qq), v1 = LDQ_B(col4 + i1), v2 = LDQ_B(col4 + i2), v3 = LDQ_B(col4 + i3);
+        sum += ((long long)quad_total(v0) + (long long)quad_total(v1)) + ((long long)quad_total(v2) + (long long)quad_total(v3));
+        qq += 4;
+        if (qq >= QUADS_PER_COL) qq -= QUADS_PER_COL;
+    }
+    return sum;
+}
+#endif
 
 // exact fp64 window mean (same operation order as embb_step.cu); rare
 static __device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
