@@ -1,4 +1,5 @@
-// K1 default variant ("sorted unit-per-thread, guarded fast math").
+// K1 general variant ("sorted unit-per-thread, guarded fast math", state in global memory) + the sort pre-pass shared
+// with the default shared-memory kernel (embb_smem.cu).
 //
 // Same algorithm and results as embb_step.cu (bit-exact: tests compare both against the oracle), but
 // organised for lane utilisation and instruction count on B200.  One thread still owns one
@@ -6,7 +7,7 @@
 // how each decision is evaluated:
 //
 //  * window_kernel / scan_kernel / scatter_kernel sort the units of a step (counting sort) by
-//    (n_prbs, PF contention class, live UEs), descending.  Every inner loop of the step has a trip
+//    (live UEs, n_prbs, PF contention class), descending.  Every inner loop of the step has a trip
 //    count given by one of those three numbers (window mean: UEs x PRBs, MI: PRBs, PF: contended RB
 //    chunks), so after the sort the 32 lanes of a warp run the same loops the same number of times.
 //    The unsorted variant measured 6.2 of 32 lanes active per instruction.

@@ -1,6 +1,6 @@
 // K1 default variant: the unit's UE table stays in SHARED MEMORY for the whole observation period.
 //
-// Same algorithm, same guarded fast math and same PRB-sorted thread->unit mapping as embb_fast.cu
+// Same algorithm, same guarded fast math and same sorted thread->unit mapping as embb_fast.cu
 // (which remains the general kernel).  What changes is where the state lives during the 50 TTIs:
 // the general kernel re-reads and re-writes every 64-byte UE record in global memory each TTI and
 // keeps its per-TTI PF scratch in local memory; both go through L1, which is far too small for
