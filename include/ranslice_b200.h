@@ -79,6 +79,17 @@ int rs_reset(rs_handle *h, float *obs);
 int rs_step(rs_handle *h, const int32_t *action, float *obs, float *reward, int32_t *labels,
             int32_t *violations, uint32_t *flags);
 
+/* Pipelined variant of rs_step for throughput loops (no reference equivalent: the reference is synchronous).
+ * rs_step_async enqueues H2D(action) + kernels on the handle's compute stream and the D2H of the results on its
+ * copy stream, and returns at once with a ticket (0 or 1, alternating); rs_wait blocks until the results of that
+ * ticket are in the caller's host buffers.  Two steps may be in flight: the copies of step i overlap the kernels of
+ * step i+1 (device outputs are double-buffered).  The action and output buffers of a ticket must stay valid and
+ * untouched until rs_wait(ticket) returns; pinned memory is needed for the overlap.  Results are identical to
+ * rs_step.  Do not mix with rs_step / rs_step_device while a ticket is outstanding. */
+int rs_step_async(rs_handle *h, const int32_t *action, float *obs, float *reward, int32_t *labels,
+                  int32_t *violations, uint32_t *flags, int32_t *ticket);
+int rs_wait(rs_handle *h, int32_t ticket);
+
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t; NULL = legacy default). */
 int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d_reward,
                    int32_t *d_labels, int32_t *d_violations, uint32_t *d_flags, void *stream);

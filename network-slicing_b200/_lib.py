@@ -48,6 +48,8 @@ def lib():
     L.rs_reset.argtypes = [vp, vp]
     L.rs_step.argtypes = [vp] + [vp] * 6
     L.rs_step_device.argtypes = [vp] + [vp] * 6 + [vp]
+    L.rs_step_async.argtypes = [vp] + [vp] * 6 + [C.POINTER(i32)]
+    L.rs_wait.argtypes = [vp, i32]
     L.rs_get_info.argtypes = [vp, i32, vp, vp]
     L.rs_get_n_ues.argtypes = [vp, vp]
     L.rs_state_size.argtypes = [vp, C.POINTER(C.c_size_t)]
@@ -63,7 +65,7 @@ def lib():
     L.rs_last_error.restype = C.c_char_p
     for name in ("rs_create", "rs_destroy", "rs_reset", "rs_step", "rs_step_device", "rs_get_info", "rs_get_n_ues",
                  "rs_state_size", "rs_get_state", "rs_set_state", "rs_get_counters", "rs_n_variables",
-                 "rs_set_profiling", "rs_get_profile", "rs_set_debug_check", "rs_get_diag"):
+                 "rs_set_profiling", "rs_get_profile", "rs_set_debug_check", "rs_get_diag", "rs_step_async", "rs_wait"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -100,6 +100,36 @@ class BatchedRanSlice:
                                       _p(hb['violations']), _p(hb['flags'])))
         return hb
 
+    def alloc_host_buffers(self):
+        """A fresh set of (pinned) host output buffers for :meth:`step_host_async`: dict of numpy arrays."""
+        N, S, V = self.n_envs, self.n_slices, self.n_variables
+        try:
+            import torch
+            pin = torch.cuda.is_available()
+            t = dict(obs=torch.empty((N, V), dtype=torch.float32, pin_memory=pin), reward=torch.empty((N,), dtype=torch.float32, pin_memory=pin),
+                     labels=torch.empty((N, S), dtype=torch.int32, pin_memory=pin), violations=torch.empty((N, S), dtype=torch.int32, pin_memory=pin),
+                     flags=torch.empty((N,), dtype=torch.int32, pin_memory=pin))
+            hb = {k: v.numpy() for k, v in t.items()}
+            hb['flags'] = hb['flags'].view(np.uint32)
+            hb['_pin'] = t
+            return hb
+        except ImportError:
+            return dict(obs=np.empty((N, V), np.float32), reward=np.empty(N, np.float32), labels=np.empty((N, S), np.int32),
+                        violations=np.empty((N, S), np.int32), flags=np.empty(N, np.uint32))
+
+    def step_host_async(self, action_i32, hb):
+        """Pipelined ``step``: enqueue H2D + kernels + D2H and return a ticket at once; ``wait(ticket)`` blocks until
+        the results are in ``hb`` (from :meth:`alloc_host_buffers`).  Two steps may be in flight, so alternate
+        between two buffer sets; ``action_i32`` (int32 [N,S], ideally pinned) and ``hb`` must stay untouched until
+        the wait.  Same results as ``step``."""
+        t = C.c_int32()
+        _lib.check(_lib.lib().rs_step_async(self._h, _p(action_i32), _p(hb['obs']), _p(hb['reward']), _p(hb['labels']),
+                                            _p(hb['violations']), _p(hb['flags']), C.byref(t)))
+        return int(t.value)
+
+    def wait(self, ticket):
+        _lib.check(_lib.lib().rs_wait(self._h, int(ticket)))
+
     def step_device(self, action, out=None):
         """torch int32 CUDA tensor [N,S] -> dict of CUDA tensors; async on the current torch stream."""
         import torch

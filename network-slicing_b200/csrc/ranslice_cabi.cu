@@ -54,6 +54,14 @@ struct rs_handle {
     unsigned long long *d_trace_elems;
     cudaStream_t stream;
     cudaStream_t side_stream;                // mMTC kernels run here, concurrently with the eMBB kernels of the same step
+    // rs_step_async: copy stream + double-buffered device I/O (set 0 aliases d_action / d_obs / ...)
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_kernels[2], ev_copied[2];
+    int32_t *a_action[2];
+    float *a_obs[2], *a_reward[2];
+    int32_t *a_labels[2], *a_violations[2];
+    uint32_t *a_flags[2];
+    int async_slot;
     cudaEvent_t ev_fork, ev_join;
     uint64_t launches;
     bool was_reset;
@@ -240,6 +248,20 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     h->d_slow_paths = h->d_trace_elems + 1;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&h->ev_kernels[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    }
+    h->a_action[0] = h->d_action; h->a_obs[0] = h->d_obs; h->a_reward[0] = h->d_reward; h->a_labels[0] = h->d_labels;
+    h->a_violations[0] = h->d_violations; h->a_flags[0] = h->d_flags;
+    CU(cudaMalloc(&h->a_action[1], N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->a_obs[1], N * V * sizeof(float)));
+    CU(cudaMalloc(&h->a_reward[1], N * sizeof(float)));
+    CU(cudaMalloc(&h->a_labels[1], N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->a_violations[1], N * S * sizeof(int32_t)));
+    CU(cudaMalloc(&h->a_flags[1], N * sizeof(uint32_t)));
+    h->async_slot = 1;
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     p.flags_acc = h->d_flags_acc;
@@ -260,6 +282,10 @@ int rs_destroy(rs_handle *h) {
     if (h->mmtc.U) { cudaFree(h->mmtc.arr_n); cudaFree(h->mmtc.arr); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (h->ev_kernels[i]) cudaEventDestroy(h->ev_kernels[i]); if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]); }
+    cudaFree(h->a_action[1]); cudaFree(h->a_obs[1]); cudaFree(h->a_reward[1]); cudaFree(h->a_labels[1]); cudaFree(h->a_violations[1]);
+    cudaFree(h->a_flags[1]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->prof_events) { for (auto e : *h->prof_events) cudaEventDestroy(e); delete h->prof_events; }
@@ -346,6 +372,37 @@ int rs_step(rs_handle *h, const int32_t *action, float *obs, float *reward, int3
     if (violations) CU(cudaMemcpyAsync(violations, h->d_violations, N * S * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (flags) CU(cudaMemcpyAsync(flags, h->d_flags, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return RS_OK;
+}
+
+int rs_step_async(rs_handle *h, const int32_t *action, float *obs, float *reward, int32_t *labels, int32_t *violations,
+                  uint32_t *flags, int32_t *ticket) {
+    if (!h || !action || !ticket) return fail(RS_E_ARG, "null handle/action/ticket");
+    CU(cudaSetDevice(h->cfg.device));
+    const size_t N = (size_t)h->p.N, S = (size_t)h->p.S, V = (size_t)h->p.V;
+    const int k = h->async_slot ^= 1;
+    // the kernels of this step overwrite device set k: wait until the copies of the step that used it are done
+    CU(cudaStreamWaitEvent(h->stream, h->ev_copied[k], 0));
+    CU(cudaMemcpyAsync(h->a_action[k], action, N * S * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int rc = rs_step_device(h, h->a_action[k], h->a_obs[k], h->a_reward[k], h->a_labels[k], h->a_violations[k], h->a_flags[k], h->stream);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_kernels[k], h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->ev_kernels[k], 0));
+    cudaStream_t cs = h->copy_stream;
+    if (obs) CU(cudaMemcpyAsync(obs, h->a_obs[k], N * V * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (reward) CU(cudaMemcpyAsync(reward, h->a_reward[k], N * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    if (labels) CU(cudaMemcpyAsync(labels, h->a_labels[k], N * S * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    if (violations) CU(cudaMemcpyAsync(violations, h->a_violations[k], N * S * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    if (flags) CU(cudaMemcpyAsync(flags, h->a_flags[k], N * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    CU(cudaEventRecord(h->ev_copied[k], cs));
+    *ticket = k;
+    return RS_OK;
+}
+
+int rs_wait(rs_handle *h, int32_t ticket) {
+    if (!h || ticket < 0 || ticket > 1) return fail(RS_E_ARG, "bad handle/ticket");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaEventSynchronize(h->ev_copied[ticket]));
     return RS_OK;
 }
 

@@ -231,3 +231,32 @@ def test_full_size_batch_rows_equal_small_batches_and_oracle(tables, scn, N):
         assert not (info["flags"] & ~np.uint32(1 | 2 | 8 | 16)).any() and (info["flags"] != 0).mean() < 1e-3
     for e in (big, lo, hi):
         e.close()
+
+
+def test_pipelined_host_api_matches_blocking_step():
+    """rs_step_async / rs_wait (two steps in flight, double-buffered device outputs) return exactly what rs_step does."""
+    scn, N, T = 0, 512, 25
+    S, n_prbs = SCN[scn]
+    a_env, b_env = make_env(scn, N, 99), make_env(scn, N, 99)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(3)
+    acts = [simplex_actions(rng, N, S, n_prbs) for _ in range(T)]
+    hbs = [b_env.alloc_host_buffers(), b_env.alloc_host_buffers()]
+    want = []
+    for a in acts:
+        obs, rew, _, info = a_env.step(a)
+        want.append((obs, rew, info["SLA_labels"], info["violations"], info["flags"]))
+    pending, got = None, [None] * T
+    for i, a in enumerate(acts):
+        tk = b_env.step_host_async(a, hbs[i & 1])
+        if pending is not None:
+            b_env.wait(pending[0])
+            hb = hbs[pending[1] & 1]
+            got[pending[1]] = tuple(hb[k].copy() for k in ("obs", "reward", "labels", "violations", "flags"))
+        pending = (tk, i)
+    b_env.wait(pending[0])
+    got[pending[1]] = tuple(hbs[pending[1] & 1][k].copy() for k in ("obs", "reward", "labels", "violations", "flags"))
+    for t in range(T):
+        for x, y in zip(want[t], got[t]):
+            assert np.array_equal(x, y), t
+    a_env.close(); b_env.close()
