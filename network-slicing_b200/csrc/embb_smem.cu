@@ -711,7 +711,7 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
     if (st.wide) embb_step_smem<1><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     else embb_step_smem<0><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     launch_embb_general(p, st, tb, 1, stream);
-    return 5;   // kernels launched
+    return 6;   // kernels launched
 }
 
 }  // namespace rs

@@ -219,12 +219,12 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
         if (const char *e = std::getenv("RS_WIDE")) h->embb.wide = std::atoi(e) != 0;
         h->embb.perm_len = (int)((2 * U) << dil);
         const size_t perm_len = (size_t)h->embb.perm_len;
-        sc.take<uint32_t>(U); sc.take<int32_t>(perm_len); sc.take<uint32_t>(2 * rs::SORT_BINS + 4); sc.take<uint32_t>(U); sc.take<float>(8); sc.take<rs::ColdRec>(U * (size_t)h->embb.K);
+        sc.take<uint32_t>(U); sc.take<int32_t>(perm_len); sc.take<uint32_t>(2 * rs::SORT_BINS + 4 + rs::SCAN_BLOCKS); sc.take<uint32_t>(U); sc.take<float>(8); sc.take<rs::ColdRec>(U * (size_t)h->embb.K);
         CU(cudaMalloc(&h->scratch, sc.off + 256));
         CU(cudaMemset(h->scratch, 0, sc.off + 256));
         Carver rc; rc.base = h->scratch;
         h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(perm_len);
-        h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
+        h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4 + rs::SCAN_BLOCKS); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
         h->embb.cold = rc.take<rs::ColdRec>(U * (size_t)h->embb.K);
     }
     if (h->mmtc.U) {   // arrival scratch of the mMTC scan kernel

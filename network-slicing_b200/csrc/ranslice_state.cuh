@@ -68,12 +68,13 @@ struct EmbbState {
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
     int32_t *perm;         // [perm_len = 2U << dil] front: unit ids sorted by descending (live UEs, n_prbs, contention class); list L grows down from the end
-    uint32_t *hist;        // [2 * SORT_BINS + 4] histogram, offsets / scatter cursors, then {front count, list-L count}
+    uint32_t *hist;        // [2 * SORT_BINS + 4 + SCAN_BLOCKS] histogram, offsets / scatter cursors, {front count, list-L count, -, pair entries}, block totals of the scan
     uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
     ColdRec *cold;         // [U][K] per-step scratch of the shared-memory kernel
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)
 };
 
+constexpr int SCAN_BLOCKS = 64;    // blocks of the two-kernel prefix scan over the sort bins (1024 bins each)
 constexpr int SORT_BINS = 65536;   // key = pair-of-lanes bit << 15 | min(live UEs, 15) << 11 | n_prbs << 3 | contention class (3 bits)
 
 struct MmtcState {
