@@ -74,17 +74,22 @@ typedef struct {
     double th, p;
     int prbs, e_snr;
     double snr[MAX_PRB];        /* ue.snr = windowed vector, slice_ran.py:44 */
+    int ran;                    /* RAN slice of the UE inside its L1 (0 unless the L1 multiplexes several, L1_level=False) */
     int64_t next_arrival;       /* VbrSource.steps_to_next_arrival */
     int nb;
     int64_t togo[MAX_BURST];    /* VbrSource.steps_to_go */
 } ue_t;
 
-typedef struct {
-    ue_t *ues; int n_ues;
+#define ORC_MAX_RAN 8
+typedef struct {                /* SliceRANeMBB (slice_ran.py:150-325) */
     int64_t cbr_next, vbr_next; /* slice_ran.py:185-186 */
     int64_t slot_counter;
     int64_t a_traffic[2], a_th[2], a_prb[2];
     double a_queue[2], a_snr[2];
+} ran_t;
+typedef struct {                /* SliceL1eMBB (slice_l1.py:128-228): one RAN slice, or n_embb of them when L1_level=False */
+    ue_t *ues; int n_ues;
+    int n_ran; ran_t ran[ORC_MAX_RAN];
     int i_prb, n_prbs;
 } embb_t;
 
@@ -99,7 +104,9 @@ typedef struct {
 struct orc_env {
     orc_config cfg;
     orc_tables tbl;
-    int S;
+    int S;                       /* L1 slices = action entries */
+    int n_l1_embb;               /* eMBB L1 slices: n_embb, or 1 when they are multiplexed (scenario_creator.py:156-177) */
+    double acc_ran[ORC_MAX_RAN * 2][10];   /* raw accumulators of every RAN slice after the last step, L1-major */
     embb_t *embb; mmtc_t *mmtc;
     orc_rng rng; philox_ctx px; uint32_t *ctr;
     double A, B;                 /* MCSCodeset.compute_factors(0.1) */
@@ -202,6 +209,7 @@ double orc_macro_cell(double x, double y, double logf, double A, double B) { /* 
 /* ------------------------------------------------------------------ lifecycle */
 int orc_n_variables(const orc_env *e) { return 10 * e->cfg.n_embb + 3 * e->cfg.n_mmtc; }
 int orc_n_ues(const orc_env *e, int s) { return e->embb[s].n_ues; }
+void orc_get_acc_ran(const orc_env *e, double *acc) { memcpy(acc, e->acc_ran, sizeof(double) * 10 * (size_t)(e->cfg.n_embb + e->cfg.n_mmtc)); }
 
 void orc_set_rng(orc_env *e, const orc_rng *rng) {
     if (rng) { e->rng = *rng; return; }
@@ -212,11 +220,16 @@ void orc_set_rng(orc_env *e, const orc_rng *rng) {
 
 orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed) {
     orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
-    e->cfg = *cfg; e->tbl = *tbl; e->S = cfg->n_embb + cfg->n_mmtc;
-    e->embb = (embb_t *)calloc(cfg->n_embb > 0 ? cfg->n_embb : 1, sizeof(embb_t));
-    for (int s = 0; s < cfg->n_embb; ++s) e->embb[s].ues = (ue_t *)calloc(MAX_UE, sizeof(ue_t));
+    e->cfg = *cfg; e->tbl = *tbl;
+    e->n_l1_embb = cfg->l1_mux ? (cfg->n_embb > 0) : cfg->n_embb;
+    e->S = e->n_l1_embb + cfg->n_mmtc;
+    e->embb = (embb_t *)calloc(e->n_l1_embb > 0 ? e->n_l1_embb : 1, sizeof(embb_t));
+    for (int s = 0; s < e->n_l1_embb; ++s) {
+        e->embb[s].ues = (ue_t *)calloc(MAX_UE, sizeof(ue_t));
+        e->embb[s].n_ran = cfg->l1_mux ? cfg->n_embb : 1;
+    }
     e->mmtc = (mmtc_t *)calloc(cfg->n_mmtc > 0 ? cfg->n_mmtc : 1, sizeof(mmtc_t));
-    e->ctr = (uint32_t *)calloc((size_t)e->S * ORC_N_STREAMS, sizeof(uint32_t));
+    e->ctr = (uint32_t *)calloc((size_t)(cfg->n_embb + cfg->n_mmtc + 1) * ORC_N_STREAMS, sizeof(uint32_t));
     e->px.key[0] = (uint32_t)seed; e->px.key[1] = (uint32_t)(seed >> 32); e->px.ctr = e->ctr;
     orc_set_rng(e, NULL);
     compute_factors(0.1, &e->A, &e->B);
@@ -226,32 +239,36 @@ orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed)
                      5e6 * tps, 10e6 * tps, 35.0 * sps, 10e4 * sps, 35.0 * sps};
     memcpy(e->norm_embb, ne, sizeof ne);
     for (int i = 0; i < 3; ++i) e->norm_mmtc[i] = 100.0 * sps;
-    for (int s = 0; s < cfg->n_embb; ++s) e->embb[s].n_prbs = 20;          /* scenario_creator.py:160 */
+    for (int s = 0; s < e->n_l1_embb; ++s) e->embb[s].n_prbs = 20;         /* scenario_creator.py:160 */
     for (int s = 0; s < cfg->n_mmtc; ++s) e->mmtc[s].n_prbs = 5;           /* :165 */
     return e;
 }
 
 void orc_destroy(orc_env *e) {
     if (!e) return;
-    for (int s = 0; s < e->cfg.n_embb; ++s) free(e->embb[s].ues);
+    for (int s = 0; s < e->n_l1_embb; ++s) free(e->embb[s].ues);
     for (int s = 0; s < e->cfg.n_mmtc; ++s) { free(e->mmtc[s].q_rep); free(e->mmtc[s].q_t0); }
     free(e->embb); free(e->mmtc); free(e->ctr); free(e);
 }
 
-static void embb_reset_info(embb_t *s) {                                    /* slice_ran.py:270-273 */
-    for (int k = 0; k < 2; ++k) { s->a_traffic[k] = s->a_th[k] = s->a_prb[k] = 0; s->a_queue[k] = s->a_snr[k] = 0.0; }
-    s->slot_counter = 0;
+static void embb_reset_info(embb_t *l1) {                                   /* slice_ran.py:270-273, every RAN slice of the L1 */
+    for (int r = 0; r < l1->n_ran; ++r) {
+        ran_t *s = &l1->ran[r];
+        for (int k = 0; k < 2; ++k) { s->a_traffic[k] = s->a_th[k] = s->a_prb[k] = 0; s->a_queue[k] = s->a_snr[k] = 0.0; }
+        s->slot_counter = 0;
+    }
 }
 static void mmtc_reset_info(mmtc_t *m) { m->a_delay = 0; m->a_rep = 0; m->a_dev = 0; }   /* :123-125 */
 
 void orc_reset(orc_env *e, float *obs) {                                    /* node_b.py:17-22 */
-    for (int s = 0; s < e->cfg.n_embb; ++s) {                               /* slice_l1.py:145-148, slice_ran.py:182-190 */
+    for (int s = 0; s < e->n_l1_embb; ++s) {                                /* slice_l1.py:145-148, slice_ran.py:182-190 */
         embb_t *sl = &e->embb[s];
-        sl->n_ues = 0; sl->cbr_next = 0; sl->vbr_next = 0;
+        sl->n_ues = 0;
+        for (int r = 0; r < sl->n_ran; ++r) { sl->ran[r].cbr_next = 0; sl->ran[r].vbr_next = 0; }
         embb_reset_info(sl);
     }
     for (int s = 0; s < e->cfg.n_mmtc; ++s) {                               /* slice_l1.py:29-39, slice_ran.py:91-101 */
-        mmtc_t *m = &e->mmtc[s]; int gs = e->cfg.n_embb + s;
+        mmtc_t *m = &e->mmtc[s]; int gs = e->n_l1_embb + s;
         m->q_n = 0; m->time = 0; mmtc_reset_info(m);
         for (int i = 0; i < N_MTC_DEV; ++i) {
             m->reps[i] = MTC_REP_SET[e->rng.choice(e->rng.ctx, gs, ORC_STREAM_MTC, 7)];
@@ -268,7 +285,7 @@ static int64_t exp_slots(orc_env *e, int s, int stream, double scale, int div_sl
     return (int64_t)rint(div_slot ? x / 1e-3 : x);     /* np.rint(x / slot_length) */
 }
 
-static int cbr_cac(const embb_t *sl) {                                      /* slice_ran.py:195-203 */
+static int cbr_cac(const ran_t *sl) {                                       /* slice_ran.py:195-203 */
     int64_t slots = sl->slot_counter > 1 ? sl->slot_counter : 1;
     double time = slots * 1e-3;
     double cbr_prb = (double)sl->a_prb[0] / (double)slots;
@@ -325,35 +342,47 @@ static void pf_allocate(orc_env *e, embb_t *sl) {                           /* s
 
 static void embb_slot(orc_env *e, int s) {                                  /* slice_l1.py:193-228 */
     embb_t *sl = &e->embb[s];
-    ue_t arrivals[2]; int n_arr = 0;
-    /* --- slice_ran.slot(), slice_ran.py:263-268 */
-    sl->slot_counter += 1;
-    if (sl->cbr_next == 0) {                                                /* :205-227 */
-        sl->cbr_next = exp_slots(e, s, ORC_STREAM_RAN, 1.0 / (2.0 / 60.0), 1);
-        if (cbr_cac(sl)) {
-            ue_t *u = &arrivals[n_arr++]; new_ue(u, 0);
-            u->remaining = exp_slots(e, s, ORC_STREAM_RAN, 30.0, 1);
+    /* --- for slice_ran in self.slices_ran: slot(), extract_users(departures), add_users(arrivals)  (slice_l1.py:195-198).
+     * RAN draws come from the stream of the RAN slice (slice index r when the L1 multiplexes several, else s); the
+     * channel, reception and VbrSource draws from the streams of the L1 (slice index s). */
+    for (int r = 0; r < sl->n_ran; ++r) {
+        ran_t *rn = &sl->ran[r];
+        const int rs = e->cfg.l1_mux ? r : s;
+        ue_t arrivals[2]; int n_arr = 0;
+        /* --- slice_ran.slot(), slice_ran.py:263-268 */
+        rn->slot_counter += 1;
+        if (rn->cbr_next == 0) {                                            /* :205-227 */
+            rn->cbr_next = exp_slots(e, rs, ORC_STREAM_RAN, 1.0 / (2.0 / 60.0), 1);
+            if (cbr_cac(rn)) {
+                ue_t *u = &arrivals[n_arr++]; new_ue(u, 0);
+                u->remaining = exp_slots(e, rs, ORC_STREAM_RAN, 30.0, 1);
+            }
+        } else rn->cbr_next -= 1;
+        if (rn->vbr_next == 0) {                                            /* :229-249 */
+            ue_t *u = &arrivals[n_arr++]; new_ue(u, 1);
+            u->next_arrival = exp_slots(e, s, ORC_STREAM_VBR, (1.0 / 1) / 1e-3, 0);   /* traffic_generators.py:65-66 */
+            u->remaining = exp_slots(e, rs, ORC_STREAM_RAN, 30.0, 1);
+            rn->vbr_next = exp_slots(e, rs, ORC_STREAM_RAN, 1.0 / (5.0 / 60.0), 1);
+        } else rn->vbr_next -= 1;
+        /* departures(), :251-261 -- live timers of THIS RAN slice in arrival order, then this slot's arrivals */
+        int w = 0;
+        for (int i = 0; i < sl->n_ues; ++i) {
+            if (sl->ues[i].ran == r) {
+                sl->ues[i].remaining -= 1;
+                if (sl->ues[i].remaining == 0) continue;                    /* extract_users keeps the order of the rest */
+            }
+            if (w != i) sl->ues[w] = sl->ues[i];
+            ++w;
         }
-    } else sl->cbr_next -= 1;
-    if (sl->vbr_next == 0) {                                                /* :229-249 */
-        ue_t *u = &arrivals[n_arr++]; new_ue(u, 1);
-        u->next_arrival = exp_slots(e, s, ORC_STREAM_VBR, (1.0 / 1) / 1e-3, 0);   /* traffic_generators.py:65-66 */
-        u->remaining = exp_slots(e, s, ORC_STREAM_RAN, 30.0, 1);
-        sl->vbr_next = exp_slots(e, s, ORC_STREAM_RAN, 1.0 / (5.0 / 60.0), 1);
-    } else sl->vbr_next -= 1;
-    /* departures(), :251-261 -- live timers in arrival order, then this slot's arrivals */
-    int w = 0;
-    for (int i = 0; i < sl->n_ues; ++i) {
-        sl->ues[i].remaining -= 1;
-        if (sl->ues[i].remaining != 0) { if (w != i) sl->ues[w] = sl->ues[i]; ++w; }   /* extract_users keeps order */
-    }
-    sl->n_ues = w;
-    for (int k = 0; k < n_arr; ++k) {                                       /* slice_l1.py:183-186 */
-        arrivals[k].remaining -= 1;
-        if (arrivals[k].remaining == 0) { e->flags |= 8u; continue; }       /* reference crashes here */
-        if (sl->n_ues >= MAX_UE) { e->flags |= 1u; continue; }
-        insert_user(e, s, &arrivals[k]);
-        sl->ues[sl->n_ues++] = arrivals[k];
+        sl->n_ues = w;
+        for (int k = 0; k < n_arr; ++k) {                                   /* slice_l1.py:183-186 */
+            arrivals[k].remaining -= 1;
+            if (arrivals[k].remaining == 0) { e->flags |= 8u; continue; }   /* reference crashes here */
+            if (sl->n_ues >= MAX_UE) { e->flags |= 1u; continue; }
+            insert_user(e, s, &arrivals[k]);
+            arrivals[k].ran = r;
+            sl->ues[sl->n_ues++] = arrivals[k];
+        }
     }
     /* --- per-UE traffic + SNR estimate, slice_l1.py:200-213 */
     int64_t queued = 0;
@@ -407,18 +436,21 @@ static void embb_slot(orc_env *e, int s) {                                  /* s
             u->th = a * u->th + b * (double)u->bits / 1e-3;
         }
     }
-    /* --- update_info, slice_ran.py:278-305 */
-    for (int t = 0; t < 2; ++t) {
-        int64_t q = 0, snr = 0, n = 0;
-        for (int i = 0; i < sl->n_ues; ++i) {
-            ue_t *u = &sl->ues[i];
-            if (u->type != t) continue;
-            sl->a_traffic[t] += u->new_bits; sl->a_th[t] += u->bits; sl->a_prb[t] += u->prbs;
-            q += u->queue; snr += u->e_snr; n += 1;
+    /* --- update_info of every RAN slice over its own UEs, slice_ran.py:278-305 */
+    for (int r = 0; r < sl->n_ran; ++r) {
+        ran_t *rn = &sl->ran[r];
+        for (int t = 0; t < 2; ++t) {
+            int64_t q = 0, snr = 0, n = 0;
+            for (int i = 0; i < sl->n_ues; ++i) {
+                ue_t *u = &sl->ues[i];
+                if (u->type != t || u->ran != r) continue;
+                rn->a_traffic[t] += u->new_bits; rn->a_th[t] += u->bits; rn->a_prb[t] += u->prbs;
+                q += u->queue; snr += u->e_snr; n += 1;
+            }
+            if (n < 1) n = 1;
+            rn->a_queue[t] += (double)q / (double)n;
+            rn->a_snr[t] += (double)snr / (double)n;
         }
-        if (n < 1) n = 1;
-        sl->a_queue[t] += (double)q / (double)n;
-        sl->a_snr[t] += (double)snr / (double)n;
     }
 }
 
@@ -457,36 +489,43 @@ uint32_t orc_step(orc_env *e, const int64_t *action, float *obs, double *reward,
                   int32_t *violations, double *acc) {
     const orc_config *c = &e->cfg;
     e->flags = 0;
-    for (int s = 0; s < c->n_embb; ++s) embb_reset_info(&e->embb[s]);      /* node_b.py:64 */
+    for (int s = 0; s < e->n_l1_embb; ++s) embb_reset_info(&e->embb[s]);   /* node_b.py:64 */
     for (int s = 0; s < c->n_mmtc; ++s) mmtc_reset_info(&e->mmtc[s]);
     int64_t i_prb = 0, asum = 0;
     for (int s = 0; s < e->S; ++s) {                                        /* node_b.py:71-74 */
         int64_t a = action[s]; asum += a;
         if (a < 0) { a = 0; e->flags |= 4u; }
         if (i_prb + a > c->n_prbs) { a = c->n_prbs - i_prb; e->flags |= 4u; }   /* reference: undefined */
-        if (s < c->n_embb) { e->embb[s].i_prb = (int)i_prb; e->embb[s].n_prbs = (int)a; }
-        else e->mmtc[s - c->n_embb].n_prbs = (int)a;
+        if (s < e->n_l1_embb) { e->embb[s].i_prb = (int)i_prb; e->embb[s].n_prbs = (int)a; }
+        else e->mmtc[s - e->n_l1_embb].n_prbs = (int)a;
         i_prb += a;
     }
     for (int t = 0; t < c->slots_per_step; ++t) {                           /* node_b.py:77-78, 35-38 */
-        for (int s = 0; s < c->n_embb; ++s) embb_slot(e, s);
+        for (int s = 0; s < e->n_l1_embb; ++s) embb_slot(e, s);
         for (int s = 0; s < c->n_mmtc; ++s) mmtc_slot(&e->mmtc[s]);
     }
     int64_t tv = 0; int v = 0;
     const double obs_time = c->slots_per_step * 1e-3;                       /* slice_ran.py:165 */
-    for (int s = 0; s < c->n_embb; ++s) {                                   /* slice_ran.py:307-325 */
-        embb_t *sl = &e->embb[s];
-        double a[10] = {(double)sl->a_traffic[0], (double)sl->a_th[0], (double)sl->a_prb[0], sl->a_queue[0], sl->a_snr[0],
-                        (double)sl->a_traffic[1], (double)sl->a_th[1], (double)sl->a_prb[1], sl->a_queue[1], sl->a_snr[1]};
-        for (int j = 0; j < 10; ++j) { obs[v++] = (float)(a[j] / e->norm_embb[j]); if (acc) acc[s * 10 + j] = a[j]; }
-        int cbr_ok = a[1] / obs_time > 10e6 || a[2] / c->slots_per_step > 20 || a[3] / c->slots_per_step < 10e4;
-        int vbr_ok = a[6] / obs_time > 15e6 || a[7] / c->slots_per_step > 30 || a[8] / c->slots_per_step < 15e4;
-        int viol = !(cbr_ok && vbr_ok);
-        violations[s] = viol; labels[s] = viol ? -1 : 1; tv += viol;       /* slice_l1.py:160-171 */
+    int row = 0;
+    for (int s = 0; s < e->n_l1_embb; ++s) {                                /* slice_ran.py:307-325 per RAN slice, slice_l1.py:160-181 per L1 */
+        embb_t *l1 = &e->embb[s];
+        int l1_viol = 0;
+        for (int r = 0; r < l1->n_ran; ++r, ++row) {
+            ran_t *sl = &l1->ran[r];
+            double a[10] = {(double)sl->a_traffic[0], (double)sl->a_th[0], (double)sl->a_prb[0], sl->a_queue[0], sl->a_snr[0],
+                            (double)sl->a_traffic[1], (double)sl->a_th[1], (double)sl->a_prb[1], sl->a_queue[1], sl->a_snr[1]};
+            for (int j = 0; j < 10; ++j) { obs[v++] = (float)(a[j] / e->norm_embb[j]); e->acc_ran[row][j] = a[j]; if (acc && r == 0) acc[s * 10 + j] = a[j]; }
+            int cbr_ok = a[1] / obs_time > 10e6 || a[2] / c->slots_per_step > 20 || a[3] / c->slots_per_step < 10e4;
+            int vbr_ok = a[6] / obs_time > 15e6 || a[7] / c->slots_per_step > 30 || a[8] / c->slots_per_step < 15e4;
+            l1_viol += !(cbr_ok && vbr_ok);
+        }
+        violations[s] = l1_viol; labels[s] = l1_viol ? -1 : 1; tv += l1_viol;   /* slice_l1.py:160-171: sum of the RAN slices' violations */
     }
     for (int s = 0; s < c->n_mmtc; ++s) {                                   /* slice_ran.py:133-148 */
-        mmtc_t *m = &e->mmtc[s]; int gs = c->n_embb + s;
+        mmtc_t *m = &e->mmtc[s]; int gs = e->n_l1_embb + s;
         double a[3] = {(double)m->a_dev, m->a_rep, m->a_delay};
+        for (int j = 0; j < 10; ++j) e->acc_ran[row][j] = j < 3 ? a[j] : 0.0;
+        ++row;
         for (int j = 0; j < 3; ++j) { obs[v++] = (float)(a[j] / e->norm_mmtc[j]); if (acc) acc[gs * 10 + j] = a[j]; }
         if (acc) for (int j = 3; j < 10; ++j) acc[gs * 10 + j] = 0;
         int viol = !(m->a_delay / c->slots_per_step < 300);

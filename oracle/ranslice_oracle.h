@@ -36,6 +36,8 @@ typedef struct orc_config {
     int32_t n_prbs, n_embb, n_mmtc, slots_per_step;
     double penalty;
     double prop_A, prop_B;          /* channel_models.py:117-124 */
+    int32_t l1_mux;                 /* 1: create_env(L1_level=False), the eMBB RAN slices share ONE L1 scheduler (scenario_creator.py:168-177) */
+    int32_t reserved;
 } orc_config;
 
 typedef struct orc_tables {
@@ -63,6 +65,8 @@ void orc_mcs_lut(const orc_tables *tbl, int e_snr, int *mcs, double *bps, int *r
 double orc_response(const orc_tables *tbl, int mcs, const double *snr, int n);
 double orc_macro_cell(double x, double y, double logf, double A, double B);
 void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* raw accumulators of every RAN slice after the last step, L1-major, [n_embb + n_mmtc][10] (info['l1_info'][l1][ran]) */
+void orc_get_acc_ran(const orc_env *e, double *acc);
 /* debugging: number of live UEs of eMBB slice s */
 int orc_n_ues(const orc_env *e, int s);
 

@@ -16,7 +16,7 @@ SCENARIOS = [(200, 5, 0), (150, 3, 2), (100, 1, 4), (70, 1, 1)]   # n_prbs, n_em
 class OrcConfig(C.Structure):
     _fields_ = [("n_prbs", C.c_int32), ("n_embb", C.c_int32), ("n_mmtc", C.c_int32),
                 ("slots_per_step", C.c_int32), ("penalty", C.c_double), ("prop_A", C.c_double),
-                ("prop_B", C.c_double)]
+                ("prop_B", C.c_double), ("l1_mux", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OrcTables(C.Structure):
@@ -65,6 +65,7 @@ def lib():
         L.orc_macro_cell.restype = C.c_double
         L.orc_macro_cell.argtypes = [C.c_double] * 5
         L.orc_n_ues.argtypes = [C.c_void_p, C.c_int]
+        L.orc_get_acc_ran.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -118,12 +119,13 @@ class OracleEnv:
     """One oracle environment (scenario index like scenario_creator.create_env)."""
 
     def __init__(self, tables, scenario, seed, slots_per_step=50, penalty=100.0,
-                 propagation="macro_cell_urban_2GHz", numpy_rng=None):
+                 propagation="macro_cell_urban_2GHz", numpy_rng=None, l1_mux=False):
         n_prbs, n_embb, n_mmtc = SCENARIOS[scenario]
         A, B = PROPAGATION[propagation]
-        self.cfg = OrcConfig(n_prbs, n_embb, n_mmtc, slots_per_step, penalty, A, B)
+        self.cfg = OrcConfig(n_prbs, n_embb, n_mmtc, slots_per_step, penalty, A, B, int(bool(l1_mux)), 0)
         self.tbl = c_tables(tables)
-        self.S = n_embb + n_mmtc
+        self.S = (int(n_embb > 0) if l1_mux else n_embb) + n_mmtc      # L1 slices = action entries (create_env(L1_level=False))
+        self.n_ran = n_embb + n_mmtc
         self.V = 10 * n_embb + 3 * n_mmtc
         self.n_prbs = n_prbs
         self.h = lib().orc_create(C.byref(self.cfg), C.byref(self.tbl), C.c_uint64(seed))
@@ -151,6 +153,12 @@ class OracleEnv:
         acc = np.zeros((self.S, 10), np.float64)
         flags = lib().orc_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(lab), _ptr(vio), _ptr(acc))
         return obs, float(rew[0]), lab, vio, acc, flags
+
+    def acc_ran(self):
+        """Raw accumulators of every RAN slice after the last step, L1-major [n_embb + n_mmtc, 10]."""
+        a = np.zeros((self.n_ran, 10), np.float64)
+        lib().orc_get_acc_ran(self.h, _ptr(a))
+        return a
 
 
 class OracleBatch:

@@ -170,7 +170,12 @@ def make_env_philox(seed, scenario, **kw):
             st["l1rx"] = px.PhiloxStream(seed, i, px.STREAM_L1RX)
             st["vbr"] = px.PhiloxStream(seed, i, px.STREAM_VBR)
             l1.rng = st["l1rx"]
-            l1.slices_ran[0].rng = st["ran"]
+            if len(l1.slices_ran) == 1:
+                l1.slices_ran[0].rng = st["ran"]
+            else:   # L1_level=False: several RAN slices multiplexed in one L1; RAN stream of RAN slice r = (slice r, RAN)
+                st["ran_mux"] = [px.PhiloxStream(seed, r, px.STREAM_RAN) for r in range(len(l1.slices_ran))]
+                for r, sr in enumerate(l1.slices_ran):
+                    sr.rng = st["ran_mux"][r]
             shared_gen = l1.snr_generator if shared_gen is None else shared_gen
             gen = copy.copy(shared_gen)          # shares .samples, private users/rng
             gen.users = {}
@@ -225,4 +230,12 @@ def run_trace(env, actions):
             names = EMBB_VARS if "cbr_th" in d else MMTC_VARS
             for j, nme in enumerate(names):
                 out["acc"][t, s, j] = d[nme]
+        if any(len(l1) > 1 for l1 in info["l1_info"]):        # multiplexed L1: accumulators of every RAN slice, L1-major
+            rows = []
+            for l1 in info["l1_info"]:
+                for r in sorted(l1):
+                    d = l1[r]
+                    names = EMBB_VARS if "cbr_th" in d else MMTC_VARS
+                    rows.append([d[n] for n in names] + [0.0] * (10 - len(names)))
+            out.setdefault("acc_ran", np.zeros((T, len(rows), 10), np.float64))[t] = np.asarray(rows, np.float64)
     return out

@@ -6,6 +6,7 @@ Runs only in the build container (needs /root/reference).  Usage:
 Fixtures (all compressed .npz, numpy version recorded inside):
   A_scn{0,1,3}  native numpy seeding (default_rng(0) + np.random.seed(0)), single env
   B_scn{0,1,3}  Philox-stream injection (tests/refharness.make_env_philox), several envs
+  B_mux{0,3}    the same with create_env(L1_level=False): eMBB RAN slices multiplexed in one L1 scheduler
   known_answers leaf-function tables (MCS LUT, response(), macro_cell, constants)
 """
 import os
@@ -23,6 +24,8 @@ SCN = {0: (5, 200), 1: (5, 150), 2: (5, 100), 3: (2, 70)}   # index -> (S, n_prb
 
 A_CASES = {"A_scn0": (0, 0, 2000), "A_scn1": (1, 0, 400), "A_scn3": (3, 0, 2000)}
 B_CASES = {"B_scn0": (0, 7000, 8, 300), "B_scn1": (1, 7100, 4, 200), "B_scn3": (3, 7200, 8, 300)}
+# create_env(L1_level=False): the eMBB RAN slices multiplexed in one L1 (scenario_creator.py:168-177); name -> (scn, seed, envs, steps)
+M_CASES = {"B_mux0": (0, 7300, 4, 200), "B_mux3": (3, 7400, 2, 120)}
 
 
 def gen_A(name):
@@ -46,6 +49,31 @@ def _gen_B_env(args):
     tr = rh.run_trace(env, act)
     tr["actions"] = act
     return tr
+
+
+def _gen_M_env(args):
+    import refharness as rh
+    scn, seed, steps = args
+    n_embb = SCN[scn][0] - (1 if scn == 3 else 0)
+    S = 1 + (1 if scn == 3 else 0)                           # L1 slices: one multiplexed eMBB L1 (+ the mMTC L1)
+    env, _ = rh.make_env_philox(seed, scn, L1_level=False)
+    assert env.n_slices == S
+    act = rh.simplex_actions(seed, S, SCN[scn][1], steps)
+    act[::9] = act[::9] // 8                                 # starved periods: deep backlogs, contended PF over all RAN slices
+    tr = rh.run_trace(env, act)
+    tr["actions"] = act
+    if "acc_ran" not in tr:                                  # single RAN slice per L1 (scenario_3): same rows as acc
+        tr["acc_ran"] = tr["acc"].copy()
+    return tr
+
+
+def gen_M(name, pool):
+    scn, base, n_envs, steps = M_CASES[name]
+    trs = list(pool.map(_gen_M_env, [(scn, base + e, steps) for e in range(n_envs)]))
+    stacked = {k: np.stack([t[k] for t in trs]) for k in trs[0]}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), scenario=scn, base_seed=base, l1_level=False,
+                        numpy_version=np.__version__, **stacked)
+    return name, int(stacked["violations"].sum()), float(stacked["reward"].mean())
 
 
 def gen_B(name, pool):
@@ -104,7 +132,7 @@ def gen_known():
 
 
 def main():
-    names = sys.argv[1:] or (["known_answers"] + list(A_CASES) + list(B_CASES))
+    names = sys.argv[1:] or (["known_answers"] + list(A_CASES) + list(B_CASES) + list(M_CASES))
     os.makedirs(OUT, exist_ok=True)
     with ProcessPoolExecutor(8) as pool:
         futs = []
@@ -116,6 +144,8 @@ def main():
         for n in names:
             if n in B_CASES:
                 print(gen_B(n, pool), flush=True)
+            elif n in M_CASES:
+                print(gen_M(n, pool), flush=True)
         for f in futs:
             print(f.result(), flush=True)
 
