@@ -49,7 +49,11 @@ typedef struct rs_config {
     int32_t max_bursts;     /* active-burst cap per VBR UE (<= 16); 0 -> default 8 */
     int32_t mtc_queue_cap;  /* mMTC backlog cap per slice; 0 -> default 128 */
     int32_t kernel_variant; /* 0 = default (fastest validated); see DESIGN.md */
-    int32_t reserved;
+    int32_t l1_mux;        /* 0: every slice has its own L1 (create_env(L1_level=True), the default);
+                            * 1: L1_level=False (scenario_creator.py:168-177): the n_embb eMBB RAN slices share ONE L1 scheduler and ONE
+                            *    action entry; action / labels / violations are then [N][(n_embb > 0) + n_mmtc], violations count the
+                            *    RAN slices in breach (0..n_embb), obs keeps its 10 n_embb + 3 n_mmtc columns.  Correctness-first
+                            *    kernel (all fp64, one thread per env, at most 32 UEs per env). */
     double penalty;         /* ran_slice.py:19 */
     double prop_A, prop_B;  /* channel_models.py:117-124 */
     uint64_t base_seed;     /* Philox key of env e is base_seed + first_env_id + e */
@@ -94,7 +98,8 @@ int rs_wait(rs_handle *h, int32_t ticket);
 int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d_reward,
                    int32_t *d_labels, int32_t *d_violations, uint32_t *d_flags, void *stream);
 
-/* info['l1_info'] of one env (node_b.py:46-49): raw accumulators of the last step, [S][10]
+/* (with l1_mux the accumulator rows are the RAN slices, L1-major: [n_embb + n_mmtc][10], and n_prbs has one entry per L1)
+ * info['l1_info'] of one env (node_b.py:46-49): raw accumulators of the last step, [S][10]
  * (eMBB order scenario_creator.py:80-82; mMTC: devices, avg_rep, delay, then zeros) and the
  * PRBs in force per slice [S]. */
 int rs_get_info(rs_handle *h, int32_t env, double *acc, int32_t *n_prbs);

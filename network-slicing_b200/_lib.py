@@ -16,7 +16,7 @@ class RsConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_envs", C.c_int32),
                 ("n_prbs", C.c_int32), ("n_embb", C.c_int32), ("n_mmtc", C.c_int32),
                 ("slots_per_step", C.c_int32), ("max_ues", C.c_int32), ("max_bursts", C.c_int32),
-                ("mtc_queue_cap", C.c_int32), ("kernel_variant", C.c_int32), ("reserved", C.c_int32),
+                ("mtc_queue_cap", C.c_int32), ("kernel_variant", C.c_int32), ("l1_mux", C.c_int32),
                 ("penalty", C.c_double), ("prop_A", C.c_double), ("prop_B", C.c_double),
                 ("base_seed", C.c_uint64), ("first_env_id", C.c_uint64)]
 

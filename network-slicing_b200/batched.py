@@ -23,10 +23,15 @@ def _p(a):
 class BatchedRanSlice:
     def __init__(self, scenario=0, n_envs=1, base_seed=0, slots_per_step=50,
                  propagation_type='macro_cell_urban_2GHz', penalty=100, device=0, first_env_id=0,
-                 max_ues=0, max_bursts=0, mtc_queue_cap=0, kernel_variant=0, tables=None):
+                 max_ues=0, max_bursts=0, mtc_queue_cap=0, kernel_variant=0, tables=None, l1_level=True):
         sc = scenarios[scenario] if isinstance(scenario, int) else scenario
         self.n_prbs, self.n_embb, self.n_mmtc = sc['n_prbs'], sc['n_embb'], sc['n_mmtc']
-        self.n_slices = self.n_embb + self.n_mmtc
+        # create_env(L1_level=False) (scenario_creator.py:168-177): the eMBB RAN slices are multiplexed in ONE L1 slice, which
+        # takes one action entry and reports one label; the observation keeps the 10 variables of every RAN slice
+        self.l1_level = bool(l1_level)
+        self.n_l1_embb = self.n_embb if self.l1_level else int(self.n_embb > 0)
+        self.n_slices = self.n_l1_embb + self.n_mmtc
+        self.n_ran = self.n_embb + self.n_mmtc
         self.n_variables = 10 * self.n_embb + 3 * self.n_mmtc
         self.n_envs, self.device, self.penalty = n_envs, device, penalty
         self.slots_per_step = slots_per_step
@@ -35,7 +40,7 @@ class BatchedRanSlice:
         t = tables or load_tables()
         self._tables = t
         self._cfg = _lib.RsConfig(_lib.RS_ABI_VERSION, device, n_envs, self.n_prbs, self.n_embb, self.n_mmtc,
-                                  slots_per_step, max_ues, max_bursts, mtc_queue_cap, kernel_variant, 0,
+                                  slots_per_step, max_ues, max_bursts, mtc_queue_cap, kernel_variant, int(not self.l1_level),
                                   float(penalty), A, B, base_seed & (2 ** 64 - 1), first_env_id)
         tb = _lib.RsTables(_p(t.trace), _p(t.mcs_rate), _p(t.mcs_snr), _p(t.mcs_order), _p(t.mcs_mod))
         h = C.c_void_p()
@@ -152,15 +157,15 @@ class BatchedRanSlice:
 
     # ---------------------------------------------------------------- introspection
     def get_info(self, env=0):
-        acc = np.zeros((self.n_slices, 10), np.float64)
+        acc = np.zeros((self.n_ran, 10), np.float64)          # one row per RAN slice (L1-major), == per L1 unless multiplexed
         prbs = np.zeros(self.n_slices, np.int32)
         _lib.check(_lib.lib().rs_get_info(self._h, env, _p(acc), _p(prbs)))
         return acc, prbs
 
     def n_ues(self):
-        out = np.zeros((self.n_envs, max(self.n_embb, 1)), np.int32)
+        out = np.zeros((self.n_envs, max(self.n_l1_embb, 1)), np.int32)
         _lib.check(_lib.lib().rs_get_n_ues(self._h, _p(out)))
-        return out[:, :self.n_embb]
+        return out[:, :self.n_l1_embb]
 
     def counters(self):
         k, t = C.c_uint64(), C.c_uint64()

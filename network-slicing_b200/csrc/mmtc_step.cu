@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(128) mmtc_reset_kernel(const __grid_constant__
     if (u >= st.U) return;
     const int env = u / p.n_mmtc, m = u - env * p.n_mmtc;
     const uint64_t seed = p.seed0 + (uint64_t)env;
-    PhiloxStream r{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(p.n_embb + m), STREAM_MTC, st.ctr[u]};
+    PhiloxStream r{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(p.n_l1e + m), STREAM_MTC, st.ctr[u]};   // stream of L1 slice n_l1e + m
     for (int i = 0; i < N_MTC_DEV; ++i) {
         const uint32_t rep_ix = r.integers(7);
         const uint32_t per_ix = r.integers(8);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) mmtc_step_kernel(const __grid_constant__ 
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int U = st.U;
     if (u >= U) return;
-    const int env = u / p.n_mmtc, m = u - env * p.n_mmtc, s = p.n_embb + m;
+    const int env = u / p.n_mmtc, m = u - env * p.n_mmtc, s = p.n_l1e + m;   // s: L1 / action index of this slice
     uint32_t flags = 0;
     // PRBs of this slice after clamping (mMTC ignores i_prb, slice_l1.py:50-51)
     int n_prbs;

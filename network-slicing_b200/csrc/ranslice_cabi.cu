@@ -20,6 +20,8 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
+void launch_embb_mux(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+void launch_embb_mux_reset(const EmbbState &st, cudaStream_t stream);
 void launch_reward(const StepParams &p, cudaStream_t stream);
 }  // namespace rs
 
@@ -88,7 +90,8 @@ void carve(rs_handle *h, Carver &c) {
     const size_t U = (size_t)e.U, K = (size_t)e.K;
     e.hdr = c.take<rs::UnitHdr>(U);
     e.ue = c.take<rs::UeRec>(U * K);
-    e.acc = c.take<double>(U * 10);
+    e.acc = c.take<double>(U * (size_t)e.R * 10);
+    e.mux = e.R > 1 || h->cfg.l1_mux ? c.take<rs::MuxRan>(U * (size_t)e.R) : nullptr;
     e.cur_prbs = c.take<int32_t>(U);
     rs::MmtcState &m = h->mmtc;
     const size_t UM = (size_t)m.U, Q = (size_t)m.Q, D = (size_t)rs::N_MTC_DEV;
@@ -143,7 +146,8 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     if (cfg->n_prbs <= 0 || cfg->n_prbs > 2 * rs::TRACE_ROWS)
         return fail(RS_E_ARG, "n_prbs must be in [1, 200] (the trace rows wrap once, channel_models.py:144-148)");
     if (cfg->slots_per_step <= 0 || cfg->slots_per_step > 255) return fail(RS_E_ARG, "slots_per_step must be in [1,255]");
-    const int K = cfg->max_ues ? cfg->max_ues : 16, MB = cfg->max_bursts ? cfg->max_bursts : 8;
+    const bool mux = cfg->l1_mux != 0;
+    const int K = mux ? 32 : (cfg->max_ues ? cfg->max_ues : 16), MB = cfg->max_bursts ? cfg->max_bursts : 8;   // a multiplexed L1 holds the UEs of all its RAN slices
     const int Q = cfg->mtc_queue_cap ? cfg->mtc_queue_cap : 128;
     if (K < 2 || K > 32 || MB < 1 || MB > 16 || Q < 1) return fail(RS_E_ARG, "caps out of range");
     if (!tables->trace || !tables->mcs_rate || !tables->mcs_snr || !tables->mcs_order || !tables->mcs_mod)
@@ -162,7 +166,9 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     h->sm_count = prop.multiProcessorCount;
 
     rs::StepParams &p = h->p;
-    p.N = cfg->n_envs; p.n_embb = cfg->n_embb; p.n_mmtc = cfg->n_mmtc; p.S = cfg->n_embb + cfg->n_mmtc;
+    p.N = cfg->n_envs; p.n_embb = cfg->n_embb; p.n_mmtc = cfg->n_mmtc;
+    p.n_l1e = mux ? (cfg->n_embb > 0 ? 1 : 0) : cfg->n_embb;
+    p.S = p.n_l1e + cfg->n_mmtc;
     p.n_prbs = cfg->n_prbs; p.slots = cfg->slots_per_step; p.V = 10 * cfg->n_embb + 3 * cfg->n_mmtc;
     p.penalty = cfg->penalty; p.prop_A = cfg->prop_A; p.prop_B = cfg->prop_B;
     p.seed0 = cfg->base_seed + cfg->first_env_id;
@@ -175,7 +181,8 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
         for (int i = 0; i < 3; ++i) p.norm_mmtc[i] = 100.0 * sps;
         p.obs_time = cfg->slots_per_step * 1e-3;
     }
-    h->embb.U = cfg->n_envs * cfg->n_embb; h->embb.K = K; h->embb.MB = MB;
+    h->embb.U = cfg->n_envs * p.n_l1e; h->embb.K = K; h->embb.MB = MB;
+    h->embb.R = mux ? cfg->n_embb : 1;
     h->mmtc.U = cfg->n_envs * cfg->n_mmtc; h->mmtc.Q = Q;
 
     Carver sizing;
@@ -209,7 +216,7 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
         // entries) stays within 2.5x the lanes the GPU keeps resident (4 blocks of 128 threads per SM).  Measured on B200:
         // 4096 envs 3.20 -> 2.78 ms/step at dil 2, 16384 envs 3.69 -> 3.43 at dil 1 (and 4.15 at dil 2), no gain beyond.
         int dil = 0;
-        if (h->cfg.kernel_variant == 0 && h->embb.K <= 16 && U > 0) {
+        if (h->cfg.kernel_variant == 0 && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {
             const double lanes = 2.5 * 4.0 * 128.0 * (double)h->sm_count;
             while (dil < 2 && 1.1 * (double)U * (double)(2 << dil) <= lanes) ++dil;
             if (const char *e = std::getenv("RS_DILUTION")) dil = std::max(0, std::min(2, std::atoi(e)));
@@ -299,6 +306,7 @@ int rs_reset(rs_handle *h, float *obs) {
     // NodeB.reset (node_b.py:17-22): UEs, timers and accumulators cleared; RNG counters keep running
     // (the reference never reseeds on reset).  eMBB: zero everything but the counters.
     if (h->embb.U) { rs::launch_embb_reset(h->embb, h->stream); h->launches += 1; }
+    if (h->embb.U && h->cfg.l1_mux) { rs::launch_embb_mux_reset(h->embb, h->stream); h->launches += 1; }
     if (h->mmtc.U) {
         rs::launch_mmtc_reset(h->p, h->mmtc, h->stream);
         h->launches += 1;
@@ -340,7 +348,8 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
         CU(cudaEventRecord(h->ev_join, h->side_stream));
     }
     if (h->embb.U) {
-        if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
+        if (h->cfg.l1_mux) { rs::launch_embb_mux(p, h->embb, h->tb, st); h->launches += 1; }
+        else if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->cfg.kernel_variant == 2 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
         else h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st);
     }
@@ -410,17 +419,17 @@ int rs_get_info(rs_handle *h, int32_t env, double *acc, int32_t *n_prbs) {
     if (!h || env < 0 || env >= h->p.N) return fail(RS_E_ARG, "bad handle/env");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    const int ne = h->p.n_embb, nm = h->p.n_mmtc;
+    const int ne = h->p.n_embb, nm = h->p.n_mmtc, nl = h->p.n_l1e;   // accumulator rows = RAN slices (ne + nm), PRB entries = L1 slices (nl + nm)
     if (acc) {
-        std::memset(acc, 0, sizeof(double) * 10 * (size_t)h->p.S);
+        std::memset(acc, 0, sizeof(double) * 10 * (size_t)(ne + nm));
         if (ne) CU(cudaMemcpy(acc, h->embb.acc + (size_t)env * ne * 10, sizeof(double) * 10 * ne, cudaMemcpyDeviceToHost));
         for (int m = 0; m < nm; ++m)
             CU(cudaMemcpy(acc + (size_t)(ne + m) * 10, h->mmtc.acc + ((size_t)env * nm + m) * 3, sizeof(double) * 3,
                           cudaMemcpyDeviceToHost));
     }
     if (n_prbs) {
-        if (ne) CU(cudaMemcpy(n_prbs, h->embb.cur_prbs + (size_t)env * ne, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost));
-        if (nm) CU(cudaMemcpy(n_prbs + ne, h->mmtc.cur_prbs + (size_t)env * nm, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost));
+        if (nl) CU(cudaMemcpy(n_prbs, h->embb.cur_prbs + (size_t)env * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost));
+        if (nm) CU(cudaMemcpy(n_prbs + nl, h->mmtc.cur_prbs + (size_t)env * nm, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost));
     }
     return RS_OK;
 }

@@ -55,8 +55,16 @@ struct __align__(16) UnitHdr {
 };
 static_assert(sizeof(UnitHdr) == 32, "UnitHdr must be 32 bytes");
 
+// RAN slice of a multiplexed L1 (create_env(L1_level=False), scenario_creator.py:168-177): arrival countdowns and the RAN
+// Philox counter of SliceRANeMBB r inside the L1 unit; the UE's RAN slice id rides in bits 28-30 of UeRec::meta.
+struct __align__(16) MuxRan { int32_t cbr_next, vbr_next; uint32_t c_ran, pad; };
+constexpr int MUX_RAN_SHIFT = 28;
+constexpr uint32_t MUX_INDEX_MASK = 0x3FFFu;               // trace index field of meta (bits 4-17) when the RAN id is present
+
 struct EmbbState {
     int U, K, MB;          // units, UE records per unit, burst slots per UE (== MAX_BURSTS)
+    int R;                 // RAN slices per unit: 1, or n_embb when the L1 multiplexes them (then U = envs, acc is [U][R][10])
+    MuxRan *mux;           // [U][R] (multiplexed mode only)
     int wide;              // 1: launch the latency variant of the shared-memory kernel (small batches)
     int dil, perm_len;     // lane dilution (log2) of the shared-memory kernel's front list and the length of perm[]: when a batch
                            // cannot fill the GPU, every 2^dil-th lane carries a unit and the rest idle -- fewer divergent units
@@ -106,7 +114,8 @@ struct Tables {
 };
 
 struct StepParams {
-    int N, S, n_embb, n_mmtc, n_prbs, slots, V;
+    int N, S, n_embb, n_mmtc, n_prbs, slots, V;   // S = action entries = L1 slices; n_embb / n_mmtc = RAN slices (V = 10 n_embb + 3 n_mmtc)
+    int n_l1e;                     // eMBB L1 slices: n_embb, or 1 when they are multiplexed (L1_level=False)
     double penalty, prop_A, prop_B;
     double norm_embb[10], norm_mmtc[3];
     double obs_time;               // slots_per_step * slot_length (slice_ran.py:165)

@@ -51,10 +51,17 @@ class RanSlice(_Base):
             raise ValueError('The action must contain as many elements as slices!')     # node_b.py:66-68
         obs, reward, _, binfo = self.batched.step(action.reshape(1, -1))
         acc, prbs = self.batched.get_info(0)
+        b = self.batched
         l1_info = []
-        for s in range(self.n_slices):                                                  # node_b.py:46-49
-            names = state_variables_embb if s < self.batched.n_embb else state_variables_mmtc
-            l1_info.append({0: {n: acc[s, j] for j, n in enumerate(names)}})
+        if getattr(b, 'l1_level', True):
+            for s in range(self.n_slices):                                              # node_b.py:46-49
+                names = state_variables_embb if s < b.n_embb else state_variables_mmtc
+                l1_info.append({0: {n: acc[s, j] for j, n in enumerate(names)}})
+        else:                                                                           # slice_l1.py:178-181: {i: slice_ran.info}
+            if b.n_embb:
+                l1_info.append({r: {n: acc[r, j] for j, n in enumerate(state_variables_embb)} for r in range(b.n_embb)})
+            for m in range(b.n_mmtc):
+                l1_info.append({0: {n: acc[b.n_embb + m, j] for j, n in enumerate(state_variables_mmtc)}})
         info = {'l1_info': l1_info, 'SLA_labels': binfo['SLA_labels'][0].astype(np.int64),
                 'violations': binfo['violations'][0].astype(np.int64), 'n_prbs': [int(x) for x in prbs],
                 'total_violations': int(binfo['total_violations'][0]), 'flags': int(binfo['flags'][0])}

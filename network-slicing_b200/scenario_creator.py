@@ -39,11 +39,10 @@ def seed_from_rng(rng):
 def create_batched_env(rng, n, n_envs, slots_per_step=50, propagation_type='macro_cell_urban_2GHz',
                        L1_level=True, penalty=100, device=0, first_env_id=0, **kw):
     from .batched import BatchedRanSlice
-    if not L1_level:
-        raise NotImplementedError("L1_level=False (multiplexed mode, scenario_creator.py:168-177) is out of scope (SURVEY 8f)")
+    # L1_level=False: the eMBB RAN slices share one L1 scheduler (scenario_creator.py:168-177); correctness-first kernel
     return BatchedRanSlice(scenario=n, n_envs=n_envs, base_seed=seed_from_rng(rng), slots_per_step=slots_per_step,
                            propagation_type=propagation_type, penalty=penalty, device=device,
-                           first_env_id=first_env_id, **kw)
+                           first_env_id=first_env_id, l1_level=bool(L1_level), **kw)
 
 
 def create_env(rng, n, slots_per_step=50, propagation_type='macro_cell_urban_2GHz', L1_level=True, penalty=100,

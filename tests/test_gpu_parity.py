@@ -260,3 +260,59 @@ def test_pipelined_host_api_matches_blocking_step():
         for x, y in zip(want[t], got[t]):
             assert np.array_equal(x, y), t
     a_env.close(); b_env.close()
+
+
+# ------------------------------------------------------------------------------------------------ L1_level=False
+@pytest.mark.parametrize("name,scn", [("B_mux0", 0), ("B_mux3", 3)])
+def test_multiplexed_l1_reference_fixture(golden, name, scn):
+    """create_env(L1_level=False): CUDA (through the C ABI) vs the unmodified reference with injected Philox streams --
+    obs, reward, per-L1 labels and violation counts, raw accumulators of every RAN slice, bit-exact."""
+    g = golden(name)
+    E, T, S = g["actions"].shape
+    env = make_env(scn, E, int(g["base_seed"]), L1_level=False)
+    assert env.n_slices == S
+    assert np.array_equal(env.reset(), g["obs0"])
+    for t in range(T):
+        obs, rew, _, info = env.step(g["actions"][:, t])
+        assert not info["flags"].any()
+        assert np.array_equal(obs, g["obs"][:, t]), "obs diverged at step %d" % t
+        assert np.array_equal(rew.astype(np.float64), g["reward"][:, t])
+        assert np.array_equal(info["SLA_labels"], g["labels"][:, t])
+        assert np.array_equal(info["violations"], g["violations"][:, t])
+        if t % 20 == 0 or t == T - 1:
+            acc, prbs = env.get_info(E - 1)
+            assert np.array_equal(acc, g["acc_ran"][E - 1, t])
+    env.close()
+
+
+def test_multiplexed_l1_vs_oracle_and_facade(tables):
+    """More envs on fresh seeds against the oracle (l1_mux), out-of-contract actions included; envs that hit the 32-UE cap
+    of the multiplexed unit are flagged and excluded; the single-env facade reports info['l1_info'] per RAN slice."""
+    scn, N, T, seed = 0, 96, 60, 515
+    env = make_env(scn, N, seed, L1_level=False)
+    orcs = [ol.OracleEnv(tables, scn, seed + e, l1_mux=True) for e in range(N)]
+    env.reset()
+    for o in orcs:
+        o.reset()
+    rng = np.random.default_rng(2)
+    ok = np.ones(N, bool)
+    for t in range(T):
+        a = rng.integers(0, 201, (N, 1)).astype(np.int32)
+        if t % 9 == 4:
+            a[::7] = 230                                    # > n_prbs: clamped and flagged on both sides
+        obs, rew, _, info = env.step(a)
+        ok &= (info["flags"] & 1) == 0                      # UE cap (32 here, 64 in the oracle)
+        for e in range(N):
+            oo, orr, olab, ovio, _, oflags = orcs[e].step(a[e])
+            if ok[e]:
+                assert np.array_equal(obs[e], oo) and float(rew[e]) == orr, (t, e)
+                assert np.array_equal(info["SLA_labels"][e], olab) and np.array_equal(info["violations"][e], ovio), (t, e)
+                assert (int(info["flags"][e]) & 4) == (oflags & 4)
+    assert ok.mean() > 0.9 and env.n_ues().max() > 12
+    env.close()
+    from ranslice_b200 import create_env
+    one = create_env(3, 0, L1_level=False)
+    one.reset()
+    o, r, d, info = one.step(np.array([150]))
+    assert o.shape == (50,) and len(info["l1_info"]) == 1 and sorted(info["l1_info"][0]) == [0, 1, 2, 3, 4]
+    assert len(info["SLA_labels"]) == 1 and info["n_prbs"] == [150]
