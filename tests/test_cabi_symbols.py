@@ -48,3 +48,25 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("expected NativeLibraryMissing")
+
+
+def test_controller_and_wrapper_entry_points_validate_arguments_without_gpu():
+    """kb_* / rs_wrap_* / rs_step_async reject bad arguments before any CUDA call (error behaviour of the boundary)."""
+    from ranslice_b200 import _lib
+    L = _lib.lib()
+    vp = ctypes.c_void_p
+    assert L.kb_create(None, None, None, None) == -1
+    assert L.kb_control_init(None, None, None, ctypes.c_double(0.05), ctypes.c_double(0.97), ctypes.c_double(0.99)) == -1
+    assert L.kb_control_update_device(None, None, None, None, None, None) == -1
+    assert L.kb_control_select_device(None, None, None, None, None) == -1
+    assert L.kb_set_exact(None, 1) == -1
+    assert L.rs_wrap_action_device(None, 0, 4, 5, 200, None, None) == -1
+    buf = (ctypes.c_int32 * 64)()
+    p = ctypes.cast(buf, vp)
+    assert L.rs_wrap_action_device(p, 0, 4, 9, 200, p, None) == -1            # more than 8 slices
+    assert b"n_slices" in L.rs_last_error()
+    assert L.rs_wrap_obs_device(p, p, ctypes.c_int64(0), None) == -1
+    assert L.rs_wrap_record_device(p, p, p, 4, 5, ctypes.c_int64(-1), None, None, None, None) == -1
+    t = ctypes.c_int32()
+    assert L.rs_step_async(None, None, None, None, None, None, None, ctypes.byref(t)) == -1
+    assert L.rs_wait(None, 0) == -1
