@@ -67,10 +67,11 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.path = tempfile.mktemp(suffix=".csv")
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            self._out = os.fdopen(fd, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                                         stdout=self._out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -80,8 +81,9 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.proc.wait()
+        self._out.close()
         sm, mx, reasons = [], [], set()
-        for line in open(self.path):
+        for line in open(self.path).read().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue

@@ -17,7 +17,6 @@ files unchanged, or a single batched file with a leading env axis.
 """
 import ctypes as C
 import os
-import time
 from itertools import product
 
 import numpy as np
