@@ -56,8 +56,9 @@ typedef struct rs_config {
                             *    kernel (all fp64, one thread per env, at most 32 UEs per env). */
     double penalty;         /* ran_slice.py:19 */
     double prop_A, prop_B;  /* channel_models.py:117-124 */
-    uint64_t base_seed;     /* Philox key of env e is base_seed + first_env_id + e */
-    uint64_t first_env_id;  /* global id of local env 0 (multi-GPU sharding, results invariant to the split) */
+    uint64_t base_seed;     /* Philox KEY of every env of the batch; the global env id first_env_id + e is counter word 3, so
+                             * batches with adjacent seeds (the reference's default_rng(seed=i) replications) share no streams */
+    uint64_t first_env_id;  /* global id of local env 0 (multi-GPU sharding, results invariant to the split); ids < 2^32 */
 } rs_config;
 
 /* Host pointers; copied to the device by rs_create. */

@@ -104,10 +104,10 @@ __device__ __forceinline__ void smem_move_slot(const SmemView &v, ColdRec *cold,
 
 // Rare RAN events of a slot on the shared-memory table; same order as ran_events in embb_fast.cu
 // (slice_ran.py:263-268, slice_l1.py:196-198).  Sets c.flags bit 31 when the unit must abort.
-__device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, ColdRec *cold, int tid, uint32_t k0, uint32_t k1,
+__device__ __noinline__ void ran_events_smem(const StepParams &p, const SmemView &v, ColdRec *cold, int tid, uint32_t k0, uint32_t k1, uint32_t genv,
                                              uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, int slots_cap, RanCtx &c) {
-    struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran}, {k0, k1, s, STREAM_CHAN, c.c_chan},
-                                                {k0, k1, s, STREAM_VBR, c.c_vbr}};
+    struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran, genv}, {k0, k1, s, STREAM_CHAN, c.c_chan, genv},
+                                                {k0, k1, s, STREAM_VBR, c.c_vbr, genv}};
     int n_ues = c.n_ues, cbr_next = c.cbr_next, vbr_next = c.vbr_next;
     uint32_t next_dep = c.next_dep, flags = c.flags;
     int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
@@ -288,11 +288,12 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
     UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
     ColdRec *cold = st.cold + (size_t)u * st.K;                  // per-step scratch: committed only if the unit does not abort
-    const uint64_t seed = p.seed0 + (uint64_t)env;
+    const uint64_t seed = p.seed0;
+    const uint32_t genv = p.env0 + (uint32_t)env;   // global env id: Philox counter word 3
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     uint32_t c_ran = hdr.ctr[0];
-    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1]}, r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2]},
-        r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
+    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1], genv}, r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2], genv},
+        r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3], genv};
 
     int n_ues = pad ? 0 : hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
     uint32_t clock = hdr.clock, next_dep = DEP_NEVER;
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
         if (!dead) {
             if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
                 RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
-                ran_events_smem(p, v, cold, tid, k0, k1, (uint32_t)s, t, clock, a_prb_all - a_prb_v, a_th_all - a_th_v, slots_cap, c);
+                ran_events_smem(p, v, cold, tid, k0, k1, genv, (uint32_t)s, t, clock, a_prb_all - a_prb_v, a_th_all - a_th_v, slots_cap, c);
                 c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
                 n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
                 if (flags & 0x80000000u) { dead = true; n_ues = 0; }

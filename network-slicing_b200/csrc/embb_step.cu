@@ -32,11 +32,12 @@ __global__ void __launch_bounds__(128) embb_step_unit_thread(const __grid_consta
 
     UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
-    const uint64_t seed = p.seed0 + (uint64_t)env;
-    PhiloxStream r_ran{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_RAN, hdr.ctr[0]};
-    PhiloxStream r_chan{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_CHAN, hdr.ctr[1]};
-    PhiloxStream r_rx{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_L1RX, hdr.ctr[2]};
-    PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
+    const uint64_t seed = p.seed0;
+    const uint32_t genv = p.env0 + (uint32_t)env;   // global env id: Philox counter word 3
+    PhiloxStream r_ran{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_RAN, hdr.ctr[0], genv};
+    PhiloxStream r_chan{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_CHAN, hdr.ctr[1], genv};
+    PhiloxStream r_rx{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_L1RX, hdr.ctr[2], genv};
+    PhiloxStream r_vbr{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)s, STREAM_VBR, hdr.ctr[3], genv};
 
     int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
     uint32_t clock = hdr.clock;
@@ -236,11 +237,12 @@ __global__ void __launch_bounds__(128) embb_step_mux_thread(const __grid_constan
     UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
     MuxRan *mux = st.mux + (size_t)u * R;
-    const uint64_t seed = p.seed0 + (uint64_t)env;
+    const uint64_t seed = p.seed0;
+    const uint32_t genv = p.env0 + (uint32_t)env;   // global env id: Philox counter word 3
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1]};
-    PhiloxStream r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2]};
-    PhiloxStream r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3]};
+    PhiloxStream r_chan{k0, k1, (uint32_t)s, STREAM_CHAN, hdr.ctr[1], genv};
+    PhiloxStream r_rx{k0, k1, (uint32_t)s, STREAM_L1RX, hdr.ctr[2], genv};
+    PhiloxStream r_vbr{k0, k1, (uint32_t)s, STREAM_VBR, hdr.ctr[3], genv};
 
     int n_ues = hdr.n_ues;
     uint32_t clock = hdr.clock;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(128) embb_step_mux_thread(const __grid_constan
         ++clock;
         // ================= for slice_ran in slices_ran: slot(), extract_users, add_users (slice_l1.py:195-198)
         for (int r = 0; r < R; ++r) {
-            PhiloxStream r_ran{k0, k1, (uint32_t)r, STREAM_RAN, c_ran[r]};
+            PhiloxStream r_ran{k0, k1, (uint32_t)r, STREAM_RAN, c_ran[r], genv};
             int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
             if (cbr_next[r] == 0) {                                              // slice_ran.py:205-227
                 cbr_next[r] = exp_slots_ms(r_ran, 1.0 / (2.0 / 60.0));

@@ -30,8 +30,9 @@ __global__ void __launch_bounds__(128) mmtc_reset_kernel(const __grid_constant__
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
     const int env = u / p.n_mmtc, m = u - env * p.n_mmtc;
-    const uint64_t seed = p.seed0 + (uint64_t)env;
-    PhiloxStream r{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(p.n_l1e + m), STREAM_MTC, st.ctr[u]};   // stream of L1 slice n_l1e + m
+    const uint64_t seed = p.seed0;
+    const uint32_t genv = p.env0 + (uint32_t)env;   // global env id: Philox counter word 3
+    PhiloxStream r{(uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(p.n_l1e + m), STREAM_MTC, st.ctr[u], genv};   // stream of L1 slice n_l1e + m
     for (int i = 0; i < N_MTC_DEV; ++i) {
         const uint32_t rep_ix = r.integers(7);
         const uint32_t per_ix = r.integers(8);

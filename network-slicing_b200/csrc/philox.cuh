@@ -1,11 +1,12 @@
 // Philox4x32-10 counter-based streams (RNG contract: network-slicing_b200/philox.py).
-// key = per-env seed, counter = (draw index, stream id, slice index, 0); one tick per variate.
+// key = base seed of the batch, counter = (draw index, stream id, slice index, global env id); one tick per variate.
+// (The env id is a counter word, not a key offset: batches with adjacent seeds share no streams.)
 #pragma once
 #include <cstdint>
 
 namespace rs {
 
-enum Stream : uint32_t { STREAM_RAN = 0, STREAM_CHAN = 1, STREAM_L1RX = 2, STREAM_VBR = 3, STREAM_MTC = 4 };
+enum Stream : uint32_t { STREAM_RAN = 0, STREAM_CHAN = 1, STREAM_L1RX = 2, STREAM_VBR = 3, STREAM_MTC = 4, STREAM_KBRL = 5 };
 
 struct U4 { uint32_t x, y, z, w; };
 
@@ -24,8 +25,8 @@ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
 
 // One (env, slice, purpose) stream; `n` is the persistent draw counter.
 struct PhiloxStream {
-    uint32_t k0, k1, slice, stream, n;
-    __device__ __forceinline__ U4 raw() { return philox4x32_10(n++, stream, slice, 0u, k0, k1); }
+    uint32_t k0, k1, slice, stream, n, env;
+    __device__ __forceinline__ U4 raw() { return philox4x32_10(n++, stream, slice, env, k0, k1); }
     // 53-bit uniform in [0,1): ((x>>5)*2^26 + (y>>6)) / 2^53, exact in fp64
     __device__ __forceinline__ double u01() {
         const U4 r = raw();

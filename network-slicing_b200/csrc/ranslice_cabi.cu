@@ -65,6 +65,11 @@ struct rs_handle {
     uint32_t *a_flags[2];
     int async_slot;
     cudaEvent_t ev_fork, ev_join;
+    // ordering between entry points that launch on different streams (rs_step_device on a caller stream, then rs_reset /
+    // rs_step / rs_step_async on the handle's own stream, or the other way round): the last step's stream and an event at its end
+    cudaEvent_t ev_last;
+    cudaStream_t last_stream;
+    bool has_last;
     uint64_t launches;
     bool was_reset;
     bool profiling;
@@ -137,6 +142,8 @@ void rs_set_error(const char *msg) { g_err = msg ? msg : ""; }   // shared with 
 
 int rs_n_variables(const rs_handle *h) { return h ? h->p.V : 0; }
 
+static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tables);
+
 int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     if (!cfg || !tables || !out) return fail(RS_E_ARG, "null argument");
     if (cfg->abi_version != RS_ABI_VERSION) return fail(RS_E_ARG, "abi_version mismatch");
@@ -150,6 +157,9 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     const int K = mux ? 32 : (cfg->max_ues ? cfg->max_ues : 16), MB = cfg->max_bursts ? cfg->max_bursts : 8;   // a multiplexed L1 holds the UEs of all its RAN slices
     const int Q = cfg->mtc_queue_cap ? cfg->mtc_queue_cap : 128;
     if (K < 2 || K > 32 || MB < 1 || MB > 16 || Q < 1) return fail(RS_E_ARG, "caps out of range");
+    if (mux && cfg->n_mmtc > 1)
+        return fail(RS_E_ARG, "l1_mux with n_mmtc > 1 is not supported: the reference multiplexes all mMTC RAN slices into ONE "
+                              "SliceL1mMTC (scenario_creator.py:173-176), this library keeps one L1 per mMTC slice");
     if (!tables->trace || !tables->mcs_rate || !tables->mcs_snr || !tables->mcs_order || !tables->mcs_mod)
         return fail(RS_E_ARG, "null table pointer");
     int ndev = 0;
@@ -161,6 +171,15 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     std::memset(static_cast<void *>(h), 0, sizeof(*h));
     h->cfg = *cfg;
     h->cfg.max_ues = K; h->cfg.max_bursts = MB; h->cfg.mtc_queue_cap = Q;
+    const int rc = create_impl(h, cfg, tables);
+    if (rc != RS_OK) { rs_destroy(h); return rc; }             // frees whatever had been allocated (the error text is kept)
+    *out = h;
+    return RS_OK;
+}
+
+static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tables) {
+    const bool mux = cfg->l1_mux != 0;
+    const int K = h->cfg.max_ues, MB = h->cfg.max_bursts, Q = h->cfg.mtc_queue_cap;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, cfg->device));
     h->sm_count = prop.multiProcessorCount;
@@ -171,7 +190,7 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     p.S = p.n_l1e + cfg->n_mmtc;
     p.n_prbs = cfg->n_prbs; p.slots = cfg->slots_per_step; p.V = 10 * cfg->n_embb + 3 * cfg->n_mmtc;
     p.penalty = cfg->penalty; p.prop_A = cfg->prop_A; p.prop_B = cfg->prop_B;
-    p.seed0 = cfg->base_seed + cfg->first_env_id;
+    p.seed0 = cfg->base_seed; p.env0 = (uint32_t)cfg->first_env_id;
     {   // scenario_creator.py:106,115-134 (same fp64 expressions)
         const double tps = cfg->slots_per_step * 1e-3;
         const int sps = cfg->slots_per_step;
@@ -201,7 +220,7 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
         for (size_t i = 0; i < n_trace; ++i) {
             const double v = tables->trace[i];
             if (std::isnan(v)) { fix[i] = 0; continue; }
-            if (std::fabs(v) >= 127.0) { delete h; return fail(RS_E_ARG, "fading trace value out of the +-127 dB fixed-point range"); }
+            if (std::fabs(v) >= 127.0) return fail(RS_E_ARG, "fading trace value out of the +-127 dB fixed-point range");
             fix[i] = (int32_t)std::llrint(v * 4194304.0);
         }
         CU(cudaMalloc(&h->d_trace_fix, n_trace * sizeof(int32_t)));
@@ -271,11 +290,11 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     h->async_slot = 1;
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
     p.flags_acc = h->d_flags_acc;
     p.trace_elems = h->d_trace_elems;
     p.slow_paths = h->d_slow_paths;
     p.debug_check = 0;
-    *out = h;
     return RS_OK;
 }
 
@@ -295,6 +314,7 @@ int rs_destroy(rs_handle *h) {
     cudaFree(h->a_flags[1]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     if (h->prof_events) { for (auto e : *h->prof_events) cudaEventDestroy(e); delete h->prof_events; }
     delete h;
     return RS_OK;
@@ -305,6 +325,10 @@ int rs_reset(rs_handle *h, float *obs) {
     CU(cudaSetDevice(h->cfg.device));
     // NodeB.reset (node_b.py:17-22): UEs, timers and accumulators cleared; RNG counters keep running
     // (the reference never reseeds on reset).  eMBB: zero everything but the counters.
+    // Steps still queued on another stream (rs_step_device on the caller's stream, rs_step_async) finish first.
+    if (h->has_last) CU(cudaStreamWaitEvent(h->stream, h->ev_last, 0));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_copied[0], 0));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_copied[1], 0));
     if (h->embb.U) { rs::launch_embb_reset(h->embb, h->stream); h->launches += 1; }
     if (h->embb.U && h->cfg.l1_mux) { rs::launch_embb_mux_reset(h->embb, h->stream); h->launches += 1; }
     if (h->mmtc.U) {
@@ -324,6 +348,8 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     if (!h->was_reset) return fail(RS_E_STATE, "rs_step before rs_reset");
     CU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    // a step on another stream than the previous one (caller's stream vs the handle's own) is ordered after it
+    if (h->has_last && h->last_stream != st) CU(cudaStreamWaitEvent(st, h->ev_last, 0));
     rs::StepParams p = h->p;
     p.action = d_action;
     p.obs = d_obs ? d_obs : h->d_obs;
@@ -364,6 +390,8 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
         for (auto &e : ev) h->prof_events->push_back(e);
     }
     CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ev_last, st));
+    h->last_stream = st; h->has_last = true;
     return RS_OK;
 }
 
@@ -372,6 +400,10 @@ int rs_step(rs_handle *h, const int32_t *action, float *obs, float *reward, int3
     if (!h || !action) return fail(RS_E_ARG, "null handle/action");
     CU(cudaSetDevice(h->cfg.device));
     const size_t N = (size_t)h->p.N, S = (size_t)h->p.S, V = (size_t)h->p.V;
+    // device I/O set 0 is shared with rs_step_async: an outstanding ticket's copies finish before it is overwritten; a
+    // step still queued on a caller's stream (rs_step_device) reads its own action buffer but shares the state
+    CU(cudaStreamWaitEvent(h->stream, h->ev_copied[0], 0));
+    if (h->has_last && h->last_stream != h->stream) CU(cudaStreamWaitEvent(h->stream, h->ev_last, 0));
     CU(cudaMemcpyAsync(h->d_action, action, N * S * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
     int rc = rs_step_device(h, h->d_action, nullptr, nullptr, nullptr, nullptr, nullptr, h->stream);
     if (rc) return rc;

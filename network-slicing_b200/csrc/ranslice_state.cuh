@@ -119,7 +119,8 @@ struct StepParams {
     double penalty, prop_A, prop_B;
     double norm_embb[10], norm_mmtc[3];
     double obs_time;               // slots_per_step * slot_length (slice_ran.py:165)
-    uint64_t seed0;                // base_seed + first_env_id
+    uint64_t seed0;                // base_seed: the Philox key of every env of the batch
+    uint32_t env0;                 // first_env_id: global id of local env 0 (Philox counter word 3 = env0 + env)
     const int32_t *action;         // [N][S]
     float *obs;                    // [N][V]
     float *reward;                 // [N]

@@ -4,8 +4,12 @@ The reference draws from one shared ``numpy.random.Generator`` (plus the legacy
 global ``np.random`` in ``traffic_generators.py:66,96-97``).  The native env
 replaces that with one counter-based stream per (env, slice, purpose):
 
-    key     = (seed_lo, seed_hi)            # 64-bit per-env seed = base_seed + global env id
-    counter = (draw_index, stream_id, slice_index, 0)
+    key     = (seed_lo, seed_hi)            # the 64-bit base seed of the batch (create_env's rng / seed)
+    counter = (draw_index, stream_id, slice_index, global env id)
+
+(The env id sits in the counter, not in the key: batches created with adjacent integer seeds -- the
+reference's replication pattern ``default_rng(seed=i) for i in range(RUNS)``, experiments_kbrl.py:47 --
+share no streams, and results stay invariant to how a batch is sharded over devices.)
 
 Every variate consumes ONE counter tick (``normal`` and ``random(2)`` consume two).
 The uniform->variate transforms below are the definition; the C oracle
@@ -51,15 +55,16 @@ def u01(x0, x1):
 class PhiloxStream:
     """Duck-typed stand-in for ``numpy.random.Generator`` (methods the reference calls)."""
 
-    def __init__(self, seed, slice_index, stream_id, counter=0):
+    def __init__(self, seed, slice_index, stream_id, counter=0, env=0):
         self.k0 = seed & MASK
         self.k1 = (seed >> 32) & MASK
         self.slice_index = slice_index
         self.stream_id = stream_id
+        self.env = env & MASK
         self.n = counter
 
     def _raw(self):
-        out = philox4x32_10(self.n & MASK, self.stream_id, self.slice_index, 0, self.k0, self.k1)
+        out = philox4x32_10(self.n & MASK, self.stream_id, self.slice_index, self.env, self.k0, self.k1)
         self.n += 1
         return out
 

@@ -1,7 +1,7 @@
 """Multi-GPU plumbing: independent env shards, one process per GPU, no collective on the step path.
 
 Envs are split into contiguous ranges of GLOBAL env ids; the Philox key of an env is
-``base_seed + global id`` (``rs_config.first_env_id``), so results do not depend on the split.
+the batch's base seed and the GLOBAL env id as a counter word (``rs_config.first_env_id``), so results do not depend on the split.
 ``torch.distributed`` is used only around the step loop: a barrier, the max-over-ranks of the device time
 and, when a caller wants them in one place, a host-side gather of the per-shard outputs.
 """

@@ -38,10 +38,10 @@ void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-typedef struct { uint32_t key[2]; uint32_t *ctr; /* [S][ORC_N_STREAMS] */ } philox_ctx;
+typedef struct { uint32_t key[2]; uint32_t env; /* global env id: counter word 3 */ uint32_t *ctr; /* [S][ORC_N_STREAMS] */ } philox_ctx;
 
 static void px_raw(philox_ctx *p, int slice, int stream, uint32_t out[4]) {
-    uint32_t c[4] = {p->ctr[slice * ORC_N_STREAMS + stream]++, (uint32_t)stream, (uint32_t)slice, 0u};
+    uint32_t c[4] = {p->ctr[slice * ORC_N_STREAMS + stream]++, (uint32_t)stream, (uint32_t)slice, p->env};
     orc_philox(c, p->key, out);
 }
 static double px_random(void *ctx, int slice, int stream) {
@@ -218,7 +218,7 @@ void orc_set_rng(orc_env *e, const orc_rng *rng) {
     e->rng.normal = px_normal; e->rng.random2 = px_random2; e->rng.choice = px_integers;
 }
 
-orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed) {
+orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed, uint32_t env_id) {
     orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
     e->cfg = *cfg; e->tbl = *tbl;
     e->n_l1_embb = cfg->l1_mux ? (cfg->n_embb > 0) : cfg->n_embb;
@@ -230,7 +230,7 @@ orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed)
     }
     e->mmtc = (mmtc_t *)calloc(cfg->n_mmtc > 0 ? cfg->n_mmtc : 1, sizeof(mmtc_t));
     e->ctr = (uint32_t *)calloc((size_t)(cfg->n_embb + cfg->n_mmtc + 1) * ORC_N_STREAMS, sizeof(uint32_t));
-    e->px.key[0] = (uint32_t)seed; e->px.key[1] = (uint32_t)(seed >> 32); e->px.ctr = e->ctr;
+    e->px.key[0] = (uint32_t)seed; e->px.key[1] = (uint32_t)(seed >> 32); e->px.env = env_id; e->px.ctr = e->ctr;
     orc_set_rng(e, NULL);
     compute_factors(0.1, &e->A, &e->B);
     for (int i = 0; i < 256; ++i) { double bps; orc_mcs_lut(tbl, i - 128, &e->lut_mcs[i], &bps, &e->lut_rate[i]); }

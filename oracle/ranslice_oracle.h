@@ -48,7 +48,8 @@ typedef struct orc_tables {
 
 typedef struct orc_env orc_env;
 
-orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed);
+/* built-in Philox streams: key = seed (the batch's base seed), counter word 3 = env_id (global env id) */
+orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed, uint32_t env_id);
 void orc_set_rng(orc_env *e, const orc_rng *rng);     /* NULL -> built-in Philox(seed) */
 void orc_destroy(orc_env *e);
 int orc_n_variables(const orc_env *e);

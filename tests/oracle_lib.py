@@ -50,7 +50,7 @@ def lib():
             build()
         L = C.CDLL(_SO)
         L.orc_create.restype = C.c_void_p
-        L.orc_create.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcTables), C.c_uint64]
+        L.orc_create.argtypes = [C.POINTER(OrcConfig), C.POINTER(OrcTables), C.c_uint64, C.c_uint32]
         L.orc_set_rng.argtypes = [C.c_void_p, C.POINTER(OrcRng)]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_n_variables.argtypes = [C.c_void_p]
@@ -119,8 +119,10 @@ class OracleEnv:
     """One oracle environment (scenario index like scenario_creator.create_env)."""
 
     def __init__(self, tables, scenario, seed, slots_per_step=50, penalty=100.0,
-                 propagation="macro_cell_urban_2GHz", numpy_rng=None, l1_mux=False):
+                 propagation="macro_cell_urban_2GHz", numpy_rng=None, l1_mux=False, env_id=0):
         n_prbs, n_embb, n_mmtc = SCENARIOS[scenario]
+        if l1_mux and n_mmtc > 1:      # the reference puts all mMTC RAN slices into ONE SliceL1mMTC (scenario_creator.py:173-176)
+            raise ValueError("l1_mux with n_mmtc > 1 is not restated by the oracle")
         A, B = PROPAGATION[propagation]
         self.cfg = OrcConfig(n_prbs, n_embb, n_mmtc, slots_per_step, penalty, A, B, int(bool(l1_mux)), 0)
         self.tbl = c_tables(tables)
@@ -128,7 +130,7 @@ class OracleEnv:
         self.n_ran = n_embb + n_mmtc
         self.V = 10 * n_embb + 3 * n_mmtc
         self.n_prbs = n_prbs
-        self.h = lib().orc_create(C.byref(self.cfg), C.byref(self.tbl), C.c_uint64(seed))
+        self.h = lib().orc_create(C.byref(self.cfg), C.byref(self.tbl), C.c_uint64(seed), C.c_uint32(env_id))
         self._rng = None
         if numpy_rng is not None:
             self._rng = NumpyRng(numpy_rng)
@@ -162,10 +164,10 @@ class OracleEnv:
 
 
 class OracleBatch:
-    """N independent oracle envs with Philox seeds base_seed + i, stepped by n_threads pthreads."""
+    """N independent oracle envs (Philox key base_seed, env ids first_env + i), stepped by n_threads pthreads."""
 
     def __init__(self, tables, scenario, n_envs, base_seed, n_threads=1, first_env=0, **kw):
-        self.envs = [OracleEnv(tables, scenario, base_seed + first_env + i, **kw) for i in range(n_envs)]
+        self.envs = [OracleEnv(tables, scenario, base_seed, env_id=first_env + i, **kw) for i in range(n_envs)]
         self.N, self.S, self.V = n_envs, self.envs[0].S, self.envs[0].V
         self.n_threads = n_threads
         self.handles = (C.c_void_p * n_envs)(*[e.h for e in self.envs])

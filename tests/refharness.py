@@ -150,7 +150,7 @@ def _route_global_exponential(scale=1.0):
     return _Ctx.current_vbr.exponential(scale)
 
 
-def make_env_philox(seed, scenario, **kw):
+def make_env_philox(seed, scenario, env_id=0, **kw):
     """Reference env whose every draw comes from per-slice Philox streams (RNG contract of the
     native env, ``ranslice_b200/philox.py``).  Returns (env, streams) with all counters at 0
     right before the caller's ``env.reset()``."""
@@ -165,15 +165,15 @@ def make_env_philox(seed, scenario, **kw):
     for i, l1 in enumerate(env.node_b.slices_l1):
         st = {}
         if l1.type == "eMBB":
-            st["ran"] = px.PhiloxStream(seed, i, px.STREAM_RAN)
-            st["chan"] = px.PhiloxStream(seed, i, px.STREAM_CHAN)
-            st["l1rx"] = px.PhiloxStream(seed, i, px.STREAM_L1RX)
-            st["vbr"] = px.PhiloxStream(seed, i, px.STREAM_VBR)
+            st["ran"] = px.PhiloxStream(seed, i, px.STREAM_RAN, env=env_id)
+            st["chan"] = px.PhiloxStream(seed, i, px.STREAM_CHAN, env=env_id)
+            st["l1rx"] = px.PhiloxStream(seed, i, px.STREAM_L1RX, env=env_id)
+            st["vbr"] = px.PhiloxStream(seed, i, px.STREAM_VBR, env=env_id)
             l1.rng = st["l1rx"]
             if len(l1.slices_ran) == 1:
                 l1.slices_ran[0].rng = st["ran"]
             else:   # L1_level=False: several RAN slices multiplexed in one L1; RAN stream of RAN slice r = (slice r, RAN)
-                st["ran_mux"] = [px.PhiloxStream(seed, r, px.STREAM_RAN) for r in range(len(l1.slices_ran))]
+                st["ran_mux"] = [px.PhiloxStream(seed, r, px.STREAM_RAN, env=env_id) for r in range(len(l1.slices_ran))]
                 for r, sr in enumerate(l1.slices_ran):
                     sr.rng = st["ran_mux"][r]
             shared_gen = l1.snr_generator if shared_gen is None else shared_gen
@@ -184,7 +184,7 @@ def make_env_philox(seed, scenario, **kw):
             gen.nominal_sinr.rng = st["chan"]
             l1.snr_generator = gen
         else:
-            st["mtc"] = px.PhiloxStream(seed, i, px.STREAM_MTC)
+            st["mtc"] = px.PhiloxStream(seed, i, px.STREAM_MTC, env=env_id)
             l1.slices_ran[0].rng = st["mtc"]
         streams.append(st)
         orig_slot = l1.slot

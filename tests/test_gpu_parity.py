@@ -210,7 +210,7 @@ def test_full_size_batch_rows_equal_small_batches_and_oracle(tables, scn, N):
     lo = make_env(scn, K, seed, first_env_id=0)
     hi = make_env(scn, K, seed, first_env_id=N - K)
     orc_lo = ol.OracleBatch(tables, scn, K, seed, n_threads=8)
-    orc_hi = ol.OracleBatch(tables, scn, K, seed + N - K, n_threads=8)      # oracle env e has seed base + e
+    orc_hi = ol.OracleBatch(tables, scn, K, seed, n_threads=8, first_env=N - K)   # same global env ids
     for e in (big, lo, hi, orc_lo, orc_hi):
         e.reset()
     rng = np.random.default_rng(77)
@@ -290,7 +290,7 @@ def test_multiplexed_l1_vs_oracle_and_facade(tables):
     of the multiplexed unit are flagged and excluded; the single-env facade reports info['l1_info'] per RAN slice."""
     scn, N, T, seed = 0, 96, 60, 515
     env = make_env(scn, N, seed, L1_level=False)
-    orcs = [ol.OracleEnv(tables, scn, seed + e, l1_mux=True) for e in range(N)]
+    orcs = [ol.OracleEnv(tables, scn, seed, env_id=e, l1_mux=True) for e in range(N)]
     env.reset()
     for o in orcs:
         o.reset()

@@ -51,7 +51,7 @@ def test_golden_multiplexed_l1(tables, golden, name, scn):
     g = golden(name)
     E, T, S = g["actions"].shape
     for e in range(E):
-        env = ol.OracleEnv(tables, scn, int(g["base_seed"]) + e, l1_mux=True)
+        env = ol.OracleEnv(tables, scn, int(g["base_seed"]), env_id=e, l1_mux=True)
         assert env.S == S
         assert np.array_equal(env.reset(), g["obs0"][e])
         for t in range(T):

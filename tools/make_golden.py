@@ -42,10 +42,10 @@ def gen_A(name):
 
 def _gen_B_env(args):
     import refharness as rh
-    scn, seed, steps = args
+    scn, base, e, steps = args
     S, n_prbs = SCN[scn]
-    env, _ = rh.make_env_philox(seed, scn)
-    act = rh.simplex_actions(seed, S, n_prbs, steps)
+    env, _ = rh.make_env_philox(base, scn, env_id=e)                # key = base seed, counter word 3 = env id
+    act = rh.simplex_actions(base + e, S, n_prbs, steps)
     tr = rh.run_trace(env, act)
     tr["actions"] = act
     return tr
@@ -53,10 +53,11 @@ def _gen_B_env(args):
 
 def _gen_M_env(args):
     import refharness as rh
-    scn, seed, steps = args
+    scn, base, e, steps = args
+    seed = base + e
     n_embb = SCN[scn][0] - (1 if scn == 3 else 0)
     S = 1 + (1 if scn == 3 else 0)                           # L1 slices: one multiplexed eMBB L1 (+ the mMTC L1)
-    env, _ = rh.make_env_philox(seed, scn, L1_level=False)
+    env, _ = rh.make_env_philox(base, scn, env_id=e, L1_level=False)
     assert env.n_slices == S
     act = rh.simplex_actions(seed, S, SCN[scn][1], steps)
     act[::9] = act[::9] // 8                                 # starved periods: deep backlogs, contended PF over all RAN slices
@@ -69,7 +70,7 @@ def _gen_M_env(args):
 
 def gen_M(name, pool):
     scn, base, n_envs, steps = M_CASES[name]
-    trs = list(pool.map(_gen_M_env, [(scn, base + e, steps) for e in range(n_envs)]))
+    trs = list(pool.map(_gen_M_env, [(scn, base, e, steps) for e in range(n_envs)]))
     stacked = {k: np.stack([t[k] for t in trs]) for k in trs[0]}
     np.savez_compressed(os.path.join(OUT, name + ".npz"), scenario=scn, base_seed=base, l1_level=False,
                         numpy_version=np.__version__, **stacked)
@@ -78,7 +79,7 @@ def gen_M(name, pool):
 
 def gen_B(name, pool):
     scn, base, n_envs, steps = B_CASES[name]
-    trs = list(pool.map(_gen_B_env, [(scn, base + e, steps) for e in range(n_envs)]))
+    trs = list(pool.map(_gen_B_env, [(scn, base, e, steps) for e in range(n_envs)]))
     stacked = {k: np.stack([t[k] for t in trs]) for k in trs[0]}   # [E, T, ...]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), scenario=scn, base_seed=base,
                         numpy_version=np.__version__, **stacked)

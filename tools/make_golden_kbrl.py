@@ -16,7 +16,57 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 OUT = os.path.join(ROOT, "tests", "golden")
 
-CASES = {"K_scn0": (0, 9000, 400, [0.97, 0.99]), "K_scn1": (1, 9100, 300, [0.99, 0.999])}
+CASES = {"K_scn0": (0, 9000, 400, [0.97, 0.99]), "K_scn1": (1, 9100, 300, [0.99, 0.999]),
+         # the reference's horizon: dictionaries of several hundred landmarks (experiments_kbrl.py runs 50 400 steps)
+         "K_long0": (0, 9200, 3000, [0.97, 0.99]),
+         # scripted states (no env) that put whole dictionaries out of reach: f == 0 exactly, so the random tie-break of
+         # GaussianKernel.predict (kernel.py:26-27) fires in update_control and in the select_action scan
+         "K_tie": (0, 9300, 80, [0.97, 0.99])}
+FULL_KINV_MAX_D = 160      # K_long: K^-1 is stored in full only for dictionaries up to this size (diag + row sums for all)
+
+
+class _Ctx:
+    learner = 0
+
+
+def _route_tie_break(ref, agent, seed, tie_calls):
+    """np.random.choice([-1, 1]) (kernel.py:27) -> Philox stream (seed, learner, STREAM_KBRL) of the learner predicting."""
+    import types
+    from ranslice_b200 import philox as px
+    streams = [px.PhiloxStream(seed, s, px.STREAM_KBRL) for s in range(len(agent.learners))]
+
+    def choice(seq):
+        tie_calls.append(_Ctx.learner)
+        return seq[streams[_Ctx.learner].integers(len(seq))]
+
+    ref.kernel.np = types.SimpleNamespace(exp=np.exp, ndim=np.ndim, array=np.array, float32=np.float32, sign=np.sign,
+                                          random=types.SimpleNamespace(choice=choice))
+    for s, h in enumerate(agent.learners):
+        orig = h.algorithm.kernel.predict
+
+        def predict(x, orig=orig, s=s):
+            _Ctx.learner = s
+            return orig(x)
+
+        h.algorithm.kernel.predict = predict
+
+
+class _ScriptedEnv:
+    """Stand-in for the env in K_tie: scripted observations / labels; every 7th step far away from everything seen."""
+
+    def __init__(self, seed, V, S):
+        self.rng, self.V, self.S, self.t = np.random.default_rng(seed), V, S, 0
+
+    def reset(self):
+        return np.zeros(self.V, np.float32)
+
+    def step(self, action):
+        self.t += 1
+        obs = self.rng.random(self.V).astype(np.float32)
+        if self.t % 7 in (3, 4):
+            obs = (obs + np.float32(40.0 + self.t)).astype(np.float32)
+        labels = np.where(self.rng.random(self.S) < 0.5, 1, -1)
+        return obs, 0.0, False, {"SLA_labels": labels, "total_violations": int((labels < 0).sum())}
 
 
 def gen(name):
@@ -24,12 +74,10 @@ def gen(name):
     scn, seed, steps, a_range = CASES[name]
     ref = rh.load_reference()
     tie_calls = []
-    ref.kernel.np = __import__("types").SimpleNamespace(
-        exp=np.exp, ndim=np.ndim, array=np.array, float32=np.float32, sign=np.sign,
-        random=__import__("types").SimpleNamespace(choice=lambda seq: tie_calls.append(1) or seq[0]))
-    env, _ = rh.make_env_philox(seed, scn)
     agent = ref.scenario_creator.create_kbrl_agent(np.random.default_rng(seed), scn, accuracy_range=a_range)
     S = agent.n_slices
+    _route_tie_break(ref, agent, seed, tie_calls)
+    env = _ScriptedEnv(seed, 10 * S, S) if name == "K_tie" else rh.make_env_philox(seed, scn)[0]
     init_action = agent.action.copy()
     init_sec = agent.security_factors.copy()
     rec = {k: [] for k in ("state", "action", "labels", "new_state", "next_action", "adjusted", "hits", "sizes",
@@ -64,16 +112,24 @@ def gen(name):
         lm[s, :D, :dims[s]] = L
         cf[s, :D] = np.asarray(h.algorithm.sv.coeff, np.float64)
         ki[s, :D, :D] = np.atleast_2d(np.asarray(h.algorithm.Kinv, np.float64))
+    extra = {}
+    if Dmax > FULL_KINV_MAX_D:         # keep the fixture small: full K^-1 only for the small dictionaries
+        extra["kinv_diag"] = np.stack([np.diag(ki[s]) for s in range(S)])
+        extra["kinv_rowsum"] = ki.sum(axis=2)
+        small = [s for s in range(S) if out["sizes"][-1][s] <= FULL_KINV_MAX_D]
+        extra["kinv_full_learners"] = np.array(small, np.int64)
+        ki = ki[small][:, :FULL_KINV_MAX_D, :FULL_KINV_MAX_D] if small else np.zeros((0, 1, 1))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), scenario=scn, seed=seed, accuracy_range=np.array(a_range),
                         init_action=init_action.astype(np.int64), init_sec=init_sec.astype(np.int64), dims=np.array(dims),
                         n_prbs=agent.n_prbs, alfa=agent.alfa, tie_calls=len(tie_calls), final_landmarks=lm,
-                        final_coeff=cf, final_kinv=ki, accuracies=agent.accuracies, numpy_version=np.__version__, **out)
+                        final_coeff=cf, final_kinv=ki, accuracies=agent.accuracies, tie_learners=np.array(tie_calls, np.int64),
+                        numpy_version=np.__version__, **extra, **out)
     return name, out["sizes"][-1].tolist(), int(out["violations"].sum()), len(tie_calls)
 
 
 if __name__ == "__main__":
     from concurrent.futures import ProcessPoolExecutor
     names = sys.argv[1:] or list(CASES)
-    with ProcessPoolExecutor(2) as ex:
+    with ProcessPoolExecutor(4) as ex:
         for r in ex.map(gen, names):
             print(r, flush=True)
