@@ -3,9 +3,11 @@
  *
  * Batched replacement for the per-learner calls KBRL_Control makes into Projectron / GaussianKernel
  * (reference: kbrl_control.py:41-114 -> algorithms/projectron.py:32-60 -> algorithms/kernel.py:8-28).
- * One learner per (env, slice): L = n_envs * n_slices learners, each with its own growing dictionary
- * (landmarks, coefficients, K^-1) resident in HBM, fp64 (with the reference's float32 stage while a
- * dictionary holds a single landmark, kernel.py:15-16).
+ * One learner per (env, slice): L = n_envs * n_slices learners, each with its own GROWING dictionary
+ * (SVvariable, algorithms/projectron.py:3-21: landmarks, coefficients, K^-1) resident in HBM, fp64 (with the
+ * reference's float32 stage while a dictionary holds a single landmark, kernel.py:15-16).  Dictionaries grow in rows
+ * of 32 landmarks taken from one device pool (K^-1 packed symmetric in 32 x 32 tiles, ~D^2/2 doubles per learner);
+ * nothing is pre-allocated per learner, so a few large dictionaries next to many small ones cost what they hold.
  *
  * x of a learner = [its slice's state variables (float32 -> float64), l1_prbs / n_prbs]
  * (kbrl_control.py:56,88).  Same conventions as ranslice_b200.h (0 / negative error code, rs_last_error()).
@@ -18,7 +20,10 @@
 extern "C" {
 #endif
 
-enum { KB_FLAG_DICT_CAP = 1u /* dictionary full: a sample that should have been added was dropped */ };
+enum {
+    KB_FLAG_DICT_CAP = 1u, /* the dictionary holds dict_cap landmarks: a sample that should have been added was dropped */
+    KB_FLAG_POOL = 2u      /* the device pool is exhausted: a sample that should have been added was dropped */
+};
 
 /* create_kbrl_agent(rng, n, accuracy_range) (scenario_creator.py:197-238): one
  * Learner(Projectron(GaussianKernel(SVvariable(), gamma), eta)) per slice, here for n_envs envs. */
@@ -27,9 +32,15 @@ typedef struct kb_config {
     int32_t device;
     int32_t n_envs, n_slices, n_prbs;
     int32_t n_variables;   /* V: row length of the state arrays */
-    int32_t dict_cap;      /* landmarks per learner (<= 1024); the reference is unbounded (flagged when hit) */
-    int32_t reserved;
+    int32_t dict_cap;      /* most landmarks ONE learner may hold (<= 2048, rounded up to 32; 0 -> 1024).  Only bounds the
+                            * per-learner row table and the shared-memory staging: memory is taken from the pool as a
+                            * dictionary grows.  The reference is unbounded (KB_FLAG_DICT_CAP when hit). */
+    int32_t pool_mb;       /* size of the dictionary pool in MiB; 0 -> min(what L full dictionaries need, 70 % of the free memory) */
     double gamma, eta;     /* scenario_creator.py:218 (gamma = 1), projectron.py:25 (eta = 0.1) */
+    uint64_t tie_seed;     /* GaussianKernel.predict draws np.random.choice([-1, 1]) when f == 0 (kernel.py:26-27): here from the */
+    uint64_t first_env_id; /* Philox stream (key tie_seed, counter (n, STREAM_KBRL, slice, first_env_id + env)), ranslice_b200/philox.py */
+    int32_t algorithm;     /* 0: Projectron (projectron.py:23-60, what create_kbrl_agent builds); 1: ProjectronPlus (:66-107) */
+    int32_t reserved;
 } kb_config;
 
 typedef struct kb_handle kb_handle;
@@ -78,6 +89,8 @@ int kb_predict(kb_handle *h, const float *state, int32_t *first_pos);
 
 /* dictionary sizes [N][S] and KB_FLAG_* per learner (host buffers, either may be NULL) */
 int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags);
+/* pool statistics (any may be NULL): bytes handed out / pool size, the largest dictionary, tie-break draws taken so far */
+int kb_get_pool(kb_handle *h, uint64_t *used_bytes, uint64_t *total_bytes, int32_t *max_dictionary, uint64_t *tie_breaks);
 /* dictionary of one learner, packed: landmarks [D][dims[s]], coeff [D], kinv [D][D]; returns D in *D_out */
 int kb_get_learner(kb_handle *h, int32_t learner, double *landmarks, double *coeff, double *kinv, int32_t *D_out);
 /* Validation switch: with on != 0 every kernel evaluation f(x) is done in fp64 in the reference's operation order;

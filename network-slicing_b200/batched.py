@@ -197,6 +197,16 @@ class BatchedRanSlice:
         return {"embb_ms": e.value / k, "mmtc_ms": m.value / k, "reward_ms": r.value / k, "steps": int(n.value),
                 "kernel": self.kernel_variant_name()}
 
+    def set_route_limits(self, single_start_max=6, single_slots=8, pair_start_max=14, pair_slots=16):
+        """Routing limits of the default eMBB kernel (tests; results never depend on them), see rs_set_route_limits."""
+        _lib.check(_lib.lib().rs_set_route_limits(self._h, single_start_max, single_slots, pair_start_max, pair_slots))
+
+    def routes(self):
+        """Units of the last step by route: dict(single, pair, general, aborted)."""
+        out = (C.c_uint64 * 4)()
+        _lib.check(_lib.lib().rs_get_routes(self._h, out))
+        return {"single": int(out[0]), "pair": int(out[1]), "general": int(out[2]), "aborted": int(out[3])}
+
     def set_debug_check(self, on=True):
         _lib.check(_lib.lib().rs_set_debug_check(self._h, int(bool(on))))
 

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offset_kernel(const __grid_
     *o = v;
     if (r0 == KEY_BINS - (int)HEAVY_BIT) st.hist[2 * KEY_BINS + 3] = v.w >> 1;   // bin HEAVY_BIT - 1: entries ahead of the first single-lane bin = 2 x pairs
     if (blockIdx.x == SCAN_BLOCKS - 1 && threadIdx.x == SCAN_THREADS - 1)       // entries of the front list
-        st.hist[2 * KEY_BINS + 0] = off + st.hist[2 * KEY_BINS + 4 + blockIdx.x];
+        { st.hist[2 * KEY_BINS + 0] = off + st.hist[2 * KEY_BINS + 4 + blockIdx.x]; st.hist[2 * KEY_BINS + 2] = st.hist[2 * KEY_BINS + 1]; }   // + list L as routed by the pre-pass
 }
 
 // Pre-pass 3: scatter.

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
     if (tix >= count) return;
     const int u_raw = st.perm[tix];
     const bool pad = u_raw < 0;                                  // idle lane lending its slots to the unit on its left
-    const int slots_cap = min(st.K, tix < (2 * (int)st.hist[2 * SORT_BINS + 3]) << st.dil ? 2 * SM_KS : SM_KS);
+    const int slots_cap = min(st.K, tix < (2 * (int)st.hist[2 * SORT_BINS + 3]) << st.dil ? st.route[3] : st.route[1]);
     const int u = pad ? 0 : u_raw;
     const int env = u / p.n_embb, s = u - env * p.n_embb;
     int i_prb, n_prbs;
@@ -707,7 +707,7 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
 #endif
         configured = true;
     }
-    launch_embb_sort(p, st, SM_MAX_START_UES_PAIR, SM_MAX_START_UES + 1, stream);
+    launch_embb_sort(p, st, st.route[2], st.route[0] + 1, stream);
     const int blocks = (st.perm_len + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
     if (st.wide) embb_step_smem<1><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     else embb_step_smem<0><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);

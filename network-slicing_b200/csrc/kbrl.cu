@@ -1,32 +1,47 @@
 // K3: KBRL inner loop -- Gaussian-kernel evaluation and Projectron dictionary projection / update,
 // batched over L = n_envs * n_slices independent learners (C ABI: include/kbrl_b200.h).
 //
-//   GaussianKernel.k_eval / k / predict   algorithms/kernel.py:8-28
+//   GaussianKernel.k_eval / k / predict   algorithms/kernel.py:8-28   (incl. the random tie-break at f == 0, :26-27)
+//   SVvariable.extend / update / insert   algorithms/projectron.py:3-21  (unbounded growing arrays)
 //   Projectron.predict / update           algorithms/projectron.py:32-60
+//   ProjectronPlus.update                 algorithms/projectron.py:66-107 (kb_config.algorithm = 1)
 //   callers restated: the select_action scan (kbrl_control.py:54-61) and the sample-augmentation loop of
 //   update_control (kbrl_control.py:103-112)
 //
-// One thread GROUP per learner (KB_GROUP = 32 threads = one warp by default, 4 groups per 128-thread block): a
-// learner-step is a chain of short phases (stage the dictionary, evaluate <= 201 candidates, find the first mistake,
-// project / extend) separated by barriers, so what matters is how many learners an SM keeps in flight and how cheap
-// the barriers are -- with one 256-thread CTA per learner the kernels spent 9.8 barrier-stall cycles per issued
-// instruction (profiles/r01f_kb_update_16384_full.txt).  Both callers evaluate f(a) = sum_j coeff_j exp(-gamma ||l_j - [s, a/n]||^2) for
-// up to n_prbs + 1 candidate allocations a of one state s.  numpy's pairwise sum over the 11 (4)
-// squared differences adds the action coordinate LAST, so the distance is separable bit-exactly:
-// base_j (state part, once per landmark) + (l_j,last - a/n)^2.  Threads own candidates and walk the
-// landmarks (broadcast from shared memory) in index order; a dictionary update (rare: ~0.3 per
-// learner-step) is a block-cooperative K^-1 k mat-vec (columns are coalesced, K^-1 is exactly
-// symmetric) and, when the sample is not well approximated, a rank-1 extension of K^-1.
-// The Gram / K^-1 products stay warp-reduced fp64: a D x D mat-vec 1.4 times per env-step is far below
-// any tensor-core crossover.
+// Both callers evaluate f(a) = sum_j coeff_j exp(-gamma ||l_j - [s, a/n]||^2) for up to n_prbs + 1 candidate
+// allocations a of one state s.  numpy's pairwise sum over the 11 (4) squared differences adds the action coordinate
+// LAST, so the distance is separable bit-exactly: base_j (state part, once per landmark) + (l_j,last - a/n)^2.
+// Threads own candidates and walk the landmarks (broadcast from shared memory) in index order; a dictionary update
+// is a block-cooperative K^-1 k mat-vec and, when the sample is not well approximated, a rank-1 extension of K^-1.
+//
+// DICTIONARY STORAGE (round 2).  The reference's dictionaries are unbounded (np.append / np.vstack); its own runs
+// reach several hundred landmarks within 3000 steps and > 1000 in the stored 50 400-step experiments.  A dense
+// K^-1[cap][cap] per learner cannot hold that (cap 1024 x 81 920 learners = 687 GB).  Each learner therefore GROWS in
+// rows of 32 landmarks taken from one device pool by a bump allocator (an atomicAdd inside the update kernel; nothing
+// is ever copied or freed until kb_reset):
+//
+//     tile row I of a learner = [ landmarks 32 x 16 | coeff 32 | K^-1 tiles (I,0) (I,1) ... (I,I), 32 x 32 each ]
+//
+// K^-1 is exactly symmetric, so only the lower block triangle is stored (diagonal tiles hold both triangles):
+// D(D+1)/2 doubles rounded up to tiles instead of cap^2 -- 0.37 MB at D = 289 instead of 8 MB at cap 1024 -- and the
+// mat-vec / rank-1 extension read and write half the bytes.  Element (i, j), i >= j: row[i >> 5] + 544 + (j >> 5) 1024
+// + (i & 31) 32 + (j & 31).  d* = K^-1 k: thread i walks j in index order (the order of the oracle): row i of the
+// tiles left of the diagonal (a 256-byte run per tile and lane, sector-efficient through L1), then column i of the
+// diagonal tile and of the tiles below it (coalesced across the lanes of a warp).
+//
+// The Gram / K^-1 products stay on CUDA cores in fp64: the only matrix-shaped work is a D x D mat-VEC (0.25 flop per
+// byte, HBM-bound from D ~ 100 on) and f(a) is one exp per (landmark, candidate) pair on a separable distance -- there
+// is no contraction for tensor cores to take (measured: tools/kb_crossover.py).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
 
 #include "../../include/kbrl_b200.h"
 #include "../../include/ranslice_b200.h"
+#include "philox.cuh"
 
 namespace kb {
 
@@ -40,6 +55,9 @@ namespace kb {
 #endif
 #ifndef KB_GROUP_PREDICT
 #define KB_GROUP_PREDICT 32
+#endif
+#ifndef KB_GROUP_PREDICT_BIG
+#define KB_GROUP_PREDICT_BIG 128
 #endif
 constexpr size_t GROUP_SMEM_PER_LANDMARK = 5 * sizeof(double) + sizeof(float4);   // base, coeff, last coord, k, d*, fp32 copy
 template <int G> struct Cfg {
@@ -56,18 +74,33 @@ template <int G> __device__ __forceinline__ void gsync(int group) {
 
 constexpr int MAX_CAND = 256;      // n_prbs + 1 <= 201
 constexpr int MAX_DIM = 16;
+constexpr int TILE = 32;                               // landmarks per tile row
+constexpr int TILE_ELEMS = TILE * TILE;                // doubles per K^-1 tile
+constexpr int ROW_HDR = TILE * MAX_DIM + TILE;         // doubles ahead of the tiles of a row: landmarks [32][16], coeff [32]
+constexpr int MAX_CAP = 2048;                          // landmarks per learner the staging in shared memory can hold
+constexpr int SMALL_CAP = 256;                         // staging capacity of the first (small-dictionary) update launch
+constexpr int SMALL_CAP_PREDICT = 128;                 // dictionaries up to this size are scanned by one warp each
+__host__ __device__ inline unsigned long long row_doubles(int I) { return (unsigned long long)ROW_HDR + (unsigned long long)(I + 1) * TILE_ELEMS; }
+
+constexpr int PEND_FRESH = -1, PEND_DONE = -2;         // State::pend: >= 0 = resume the augmentation loop at this allocation
 
 struct State {
-    int L, S, V, n_prbs, cap;
+    int L, S, V, n_prbs, cap, tmax;
     int exact_only;    // kb_set_exact: evaluate every f in fp64 like the reference (validation of the guarded fast path)
+    int plus;          // ProjectronPlus.update (projectron.py:66-107) instead of Projectron.update
     double gamma, eta;
     int dims[8], offs[8];
-    int *D;            // [L]
-    double *lm;        // [L][cap][MAX_DIM]
-    double *coeff;     // [L][cap]
-    double *kinv;      // [L][cap][cap] (exactly symmetric)
-    uint32_t *flags;   // [L]
-    unsigned long long *updates;   // [1]
+    int *D;                          // [L]
+    unsigned long long *rows;        // [L][tmax] pool offset (in doubles) of tile row I; rows (D + 31) / 32 .. are not allocated
+    double *pool;
+    unsigned long long pool_doubles;
+    unsigned long long *cursor;      // [1] bump allocator
+    uint32_t *flags;                 // [L]
+    unsigned long long *updates;     // [1]
+    int *pend;                       // [L] hand-over between the two update launches of a step (small / large dictionaries)
+    uint32_t *tie_ctr;               // [L] draws taken from the learner's tie-break stream
+    int *max_d;                      // [1] largest dictionary seen
+    uint32_t k0, k1, env0;           // tie-break stream: Philox key = seed, counter = (n, STREAM_KBRL, slice, env0 + env)
 };
 
 // Device-resident KBRL_Control state (kbrl_control.py:28-39); acc == nullptr while kb_control_init has not been called
@@ -96,15 +129,28 @@ __device__ __forceinline__ double base_dist(const double *l, const double *x, in
     return r;
 }
 
-// shared-memory slice of one group
-__device__ __forceinline__ void carve(unsigned char *raw, int cap, int group, double *&base, double *&cf, double *&ll, double *&kf,
-                                      double *&ds, float4 *&fast) {
-    double *p = reinterpret_cast<double *>(raw + (size_t)group * cap * GROUP_SMEM_PER_LANDMARK);
-    base = p; cf = base + cap; ll = cf + cap; kf = ll + cap; ds = kf + cap;
-    fast = reinterpret_cast<float4 *>(ds + cap);             // [cap] fp32 copy of the staged dictionary (guarded fast path)
+// shared-memory slice of one group: tile-row pointers of its learner, then the staged dictionary
+__device__ __forceinline__ void carve(unsigned char *raw, int capS, int tmax, int group, double **&rowp, double *&base, double *&cf,
+                                      double *&ll, double *&kf, double *&ds, float4 *&fast) {
+    unsigned char *p0 = raw + (size_t)group * ((size_t)tmax * sizeof(double *) + (size_t)capS * GROUP_SMEM_PER_LANDMARK);
+    rowp = reinterpret_cast<double **>(p0);
+    double *p = reinterpret_cast<double *>(p0 + (size_t)tmax * sizeof(double *));
+    base = p; cf = base + capS; ll = cf + capS; kf = ll + capS; ds = kf + capS;
+    fast = reinterpret_cast<float4 *>(ds + capS);            // [capS] fp32 copy of the staged dictionary (guarded fast path)
 }
 // per-group scalars
-struct GroupVars { double xs[MAX_DIM]; double delta, fa0; unsigned long long minb; int first, D, sf, pad; };
+struct GroupVars { double xs[MAX_DIM]; double delta, fa0; unsigned long long minb; int first, D, sf, ok; };
+
+__device__ __forceinline__ double *lm_ptr(double *const *rowp, int j) { return rowp[j >> 5] + (j & 31) * MAX_DIM; }
+__device__ __forceinline__ double *cf_ptr(double *const *rowp, int j) { return rowp[j >> 5] + TILE * MAX_DIM + (j & 31); }
+__device__ __forceinline__ double *tile_ptr(double *const *rowp, int I, int J) { return rowp[I] + ROW_HDR + (size_t)J * TILE_ELEMS; }
+
+// np.random.choice([-1, 1]) of GaussianKernel.predict (kernel.py:26-27) from the learner's Philox stream (philox.py: choice =
+// seq[integers(len(seq))], one counter tick)
+__device__ __forceinline__ int tie_draw(const State &kb, int env, int s, uint32_t n) {
+    rs::PhiloxStream r{kb.k0, kb.k1, (uint32_t)s, rs::STREAM_KBRL, n, kb.env0 + (uint32_t)env};
+    return r.integers(2u) ? 1 : -1;
+}
 
 // f(a) for candidate a with the dictionary staged in shared memory (kernel.py:13-25 incl. the D == 1 float32 stage)
 __device__ __forceinline__ double eval_f(int D, double gamma, const double *base, const double *cf, const double *ll, double xa) {
@@ -122,12 +168,13 @@ __device__ __forceinline__ double eval_f(int D, double gamma, const double *base
     return f;
 }
 
-// Guarded fp32 evaluation of f(a).  Only the SIGN of f is ever used (kernel.py:25, projectron.py:40), so f is first
-// summed in fp32 with ex2.approx together with G = sum |coeff_j| k_j; the fp32 result differs from the reference's
-// fp64 sum by less than (1e-5 + 1.2e-7 D) G  (|arg| <= 126 before a term flushes to zero: argument error <= 5e-7 +
-// 1.2e-7 |arg|, ex2.approx 2^-22, D sequential fp32 additions); the guard (4e-5 + 3e-7 D) G leaves a factor 2.5-4.  Inside that band -- a candidate sitting on the decision boundary -- f is re-evaluated
-// exactly like the reference (eval_f).  Dictionaries of 0 or 1 landmarks (the reference's float32 stage) go straight
-// to eval_f.
+// Guarded fp32 evaluation of f(a).  Only the SIGN of f is ever used by Projectron (kernel.py:25, projectron.py:40), so f
+// is first summed in fp32 with ex2.approx together with G = sum |coeff_j| k_j; the fp32 result differs from the
+// reference's fp64 sum by less than (1e-5 + 1.2e-7 D) G  (|arg| <= 126 before a term flushes to zero: argument error
+// <= 5e-7 + 1.2e-7 |arg|, ex2.approx 2^-22, D sequential fp32 additions); the guard (4e-5 + 3e-7 D) G leaves a factor
+// 2.5-4.  Inside that band -- a candidate sitting on the decision boundary, or f == 0 exactly (the tie-break) -- f is
+// re-evaluated exactly like the reference (eval_f).  Dictionaries of 0 or 1 landmarks (the reference's float32 stage)
+// go straight to eval_f.
 constexpr float LOG2E = 1.4426950408889634f;
 #ifdef KB_CHECK
 __device__ unsigned long long g_kb_dbg[4];   // [0] accepted fast results, [1] sign mismatches among them, [2] max |f32-f64|/G * 1e9, [3] guard hits
@@ -164,22 +211,22 @@ __device__ __forceinline__ double eval_f_guarded(int D, double gamma, const doub
     return eval_f(D, gamma, base, cf, ll, xa);
 }
 
-// Stages the dictionary of learner l for state xs: exact fp64 (base, coeff, last coordinate) and the fp32 copy of the
+// Stages the dictionary of a learner for state xs: exact fp64 (base, coeff, last coordinate) and the fp32 copy of the
 // fast path.  The fp32 exponents are taken RELATIVE to the closest landmark (min_j base_j): sign(f) does not change
 // when every term is scaled by exp(gamma min_j base_j), and without the shift a state far from all landmarks puts
 // every term below the fp32 normal range (measured: flushed terms flipped 140 of 1.1e9 decisions).
 // Group-wide; ends with the dictionary visible to all threads of the group (callers need no further barrier for it).
 // Returns whether the fp32 fast path may be used for this (dictionary, state).
 template <int GROUP>
-__device__ bool stage_dictionary(const State &kb, int l, int D, int d, GroupVars &g, int group, int gt, double *base, double *cf,
-                                 double *ll, float4 *fast) {
-    const double *lm = kb.lm + (size_t)l * kb.cap * MAX_DIM;
+__device__ bool stage_dictionary(const State &kb, double *const *rowp, int D, int d, GroupVars &g, int group, int gt, double *base,
+                                 double *cf, double *ll, float4 *fast) {
     const double g2 = kb.gamma * 1.4426950408889634;
     if (gt == 0) g.minb = ~0ull;
     gsync<GROUP>(group);
     for (int j = gt; j < D; j += GROUP) {
-        const double b = base_dist(lm + (size_t)j * MAX_DIM, g.xs, d - 1);
-        base[j] = b; cf[j] = kb.coeff[(size_t)l * kb.cap + j]; ll[j] = lm[(size_t)j * MAX_DIM + d - 1];
+        const double *lm = lm_ptr(rowp, j);
+        const double b = base_dist(lm, g.xs, d - 1);
+        base[j] = b; cf[j] = *cf_ptr(rowp, j); ll[j] = lm[d - 1];
         atomicMin(&g.minb, (unsigned long long)__double_as_longlong(b));       // b >= 0: the bit pattern orders like the value
     }
     gsync<GROUP>(group);
@@ -188,43 +235,140 @@ __device__ bool stage_dictionary(const State &kb, int l, int D, int d, GroupVars
         fast[j] = make_float4((float)(g2 * (base[j] - minb)), (float)cf[j], (float)ll[j], 0.f);
     gsync<GROUP>(group);
     // Past exp(-600) the reference's own fp64 terms run into the denormal range / underflow to 0 (f == 0 is a decision
-    // of its own): such far-away states are evaluated exactly.  Below it, every term that fp32 flushes after the shift
-    // (< 2^-126 of the scale) is equally negligible in fp64.
-    return kb.gamma * minb <= 600.0 && !kb.exact_only;
+    // of its own: the tie-break): such far-away states are evaluated exactly.  Below it, every term that fp32 flushes
+    // after the shift (< 2^-126 of the scale) is equally negligible in fp64.  ProjectronPlus needs the VALUE of f.
+    return kb.gamma * minb <= 600.0 && !kb.exact_only && !kb.plus;
+}
+
+// tile-row pointers of learner l into shared memory (rows 0 .. (D + 31) / 32 - 1 exist)
+template <int GROUP>
+__device__ __forceinline__ void load_rows(const State &kb, int l, int D, double **rowp, int gt) {
+    const int T = (D + TILE - 1) >> 5;
+    for (int I = gt; I < T; I += GROUP) rowp[I] = kb.pool + kb.rows[(size_t)l * kb.tmax + I];
 }
 
 // ---------------------------------------------------------------------------------------------
+// select_action scan (kbrl_control.py:54-61): first allocation whose prediction is +1.  big == 0: dictionaries of at most
+// capS landmarks; big == 1: the larger ones (one wider group per learner).  A candidate with f == 0 exactly draws its
+// prediction from the tie-break stream, in scan order.
 template <int GROUP>
-__global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const State kb, const float *__restrict__ state, int32_t *first_pos) {
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const State kb, const int capS, const int big,
+                                                                      const float *__restrict__ state, int32_t *first_pos) {
     extern __shared__ __align__(16) unsigned char raw[];
     constexpr int GROUPS = Cfg<GROUP>::GROUPS;
     __shared__ GroupVars gv[GROUPS];
     const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
     const int l = blockIdx.x * GROUPS + group;
     if (l >= kb.L) return;                                    // whole group
-    double *base, *cf, *ll, *kf, *ds;
+    const int D = kb.D[l];
+    if (big ? D <= SMALL_CAP_PREDICT : D > SMALL_CAP_PREDICT) return;     // the other launch scans this learner
+    double **rowp, *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, kb.cap, group, base, cf, ll, kf, ds, fast);
+    carve(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
     GroupVars &g = gv[group];
     const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
     if (gt < d - 1) g.xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
     if (gt == 0) g.first = 1 << 30;
+    load_rows<GROUP>(kb, l, D, rowp, gt);
     gsync<GROUP>(group);
-    const int D = kb.D[l];
-    const bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
-    int first = 1 << 30;
+    const bool fast_ok = stage_dictionary<GROUP>(kb, rowp, D, d, g, group, gt, base, cf, ll, fast);
+    int first = 1 << 30;                                      // key: a << 1 | (f > 0); ties (f == 0, D > 0) enter with bit 0 clear
     for (int a = gt; a <= kb.n_prbs; a += GROUP) {
         const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, nullptr);
-        if (f > 0.0) first = min(first, a);                   // prediction == +1 (kernel.py:25)
+        if (f > 0.0) first = min(first, (a << 1) | 1);        // prediction == +1 (kernel.py:25)
+        else if (f == 0.0 && D > 0) first = min(first, a << 1);
     }
     if (first != (1 << 30)) atomicMin(&g.first, first);
     gsync<GROUP>(group);
-    if (gt == 0) first_pos[l] = g.first == (1 << 30) ? -1 : g.first;
+    if (gt == 0) {
+        int key = g.first, res = -1;
+        if (key != (1 << 30)) {
+            if (key & 1) res = key >> 1;
+            else {                                            // a tie before the first +1: replay the scan from there in order
+                uint32_t tn = kb.tie_ctr[l];
+                for (int a = key >> 1; a <= kb.n_prbs; ++a) {
+                    const double f = eval_f(D, kb.gamma, base, cf, ll, (double)a / (double)kb.n_prbs);
+                    if (f > 0.0 || (f == 0.0 && tie_draw(kb, env, s, tn++) == 1)) { res = a; break; }
+                }
+                kb.tie_ctr[l] = tn;
+            }
+        }
+        first_pos[l] = res;
+    }
+}
+
+// d* = K^-1 k for the staged k (kf): thread i sums row i of the symmetric matrix in index order -- row i of the tiles
+// left of the diagonal, then column i of the diagonal tile and of the tiles below it (K^-1[i][j] == K^-1[j][i]).
+template <int GROUP>
+__device__ __forceinline__ void kinv_matvec(double *const *rowp, int D, const double *kf, double *ds, int gt) {
+    for (int i = gt; i < D; i += GROUP) {
+        const int I = i >> 5, r = i & 31;
+        double acc = 0.0;
+        const double *rowI = rowp[I] + ROW_HDR + r * TILE;
+        for (int J = 0; J < I; ++J) {
+            const double2 *p = reinterpret_cast<const double2 *>(rowI + (size_t)J * TILE_ELEMS);
+            const double *k = kf + J * TILE;
+#pragma unroll 4
+            for (int c = 0; c < TILE / 2; ++c) {
+                const double2 v = p[c];
+                acc += v.x * k[2 * c];
+                acc += v.y * k[2 * c + 1];
+            }
+        }
+        for (int J = I; J * TILE < D; ++J) {
+            const double *q = rowp[J] + ROW_HDR + (size_t)I * TILE_ELEMS + r;
+            const double *k = kf + J * TILE;
+            const int nj = min(TILE, D - J * TILE);
+#pragma unroll 4
+            for (int jr = 0; jr < nj; ++jr) acc += q[jr * TILE] * k[jr];
+        }
+        ds[i] = acc;
+    }
+}
+
+// K^-1 <- [[K^-1, 0], [0, 0]] + [d*; -1][d*; -1]^T / delta over the stored tiles (projectron.py:54-58); ds[D] == -1.
+// Row D and column D are new: their old value is 0 (never read).  Diagonal tiles update both triangles with the same
+// commutative products, so the matrix stays exactly symmetric.
+template <int GROUP>
+__device__ __forceinline__ void kinv_extend(double *const *rowp, int D, const double *ds, double delta, int gt) {
+    const int m = D + 1, Tn = (m + TILE - 1) >> 5;
+    for (int I = 0; I < Tn; ++I) {
+        const int ni = min(TILE, m - I * TILE);
+        for (int J = 0; J <= I; ++J) {
+            double *t = tile_ptr(rowp, I, J);
+            const int nj = min(TILE, m - J * TILE);
+            for (int e = gt; e < ni * TILE; e += GROUP) {
+                const int r = e >> 5, c = e & 31;
+                if (c >= nj) continue;
+                const int i = I * TILE + r, j = J * TILE + c;
+                const double add = ds[i] * ds[j] / delta;
+                const double old = (i == D || j == D) ? 0.0 : t[e];
+                t[e] = old + add;
+            }
+        }
+    }
+}
+
+// bump allocation of tile row I of learner l (thread 0 of the group); returns nullptr when the pool is exhausted
+__device__ __forceinline__ double *alloc_row(const State &kb, int l, int I) {
+    const unsigned long long need = row_doubles(I);
+    const unsigned long long off = atomicAdd(kb.cursor, need);
+    if (off + need > kb.pool_doubles) {
+        atomicAdd(kb.cursor, 0ull - need);
+        return nullptr;
+    }
+    kb.rows[(size_t)l * kb.tmax + I] = off;
+    return kb.pool + off;
 }
 
 // ---------------------------------------------------------------------------------------------
+// Projectron part of update_control (+ the E-learner when ctl.acc != nullptr).  Two launches per step: stage 0 stages at
+// most capS = SMALL_CAP landmarks (14 KB of shared memory, four learners per SM... per 256 threads) and hands a learner
+// whose dictionary reaches that size to stage 1 (capS = cap), which starts it (pend == PEND_FRESH) or resumes its
+// augmentation loop at allocation `pend`.
 template <int GROUP>
-__global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) update_kernel(const State kb, const float *__restrict__ state,
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) update_kernel(const State kb, const int capS, const int stage,
+                                                         const float *__restrict__ state,
                                                          const int32_t *__restrict__ action,
                                                          const int32_t *__restrict__ labels, int32_t *y_pred,
                                                          const Control ctl, int32_t *hits) {
@@ -234,46 +378,55 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
     const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
     const int l = blockIdx.x * GROUPS + group;
     if (l >= kb.L) return;                                    // whole group
-    double *base, *cf, *ll, *kf, *ds;
+    const int pend = kb.pend[l];                              // stage 0: PEND_FRESH for every learner (set by the host)
+    if (stage && pend == PEND_DONE) return;
+    int D = kb.D[l];
+    if (!stage && D >= capS) return;                          // large dictionary: stage 1 takes it (pend stays PEND_FRESH)
+    double **rowp, *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, kb.cap, group, base, cf, ll, kf, ds, fast);
+    carve(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
     GroupVars &g = gv[group];
     double *xs = g.xs;
-    const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs, cap = kb.cap;
+    const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs;
     if (gt < d - 1) xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
     const int y = labels[l];
     const int a0 = min(max(action[l], 0), n);
     const int lo = y == 1 ? a0 : 0, hi = y == 1 ? n : a0;     // kbrl_control.py:103-112
-    double *lm = kb.lm + (size_t)l * cap * MAX_DIM;
-    double *coeff = kb.coeff + (size_t)l * cap;
-    double *kinv = kb.kinv + (size_t)l * cap * cap;
-    int D = kb.D[l];
-    int cur = lo;
-    bool first_round = true;
+    int cur = pend >= 0 ? pend : lo;
+    bool first_round = pend < 0;
     unsigned n_updates = 0;
+    uint32_t tie_n = kb.tie_ctr[l];
+    load_rows<GROUP>(kb, l, D, rowp, gt);
     gsync<GROUP>(group);
     // The dictionary is staged from HBM once; a round's update is mirrored into the staged copy (the state part of
     // a new landmark equals the current state exactly, so its base distance is 0 and becomes the new minimum).
-    bool fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);
+    bool fast_ok = stage_dictionary<GROUP>(kb, rowp, D, d, g, group, gt, base, cf, ll, fast);
     const double g2 = kb.gamma * 1.4426950408889634;
     // E-learner inputs, loaded early so that their latency hides behind the first evaluation round
     const int ctl_margin = ctl.acc ? max(0, ctl.margins[l]) : 0;
     const int ctl_adjusted = ctl.acc ? ctl.adjusted[env] : 0;
     double acc_v = 0.0;
     if (ctl.acc && gt < n) acc_v = ctl.acc[(size_t)l * n + gt];
+    int handed_over = -1;
     while (cur <= hi) {
         if (gt == 0) g.first = 1 << 30;
         gsync<GROUP>(group);
-        int first = 1 << 30;
+        int first = 1 << 30;                                   // key: a << 1 | (f != 0)
         for (int a = cur + gt; a <= hi; a += GROUP) {
             const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)n, nullptr);
             if (first_round && a == a0) g.fa0 = f;
-            if (f * (double)y <= 0.0) first = min(first, a);   // Projectron.update acts only on mistakes (projectron.py:40)
+            // Projectron.update acts on mistakes (f y <= 0, projectron.py:40); ProjectronPlus also inside the margin (:70-72)
+            const bool act = kb.plus ? f * (double)y < 1.0 : f * (double)y <= 0.0;
+            if (act) first = min(first, (a << 1) | (f != 0.0));
         }
         if (first != (1 << 30)) atomicMin(&g.first, first);
         gsync<GROUP>(group);
         if (first_round) {                                     // the predict of kbrl_control.py:89 (before any update)
-            const int yp = D == 0 ? 0 : (g.fa0 > 0.0 ? 1 : -1);
+            int yp = 0;
+            if (D > 0) {
+                yp = g.fa0 > 0.0 ? 1 : -1;
+                if (g.fa0 == 0.0) yp = tie_draw(kb, env, s, tie_n++);      // kernel.py:26-27 (every thread: same draw)
+            }
             if (gt == 0 && y_pred) y_pred[l] = yp;
             first_round = false;
             if (ctl.acc) {                                     // E-learner part of update_control (kbrl_control.py:90-101)
@@ -298,88 +451,151 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
                 }
             }
         }
-        const int astar = g.first;
-        if (astar == (1 << 30)) break;
-        // ---- Projectron.update at x = [s, astar / n] (projectron.py:41-60)
+        const int key = g.first;
+        if (key == (1 << 30)) break;
+        const int astar = key >> 1;
+        if (!stage && D >= capS) { handed_over = astar; break; }   // staging is full: stage 1 resumes at astar
+        // ---- Projectron.update at x = [s, astar / n] (projectron.py:41-60); its predict drew a tie-break if f == 0
         const double xa = (double)astar / (double)n;
         ++n_updates;
+        if (D > 0 && !(key & 1)) ++tie_n;
         if (D <= 1) {                                          // float32 stage: Kinv, K_f, coeff are float32 arrays of length 1
             if (gt == 0) {
-                float kfv = 0.f, ki = 0.f;
-                if (D == 1) { const double t = ll[0] - xa; kfv = (float)exp(-kb.gamma * (base[0] + t * t)); ki = (float)kinv[0]; }
+                float kfv = 0.f, ki = 0.f, f32 = 0.f;
+                if (D == 1) {
+                    const double t = ll[0] - xa;
+                    kfv = (float)exp(-kb.gamma * (base[0] + t * t)); ki = (float)tile_ptr(rowp, 0, 0)[0];
+                    f32 = kfv * (float)cf[0];
+                }
                 const float dsv = ki * kfv;
                 const double dot = (double)(float)(dsv * kfv);
                 double delta = 1.0 - dot;
                 if (delta < 0.0) delta = 0.0;
-                if (delta <= kb.eta) coeff[0] = (double)(float)((float)coeff[0] + (float)y * dsv);
-                else {
-                    for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
-                    lm[(size_t)D * MAX_DIM + d - 1] = xa;
-                    coeff[D] = (double)y;
-                    if (D == 0) kinv[0] = (double)(float)(1.0 / 1.0);
-                    else {
-                        const double dse[2] = {(double)dsv, -1.0};
-                        kinv[1] = 0.0; kinv[cap] = 0.0; kinv[cap + 1] = 0.0;
-                        for (int i = 0; i < 2; ++i)
-                            for (int j = 0; j < 2; ++j) kinv[(size_t)i * cap + j] += dse[i] * dse[j] / delta;
+                const double margin = (double)y * (double)f32;                 // y * self.f (np.int64 * np.float32 -> float64)
+                int newD = D;
+                if (kb.plus && margin > 0.0) {                                 // ProjectronPlus inside the margin (:72-84); never reached with D == 0 (f = 0)
+                    const double loss = 1.0 - margin;
+                    double norm_xt = 1.0 - delta;
+                    if (norm_xt < 0.0) norm_xt = 0.0;
+                    if (loss - delta / kb.eta > 0.0) {
+                        const double alpha = fmin(fmin(loss / norm_xt, 1.0), 2.0 * (loss - delta / kb.eta) / norm_xt);
+                        // coeff (float32[1]) += alpha * y * d_star: the product is float64 (numpy scalars are not weak), the in-place add rounds to float32
+                        *cf_ptr(rowp, 0) = (double)(float)(cf[0] + (alpha * (double)y) * (double)dsv);
                     }
-                    g.D = D + 1;
+                } else if (delta <= kb.eta) *cf_ptr(rowp, 0) = (double)(float)((float)cf[0] + (float)y * dsv);
+                else {
+                    double *row0 = D == 0 ? alloc_row(kb, l, 0) : rowp[0];
+                    if (!row0) atomicOr(&kb.flags[l], (uint32_t)KB_FLAG_POOL);
+                    else {
+                        rowp[0] = row0;
+                        double *lmn = lm_ptr(rowp, D);
+                        for (int i = 0; i < d - 1; ++i) lmn[i] = xs[i];
+                        lmn[d - 1] = xa;
+                        *cf_ptr(rowp, D) = (double)y;
+                        double *t00 = tile_ptr(rowp, 0, 0);
+                        if (D == 0) t00[0] = (double)(float)(1.0 / 1.0);
+                        else {
+                            const double dse[2] = {(double)dsv, -1.0};
+                            t00[1] = 0.0; t00[TILE] = 0.0; t00[TILE + 1] = 0.0;
+                            for (int i = 0; i < 2; ++i)
+                                for (int j = 0; j < 2; ++j) t00[i * TILE + j] += dse[i] * dse[j] / delta;
+                        }
+                        newD = D + 1;
+                    }
                 }
-                if (delta <= kb.eta) g.D = D;
+                g.D = newD;
             }
             gsync<GROUP>(group);
             D = g.D;
-            fast_ok = stage_dictionary<GROUP>(kb, l, D, d, g, group, gt, base, cf, ll, fast);   // float32 stage: tiny, re-staged
+            fast_ok = stage_dictionary<GROUP>(kb, rowp, D, d, g, group, gt, base, cf, ll, fast);   // float32 stage: tiny, re-staged
         } else {
             for (int j = gt; j < D; j += GROUP) { const double t = ll[j] - xa; kf[j] = exp(-kb.gamma * (base[j] + t * t)); }
             gsync<GROUP>(group);
-            for (int i = gt; i < D; i += GROUP) {      // d* = K^-1 k; column i == row i (symmetric), coalesced
-                double acc = 0.0;
-                for (int j = 0; j < D; ++j) acc += kinv[(size_t)j * cap + i] * kf[j];
-                ds[i] = acc;
-            }
+            kinv_matvec<GROUP>(rowp, D, kf, ds, gt);
             gsync<GROUP>(group);
-            if (gt == 0) {                                   // delta = max(Kii - d* . k, 0), index order
+            if (gt == 0) {                                   // delta = max(Kii - d* . k, 0), index order; f for ProjectronPlus
                 double dot = 0.0;
                 for (int i = 0; i < D; ++i) dot += ds[i] * kf[i];
                 double delta = 1.0 - dot;
                 g.delta = delta < 0.0 ? 0.0 : delta;
+                g.ok = 1;
+                if (kb.plus) {
+                    double f = 0.0;
+                    for (int j = 0; j < D; ++j) f += kf[j] * cf[j];
+                    g.fa0 = f;                                // (fa0 is free after the first round)
+                }
             }
             gsync<GROUP>(group);
             const double delta = g.delta;
-            if (delta <= kb.eta) {                                    // sv.update(y * d_star)
+            const double margin = kb.plus ? (double)y * g.fa0 : 0.0;
+            if (kb.plus && margin > 0.0) {                            // ProjectronPlus inside the margin (projectron.py:72-84)
+                const double loss = 1.0 - margin;
+                double norm_xt = 1.0 - delta;
+                if (norm_xt < 0.0) norm_xt = 0.0;
+                if (loss - delta / kb.eta > 0.0) {
+                    const double alpha = fmin(fmin(loss / norm_xt, 1.0), 2.0 * (loss - delta / kb.eta) / norm_xt);
+                    const double ay = alpha * (double)y;
+                    for (int i = gt; i < D; i += GROUP) {
+                        const double c = cf[i] + ay * ds[i];
+                        *cf_ptr(rowp, i) = c; cf[i] = c; fast[i].y = (float)c;
+                    }
+                }
+            } else if (delta <= kb.eta) {                             // sv.update(y * d_star)
                 for (int i = gt; i < D; i += GROUP) {
-                    const double c = coeff[i] + (double)y * ds[i];
-                    coeff[i] = c; cf[i] = c; fast[i].y = (float)c;
+                    const double c = cf[i] + (double)y * ds[i];
+                    *cf_ptr(rowp, i) = c; cf[i] = c; fast[i].y = (float)c;
                 }
-            } else if (D < cap) {                                     // sv.extend / insert + rank-1 extension of K^-1
-                if (gt == 0) {
-                    for (int i = 0; i < d - 1; ++i) lm[(size_t)D * MAX_DIM + i] = xs[i];
-                    lm[(size_t)D * MAX_DIM + d - 1] = xa;
-                    coeff[D] = (double)y;
-                    ds[D] = -1.0;
-                    base[D] = 0.0; cf[D] = (double)y; ll[D] = xa;          // staged copy of the new landmark
+            } else if (D < kb.cap) {                                  // sv.extend / insert + rank-1 extension of K^-1
+                if ((D & (TILE - 1)) == 0) {                          // the new landmark opens a tile row
+                    if (gt == 0) {
+                        double *row = alloc_row(kb, l, D >> 5);
+                        if (row) rowp[D >> 5] = row; else { g.ok = 0; atomicOr(&kb.flags[l], (uint32_t)KB_FLAG_POOL); }
+                    }
+                    gsync<GROUP>(group);
                 }
-                for (int i = gt; i <= D; i += GROUP) { kinv[(size_t)i * cap + D] = 0.0; kinv[(size_t)D * cap + i] = 0.0; }
-                gsync<GROUP>(group);
-                const int m = D + 1;
-                for (int idx = gt; idx < m * m; idx += GROUP) {
-                    const int i = idx / m, j = idx - i * m;
-                    kinv[(size_t)i * cap + j] += ds[i] * ds[j] / delta;
+                if (g.ok) {
+                    if (gt == 0) {
+                        double *lmn = lm_ptr(rowp, D);
+                        for (int i = 0; i < d - 1; ++i) lmn[i] = xs[i];
+                        lmn[d - 1] = xa;
+                        *cf_ptr(rowp, D) = (double)y;
+                        ds[D] = -1.0;
+                        base[D] = 0.0; cf[D] = (double)y; ll[D] = xa;          // staged copy of the new landmark
+                    }
+                    gsync<GROUP>(group);
+                    kinv_extend<GROUP>(rowp, D, ds, delta, gt);
+                    D += 1;
+                    for (int j = gt; j < D; j += GROUP)                      // fp32 copy relative to the new minimum (0)
+                        fast[j] = make_float4((float)(g2 * base[j]), (float)cf[j], (float)ll[j], 0.f);
+                    fast_ok = !kb.exact_only && !kb.plus;
                 }
-                D = m;
-                for (int j = gt; j < D; j += GROUP)                      // fp32 copy relative to the new minimum (0)
-                    fast[j] = make_float4((float)(g2 * base[j]), (float)cf[j], (float)ll[j], 0.f);
-                fast_ok = !kb.exact_only;
-            } else if (gt == 0) kb.flags[l] |= KB_FLAG_DICT_CAP;
+            } else if (gt == 0) atomicOr(&kb.flags[l], (uint32_t)KB_FLAG_DICT_CAP);
             gsync<GROUP>(group);
         }
         cur = astar + 1;
     }
     if (gt == 0) {
         kb.D[l] = D;
+        kb.tie_ctr[l] = tie_n;
+        kb.pend[l] = handed_over >= 0 ? handed_over : PEND_DONE;
         if (n_updates) atomicAdd(kb.updates, (unsigned long long)n_updates);
+        if (D > *kb.max_d) atomicMax(kb.max_d, D);
     }
+}
+
+// dense copy of one learner's dictionary (kb_get_learner): landmarks [D][MAX_DIM], coeff [D], kinv [D][D]
+__global__ void gather_kernel(const State kb, int l, double *lm, double *coeff, double *kinv) {
+    const int D = kb.D[l], tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    const unsigned long long *rows = kb.rows + (size_t)l * kb.tmax;
+    for (int idx = tid; idx < D * D; idx += nt) {
+        const int a = idx / D, b = idx - a * D, i = max(a, b), j = min(a, b);
+        kinv[idx] = kb.pool[rows[i >> 5] + ROW_HDR + (size_t)(j >> 5) * TILE_ELEMS + (i & 31) * TILE + (j & 31)];
+    }
+    for (int idx = tid; idx < D * MAX_DIM; idx += nt) {
+        const int q = idx / MAX_DIM;
+        lm[idx] = kb.pool[rows[q >> 5] + (q & 31) * MAX_DIM + (idx - q * MAX_DIM)];
+    }
+    for (int idx = tid; idx < D; idx += nt) coeff[idx] = kb.pool[rows[idx >> 5] + TILE * MAX_DIM + (idx & 31)];
 }
 
 // Tail of KBRL_Control.select_action (kbrl_control.py:57-73) + adjust_action (:75-78); one thread per env.
@@ -417,17 +633,20 @@ struct kb_handle {
     kb_config cfg;
     kb::State st;
     kb::Control ctl;
-    size_t smem_update, smem_predict;
+    int cap_small;                           // staging capacity of the small-dictionary update launch
+    size_t smem_update_small, smem_update_big, smem_predict_small, smem_predict_big;
     cudaStream_t stream;
     float *d_state;
     int32_t *d_action, *d_labels, *d_out;
+    double *d_gather;                        // kb_get_learner scratch (grown on demand)
+    size_t gather_doubles;
     uint64_t launches;
 };
 
 // error text is shared with ranslice_cabi.cu through rs_set_error
 extern "C" void rs_set_error(const char *msg);
 namespace {
-constexpr int UG = kb::Cfg<KB_GROUP_UPDATE>::GROUPS, PG = kb::Cfg<KB_GROUP_PREDICT>::GROUPS;
+constexpr int UG = kb::Cfg<KB_GROUP_UPDATE>::GROUPS, PG = kb::Cfg<KB_GROUP_PREDICT>::GROUPS, PGB = kb::Cfg<KB_GROUP_PREDICT_BIG>::GROUPS;
 int kfail(int code, const std::string &m) { rs_set_error(m.c_str()); return code; }
 }
 #define KCU(call)                                                                                  \
@@ -436,6 +655,53 @@ int kfail(int code, const std::string &m) { rs_set_error(m.c_str()); return code
         if (e_ != cudaSuccess) return kfail(RS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+static int kb_create_impl(kb_handle *h, const kb_config *cfg, const int32_t *dims, const int32_t *offsets) {
+    const int cap = h->cfg.dict_cap;
+    kb::State &st = h->st;
+    st.L = cfg->n_envs * cfg->n_slices; st.S = cfg->n_slices; st.V = cfg->n_variables; st.n_prbs = cfg->n_prbs;
+    st.cap = cap; st.tmax = cap / kb::TILE;
+    st.gamma = cfg->gamma; st.eta = cfg->eta; st.exact_only = 0; st.plus = cfg->algorithm == 1;
+    st.k0 = (uint32_t)cfg->tie_seed; st.k1 = (uint32_t)(cfg->tie_seed >> 32); st.env0 = (uint32_t)cfg->first_env_id;
+    for (int s = 0; s < 8; ++s) { st.dims[s] = s < cfg->n_slices ? dims[s] : 0; st.offs[s] = s < cfg->n_slices ? offsets[s] : 0; }
+    const size_t L = (size_t)st.L;
+    KCU(cudaMalloc(&st.D, L * sizeof(int)));
+    KCU(cudaMalloc(&st.rows, L * st.tmax * sizeof(unsigned long long)));
+    KCU(cudaMalloc(&st.flags, L * sizeof(uint32_t)));
+    KCU(cudaMalloc(&st.pend, L * sizeof(int)));
+    KCU(cudaMalloc(&st.tie_ctr, L * sizeof(uint32_t)));
+    KCU(cudaMalloc(&st.updates, sizeof(unsigned long long)));
+    KCU(cudaMalloc(&st.cursor, sizeof(unsigned long long)));
+    KCU(cudaMalloc(&st.max_d, sizeof(int)));
+    {   // dictionary pool: what every learner would need at full size, capped by pool_mb or (by default) 70 % of the free memory
+        unsigned long long full = 0;
+        for (int I = 0; I < st.tmax; ++I) full += kb::row_doubles(I);
+        full *= L;
+        size_t free_b = 0, total_b = 0;
+        KCU(cudaMemGetInfo(&free_b, &total_b));
+        unsigned long long want = cfg->pool_mb > 0 ? (unsigned long long)cfg->pool_mb * (1ull << 20) / sizeof(double)
+                                                   : std::min<unsigned long long>(full, (unsigned long long)(0.7 * (double)free_b) / sizeof(double));
+        want = std::max<unsigned long long>(std::min(want, full), kb::row_doubles(0));
+        cudaError_t e = cudaMalloc(&st.pool, want * sizeof(double));
+        if (e != cudaSuccess) return kfail(RS_E_NOMEM, "dictionary pool of " + std::to_string(want * sizeof(double) >> 20) + " MB: " + cudaGetErrorString(e));
+        st.pool_doubles = want;
+    }
+    KCU(cudaMalloc(&h->d_state, (size_t)cfg->n_envs * cfg->n_variables * sizeof(float)));
+    KCU(cudaMalloc(&h->d_action, L * sizeof(int32_t)));
+    KCU(cudaMalloc(&h->d_labels, L * sizeof(int32_t)));
+    KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
+    KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->cap_small = std::min(cap, kb::SMALL_CAP);
+    const size_t rowp = (size_t)st.tmax * sizeof(double *);
+    h->smem_update_small = (size_t)UG * (rowp + (size_t)h->cap_small * kb::GROUP_SMEM_PER_LANDMARK);
+    h->smem_update_big = (size_t)UG * (rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK);
+    h->smem_predict_small = (size_t)PG * (rowp + (size_t)std::min(cap, kb::SMALL_CAP_PREDICT) * kb::GROUP_SMEM_PER_LANDMARK);
+    h->smem_predict_big = (size_t)PGB * (rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK);
+    KCU(cudaFuncSetAttribute(kb::update_kernel<KB_GROUP_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update_big));
+    KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_small));
+    KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_big));
+    return kb_reset(h);
+}
+
 extern "C" {
 
 int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets, kb_handle **out) {
@@ -443,8 +709,11 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     if (cfg->abi_version != RS_ABI_VERSION) return kfail(RS_E_ARG, "abi_version mismatch");
     if (cfg->n_envs <= 0 || cfg->n_slices <= 0 || cfg->n_slices > 8 || cfg->n_prbs <= 0 || cfg->n_prbs + 1 > kb::MAX_CAND)
         return kfail(RS_E_ARG, "bad n_envs / n_slices / n_prbs");
-    const int cap = cfg->dict_cap ? cfg->dict_cap : 256;
-    if (cap < 2 || cap > 1024) return kfail(RS_E_ARG, "dict_cap must be in [2, 1024]");
+    if (cfg->algorithm != 0 && cfg->algorithm != 1) return kfail(RS_E_ARG, "algorithm must be 0 (Projectron) or 1 (ProjectronPlus)");
+    if (cfg->pool_mb < 0) return kfail(RS_E_ARG, "pool_mb must be >= 0");
+    int cap = cfg->dict_cap ? cfg->dict_cap : 1024;
+    if (cap < 2 || cap > kb::MAX_CAP) return kfail(RS_E_ARG, "dict_cap must be in [2, 2048]");
+    cap = (cap + kb::TILE - 1) / kb::TILE * kb::TILE;                      // whole tile rows
     for (int s = 0; s < cfg->n_slices; ++s) {
         // separable distance needs the action coordinate to be added last by numpy's pairwise sum: len(x) != 8, < 16
         if (dims[s] < 2 || dims[s] == 8 || dims[s] >= kb::MAX_DIM) return kfail(RS_E_ARG, "unsupported x dimension (need 2..15, != 8)");
@@ -457,36 +726,23 @@ int kb_create(const kb_config *cfg, const int32_t *dims, const int32_t *offsets,
     kb_handle *h = new kb_handle();
     h->cfg = *cfg; h->cfg.dict_cap = cap; h->launches = 0;
     h->ctl = kb::Control{};
-    kb::State &st = h->st;
-    st.L = cfg->n_envs * cfg->n_slices; st.S = cfg->n_slices; st.V = cfg->n_variables; st.n_prbs = cfg->n_prbs; st.cap = cap;
-    st.gamma = cfg->gamma; st.eta = cfg->eta; st.exact_only = 0;
-    for (int s = 0; s < 8; ++s) { st.dims[s] = s < cfg->n_slices ? dims[s] : 0; st.offs[s] = s < cfg->n_slices ? offsets[s] : 0; }
-    const size_t L = (size_t)st.L;
-    KCU(cudaMalloc(&st.D, L * sizeof(int)));
-    KCU(cudaMalloc(&st.lm, L * cap * kb::MAX_DIM * sizeof(double)));
-    KCU(cudaMalloc(&st.coeff, L * cap * sizeof(double)));
-    KCU(cudaMalloc(&st.kinv, L * cap * cap * sizeof(double)));
-    KCU(cudaMalloc(&st.flags, L * sizeof(uint32_t)));
-    KCU(cudaMalloc(&st.updates, sizeof(unsigned long long)));
-    KCU(cudaMalloc(&h->d_state, (size_t)cfg->n_envs * cfg->n_variables * sizeof(float)));
-    KCU(cudaMalloc(&h->d_action, L * sizeof(int32_t)));
-    KCU(cudaMalloc(&h->d_labels, L * sizeof(int32_t)));
-    KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
-    KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    h->smem_update = (size_t)kb::Cfg<KB_GROUP_UPDATE>::GROUPS * cap * kb::GROUP_SMEM_PER_LANDMARK;
-    h->smem_predict = (size_t)kb::Cfg<KB_GROUP_PREDICT>::GROUPS * cap * kb::GROUP_SMEM_PER_LANDMARK;
-    KCU(cudaFuncSetAttribute(kb::update_kernel<KB_GROUP_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update));
-    KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict));
+    h->st = kb::State{};
+    const int rc = kb_create_impl(h, cfg, dims, offsets);
+    if (rc != RS_OK) { kb_destroy(h); return rc; }                         // frees whatever had been allocated
     *out = h;
-    return kb_reset(h);
+    return RS_OK;
 }
 
 int kb_reset(kb_handle *h) {
     if (!h) return kfail(RS_E_ARG, "null handle");
     KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
     KCU(cudaMemset(h->st.D, 0, (size_t)h->st.L * sizeof(int)));
     KCU(cudaMemset(h->st.flags, 0, (size_t)h->st.L * sizeof(uint32_t)));
+    KCU(cudaMemset(h->st.tie_ctr, 0, (size_t)h->st.L * sizeof(uint32_t)));
     KCU(cudaMemset(h->st.updates, 0, sizeof(unsigned long long)));
+    KCU(cudaMemset(h->st.cursor, 0, sizeof(unsigned long long)));          // the whole pool is free again
+    KCU(cudaMemset(h->st.max_d, 0, sizeof(int)));
     return RS_OK;
 }
 
@@ -494,12 +750,41 @@ int kb_destroy(kb_handle *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(h->st.D); cudaFree(h->st.lm); cudaFree(h->st.coeff); cudaFree(h->st.kinv); cudaFree(h->st.flags);
+    cudaFree(h->st.D); cudaFree(h->st.rows); cudaFree(h->st.pool); cudaFree(h->st.flags); cudaFree(h->st.pend); cudaFree(h->st.tie_ctr);
+    cudaFree(h->st.cursor); cudaFree(h->st.max_d);
     cudaFree(h->ctl.acc); cudaFree(h->ctl.sec); cudaFree(h->ctl.margins); cudaFree(h->ctl.adjusted); cudaFree(h->ctl.action);
     cudaFree(h->ctl.first);
-    cudaFree(h->st.updates); cudaFree(h->d_state); cudaFree(h->d_action); cudaFree(h->d_labels); cudaFree(h->d_out);
+    cudaFree(h->st.updates); cudaFree(h->d_state); cudaFree(h->d_action); cudaFree(h->d_labels); cudaFree(h->d_out); cudaFree(h->d_gather);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return RS_OK;
+}
+
+// the two launches of an update step: dictionaries below cap_small with a small staging area, then the rest
+static int launch_update(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels, int32_t *d_y_pred,
+                         const kb::Control &ctl, int32_t *d_hits, cudaStream_t st) {
+    KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
+    KCU(cudaMemsetAsync(h->st.pend, 0xFF, (size_t)h->st.L * sizeof(int), st));            // PEND_FRESH
+    const int blocks = (h->st.L + UG - 1) / UG, threads = kb::Cfg<KB_GROUP_UPDATE>::THREADS;
+    kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, 0, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+    h->launches += 1;
+    if (h->st.cap > h->cap_small) {
+        kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_big, st>>>(h->st, h->st.cap, 1, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+        h->launches += 1;
+    }
+    KCU(cudaGetLastError());
+    return RS_OK;
+}
+
+static int launch_predict(kb_handle *h, const float *d_state, int32_t *d_first, cudaStream_t st) {
+    const int cs = std::min(h->st.cap, kb::SMALL_CAP_PREDICT);
+    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict_small, st>>>(h->st, cs, 0, d_state, d_first);
+    h->launches += 1;
+    if (h->st.cap > cs) {
+        kb::predict_kernel<KB_GROUP_PREDICT_BIG><<<(h->st.L + PGB - 1) / PGB, kb::Cfg<KB_GROUP_PREDICT_BIG>::THREADS, h->smem_predict_big, st>>>(h->st, h->st.cap, 1, d_state, d_first);
+        h->launches += 1;
+    }
+    KCU(cudaGetLastError());
     return RS_OK;
 }
 
@@ -507,12 +792,7 @@ int kb_update_device(kb_handle *h, const float *d_state, const int32_t *d_action
                      int32_t *d_y_pred, void *stream) {
     if (!h || !d_state || !d_action || !d_labels || !d_y_pred) return kfail(RS_E_ARG, "null argument");
     KCU(cudaSetDevice(h->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    kb::update_kernel<KB_GROUP_UPDATE><<<(h->st.L + UG - 1) / UG, kb::Cfg<KB_GROUP_UPDATE>::THREADS, h->smem_update, st>>>(h->st, d_state, d_action, d_labels, d_y_pred, kb::Control{}, nullptr);
-    h->launches += 1;
-    KCU(cudaGetLastError());
-    return RS_OK;
+    return launch_update(h, d_state, d_action, d_labels, d_y_pred, kb::Control{}, nullptr, (cudaStream_t)stream);
 }
 
 int kb_control_init(kb_handle *h, const int32_t *initial_action, const int32_t *security_factor, double alfa,
@@ -544,12 +824,7 @@ int kb_control_update_device(kb_handle *h, const float *d_state, const int32_t *
     if (!h || !d_state || !d_action || !d_labels) return kfail(RS_E_ARG, "null argument");
     if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
     KCU(cudaSetDevice(h->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    kb::update_kernel<KB_GROUP_UPDATE><<<(h->st.L + UG - 1) / UG, kb::Cfg<KB_GROUP_UPDATE>::THREADS, h->smem_update, st>>>(h->st, d_state, d_action, d_labels, nullptr, h->ctl, d_hits);
-    h->launches += 1;
-    KCU(cudaGetLastError());
-    return RS_OK;
+    return launch_update(h, d_state, d_action, d_labels, nullptr, h->ctl, d_hits, (cudaStream_t)stream);
 }
 
 int kb_control_select_device(kb_handle *h, const float *d_state, int32_t *d_action, int32_t *d_adjusted, void *stream) {
@@ -557,9 +832,10 @@ int kb_control_select_device(kb_handle *h, const float *d_state, int32_t *d_acti
     if (!h->ctl.acc) return kfail(RS_E_ARG, "kb_control_init has not been called");
     KCU(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict, st>>>(h->st, d_state, h->ctl.first);
+    const int rc = launch_predict(h, d_state, h->ctl.first, st);
+    if (rc) return rc;
     kb::select_kernel<<<(h->cfg.n_envs + 127) / 128, 128, 0, st>>>(h->st, h->ctl, d_action, d_adjusted);
-    h->launches += 2;
+    h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
 }
@@ -582,10 +858,7 @@ int kb_control_get(kb_handle *h, int32_t *action, int32_t *security_factors, int
 int kb_predict_device(kb_handle *h, const float *d_state, int32_t *d_first_pos, void *stream) {
     if (!h || !d_state || !d_first_pos) return kfail(RS_E_ARG, "null argument");
     KCU(cudaSetDevice(h->cfg.device));
-    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict, (cudaStream_t)stream>>>(h->st, d_state, d_first_pos);
-    h->launches += 1;
-    KCU(cudaGetLastError());
-    return RS_OK;
+    return launch_predict(h, d_state, d_first_pos, (cudaStream_t)stream);
 }
 
 int kb_update(kb_handle *h, const float *state, const int32_t *action, const int32_t *labels, int32_t *y_pred) {
@@ -623,22 +896,53 @@ int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags) {
     return RS_OK;
 }
 
+int kb_get_pool(kb_handle *h, uint64_t *used_bytes, uint64_t *total_bytes, int32_t *max_dictionary, uint64_t *tie_breaks) {
+    if (!h) return kfail(RS_E_ARG, "null handle");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    unsigned long long cur = 0;
+    int md = 0;
+    KCU(cudaMemcpy(&cur, h->st.cursor, sizeof cur, cudaMemcpyDeviceToHost));
+    KCU(cudaMemcpy(&md, h->st.max_d, sizeof md, cudaMemcpyDeviceToHost));
+    if (used_bytes) *used_bytes = cur * sizeof(double);
+    if (total_bytes) *total_bytes = h->st.pool_doubles * sizeof(double);
+    if (max_dictionary) *max_dictionary = md;
+    if (tie_breaks) {
+        std::vector<uint32_t> t((size_t)h->st.L);
+        KCU(cudaMemcpy(t.data(), h->st.tie_ctr, t.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        uint64_t sum = 0;
+        for (uint32_t v : t) sum += v;
+        *tie_breaks = sum;
+    }
+    return RS_OK;
+}
+
 int kb_get_learner(kb_handle *h, int32_t l, double *landmarks, double *coeff, double *kinv, int32_t *D_out) {
     if (!h || l < 0 || l >= h->st.L) return kfail(RS_E_ARG, "bad handle / learner");
     KCU(cudaSetDevice(h->cfg.device));
     KCU(cudaDeviceSynchronize());
     int D = 0;
     KCU(cudaMemcpy(&D, h->st.D + l, sizeof(int), cudaMemcpyDeviceToHost));
-    const int cap = h->st.cap, d = h->st.dims[l % h->st.S];
-    if (landmarks && D) {
-        std::vector<double> tmp((size_t)D * kb::MAX_DIM);
-        KCU(cudaMemcpy(tmp.data(), h->st.lm + (size_t)l * cap * kb::MAX_DIM, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < D; ++i) for (int j = 0; j < d; ++j) landmarks[(size_t)i * d + j] = tmp[(size_t)i * kb::MAX_DIM + j];
+    const int d = h->st.dims[l % h->st.S];
+    if (D && (landmarks || coeff || kinv)) {
+        const size_t need = (size_t)D * D + (size_t)D * kb::MAX_DIM + (size_t)D;
+        if (need > h->gather_doubles) {
+            cudaFree(h->d_gather); h->d_gather = nullptr; h->gather_doubles = 0;
+            KCU(cudaMalloc(&h->d_gather, need * sizeof(double)));
+            h->gather_doubles = need;
+        }
+        double *g_kinv = h->d_gather, *g_lm = g_kinv + (size_t)D * D, *g_cf = g_lm + (size_t)D * kb::MAX_DIM;
+        kb::gather_kernel<<<64, 256>>>(h->st, l, g_lm, g_cf, g_kinv);
+        KCU(cudaGetLastError());
+        KCU(cudaDeviceSynchronize());
+        if (landmarks) {
+            std::vector<double> tmp((size_t)D * kb::MAX_DIM);
+            KCU(cudaMemcpy(tmp.data(), g_lm, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < D; ++i) for (int j = 0; j < d; ++j) landmarks[(size_t)i * d + j] = tmp[(size_t)i * kb::MAX_DIM + j];
+        }
+        if (coeff) KCU(cudaMemcpy(coeff, g_cf, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost));
+        if (kinv) KCU(cudaMemcpy(kinv, g_kinv, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost));
     }
-    if (coeff && D) KCU(cudaMemcpy(coeff, h->st.coeff + (size_t)l * cap, (size_t)D * sizeof(double), cudaMemcpyDeviceToHost));
-    if (kinv && D)
-        KCU(cudaMemcpy2D(kinv, (size_t)D * sizeof(double), h->st.kinv + (size_t)l * cap * cap, (size_t)cap * sizeof(double),
-                         (size_t)D * sizeof(double), D, cudaMemcpyDeviceToHost));
     if (D_out) *D_out = D;
     return RS_OK;
 }

@@ -201,6 +201,7 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         p.obs_time = cfg->slots_per_step * 1e-3;
     }
     h->embb.U = cfg->n_envs * p.n_l1e; h->embb.K = K; h->embb.MB = MB;
+    h->embb.route[0] = 6; h->embb.route[1] = 8; h->embb.route[2] = 14; h->embb.route[3] = 16;   // embb_smem.cu: SM_KS = 8 slots per lane
     h->embb.R = mux ? cfg->n_embb : 1;
     h->mmtc.U = cfg->n_envs * cfg->n_mmtc; h->mmtc.Q = Q;
 
@@ -525,6 +526,27 @@ int rs_selftest(void) {
             if (q2 != x / dn) return fail(RS_E_STATE, "two-FMA division by a count is not exact");
         }
     }
+    return RS_OK;
+}
+
+int rs_set_route_limits(rs_handle *h, int32_t single_start_max, int32_t single_slots, int32_t pair_start_max, int32_t pair_slots) {
+    if (!h) return fail(RS_E_ARG, "null handle");
+    if (single_slots < 1 || single_slots > 8 || pair_slots < single_slots || pair_slots > 16 || single_start_max < 0 ||
+        single_start_max > single_slots || pair_start_max < single_start_max || pair_start_max > pair_slots)
+        return fail(RS_E_ARG, "route limits: 0 <= single_start_max <= single_slots <= 8, single_start_max <= pair_start_max <= pair_slots <= 16");
+    h->embb.route[0] = single_start_max; h->embb.route[1] = single_slots; h->embb.route[2] = pair_start_max; h->embb.route[3] = pair_slots;
+    return RS_OK;
+}
+
+int rs_get_routes(rs_handle *h, uint64_t *out4) {
+    if (!h || !out4) return fail(RS_E_ARG, "null argument");
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (!h->embb.U || h->cfg.l1_mux || h->cfg.kernel_variant != 0 || h->embb.K > 16) return RS_OK;   // other variants do not route
+    uint32_t t[4];
+    CU(cudaMemcpy(t, h->embb.hist + 2 * rs::SORT_BINS, sizeof t, cudaMemcpyDeviceToHost));
+    out4[0] = (uint64_t)t[0] - 2ull * t[3]; out4[1] = t[3]; out4[2] = t[2]; out4[3] = (uint64_t)t[1] - t[2];
     return RS_OK;
 }
 

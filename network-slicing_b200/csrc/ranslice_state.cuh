@@ -65,6 +65,9 @@ struct EmbbState {
     int U, K, MB;          // units, UE records per unit, burst slots per UE (== MAX_BURSTS)
     int R;                 // RAN slices per unit: 1, or n_embb when the L1 multiplexes them (then U = envs, acc is [U][R][10])
     MuxRan *mux;           // [U][R] (multiplexed mode only)
+    int route[4];          // routing limits of the shared-memory kernel: units starting a step with <= route[0] UEs own one lane and
+                           // may grow to route[1] slots, up to route[2] UEs a pair of lanes / route[3] slots, beyond: list L (general
+                           // kernel); outgrowing the slots aborts and replays.  Defaults 6 / 8 / 14 / 16; tests shrink them (rs_set_route_limits)
     int wide;              // 1: launch the latency variant of the shared-memory kernel (small batches)
     int dil, perm_len;     // lane dilution (log2) of the shared-memory kernel's front list and the length of perm[]: when a batch
                            // cannot fill the GPU, every 2^dil-th lane carries a unit and the rest idle -- fewer divergent units
@@ -76,7 +79,7 @@ struct EmbbState {
     // per-step scheduling scratch (not part of the checkpoint semantics, rebuilt every step)
     uint32_t *win;         // [U] i_prb (low 16) | n_prbs (high 16) of this step
     int32_t *perm;         // [perm_len = 2U << dil] front: unit ids sorted by descending (live UEs, n_prbs, contention class); list L grows down from the end
-    uint32_t *hist;        // [2 * SORT_BINS + 4 + SCAN_BLOCKS] histogram, offsets / scatter cursors, {front count, list-L count, -, pair entries}, block totals of the scan
+    uint32_t *hist;        // [2 * SORT_BINS + 4 + SCAN_BLOCKS] histogram, offsets / scatter cursors, {front count, list-L count (direct + aborted), list-L count before the slice kernel (direct), pair entries}, block totals of the scan
     uint32_t *hint;        // [U] contended PF-loop iterations of the previous step << 8 | its n_prbs (sort hint only; never affects results)
     ColdRec *cold;         // [U][K] per-step scratch of the shared-memory kernel
     float *dbg;            // [8] guard-band validation maxima (debug_check runs only)

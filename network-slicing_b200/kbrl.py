@@ -22,8 +22,9 @@ mmtc_sec, mmtc_a = (1, 4), (2, 10)        # :192-193
 
 class KbConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("n_envs", C.c_int32), ("n_slices", C.c_int32),
-                ("n_prbs", C.c_int32), ("n_variables", C.c_int32), ("dict_cap", C.c_int32), ("reserved", C.c_int32),
-                ("gamma", C.c_double), ("eta", C.c_double)]
+                ("n_prbs", C.c_int32), ("n_variables", C.c_int32), ("dict_cap", C.c_int32), ("pool_mb", C.c_int32),
+                ("gamma", C.c_double), ("eta", C.c_double), ("tie_seed", C.c_uint64), ("first_env_id", C.c_uint64),
+                ("algorithm", C.c_int32), ("reserved", C.c_int32)]
 
 
 def _p(a):
@@ -49,9 +50,10 @@ def _bind(L):
     L.kb_get_sizes.argtypes = [vp, vp, vp]
     L.kb_get_learner.argtypes = [vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.kb_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.kb_get_pool.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     for n in ("kb_create", "kb_destroy", "kb_reset", "kb_update", "kb_predict", "kb_update_device", "kb_predict_device",
               "kb_get_sizes", "kb_get_learner", "kb_get_counters", "kb_control_init", "kb_control_update_device",
-              "kb_control_select_device", "kb_control_get", "kb_set_exact"):
+              "kb_control_select_device", "kb_control_get", "kb_set_exact", "kb_get_pool"):
         getattr(L, n).restype = C.c_int
     L._kb_bound = True
     return L
@@ -60,7 +62,12 @@ def _bind(L):
 class BatchedProjectron:
     """One ``Projectron(GaussianKernel(SVvariable(), gamma), eta)`` per (env, slice), on the GPU."""
 
-    def __init__(self, scenario, n_envs, dict_cap=256, device=0, gamma=1.0, eta=0.1):
+    def __init__(self, scenario, n_envs, dict_cap=1024, device=0, gamma=1.0, eta=0.1, tie_seed=0, first_env_id=0,
+                 pool_mb=0, algorithm="projectron"):
+        """``dict_cap`` only bounds the size ONE dictionary may reach (the reference's are unbounded, flagged when hit);
+        memory comes from a device pool of ``pool_mb`` MiB (0: automatic) as the dictionaries grow.  ``tie_seed`` keys
+        the Philox stream behind the random tie-break of ``GaussianKernel.predict`` (kernel.py:26-27);
+        ``algorithm``: "projectron" (projectron.py:23-60) or "projectron_plus" (:66-107)."""
         sc = scenarios[scenario] if isinstance(scenario, int) else scenario
         self.n_envs, self.n_prbs, self.device = n_envs, sc['n_prbs'], device
         n_embb, n_mmtc = sc['n_embb'], sc['n_mmtc']
@@ -69,8 +76,9 @@ class BatchedProjectron:
         self.offsets = np.concatenate([[0], np.cumsum(self.dims - 1)[:-1]]).astype(np.int32)
         self.n_variables = int((self.dims - 1).sum())
         L = _bind(_lib.lib())
-        cfg = KbConfig(_lib.RS_ABI_VERSION, device, n_envs, self.n_slices, self.n_prbs, self.n_variables, dict_cap, 0,
-                       gamma, eta)
+        algo = {"projectron": 0, "projectron_plus": 1}[algorithm]
+        cfg = KbConfig(_lib.RS_ABI_VERSION, device, n_envs, self.n_slices, self.n_prbs, self.n_variables, dict_cap, pool_mb,
+                       gamma, eta, int(tie_seed) & (2 ** 64 - 1), first_env_id, algo, 0)
         h = C.c_void_p()
         _lib.check(L.kb_create(C.byref(cfg), _p(self.dims), _p(self.offsets), C.byref(h)))
         self._h, self._L = h, L
@@ -134,6 +142,13 @@ class BatchedProjectron:
         Dout = C.c_int32()
         _lib.check(self._L.kb_get_learner(self._h, l, _p(lm), _p(cf), _p(ki), C.byref(Dout)))
         return lm[:D], cf[:D], ki[:D, :D]
+
+    def pool(self):
+        """dict(used_bytes, total_bytes, max_dictionary, tie_breaks) of the dictionary pool."""
+        u, t, m, tb = C.c_uint64(), C.c_uint64(), C.c_int32(), C.c_uint64()
+        _lib.check(self._L.kb_get_pool(self._h, C.byref(u), C.byref(t), C.byref(m), C.byref(tb)))
+        return {"used_bytes": int(u.value), "total_bytes": int(t.value), "max_dictionary": int(m.value),
+                "tie_breaks": int(tb.value)}
 
     def counters(self):
         k, u = C.c_uint64(), C.c_uint64()
@@ -310,7 +325,8 @@ class DeviceKBRLControl:
                 'adjusted': t(adjusted_actions), 'SLA': t(SLA_history), 'violation': t(violation_history)}
 
 
-def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=256, device=0, resident=False):
+def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=1024, device=0, resident=False,
+                      tie_seed=None, first_env_id=0, pool_mb=0, algorithm="projectron"):
     """``scenario_creator.create_kbrl_agent`` (scenario_creator.py:197-238): random initial action and security
     factor per learner (drawn per env from ``rng`` in the reference's order), gamma = 1, eta = 0.1."""
     sc = scenarios[n]
@@ -322,7 +338,10 @@ def create_kbrl_agent(rng, n, accuracy_range=(0.99, 0.999), n_envs=1, dict_cap=2
             ia[e, s] = rng.integers(embb_a[0], embb_a[1]); sec[e, s] = rng.integers(embb_sec[0], embb_sec[1])
         for s in range(n_embb, n_embb + n_mmtc):
             ia[e, s] = rng.integers(mmtc_a[0], mmtc_a[1]); sec[e, s] = rng.integers(mmtc_sec[0], mmtc_sec[1])
-    learners = BatchedProjectron(n, n_envs, dict_cap=dict_cap, device=device)
+    if tie_seed is None:           # the reference's tie-break uses the global np.random; here: one more draw from rng
+        tie_seed = int(rng.integers(0, 2 ** 63 - 1))
+    learners = BatchedProjectron(n, n_envs, dict_cap=dict_cap, device=device, tie_seed=tie_seed, first_env_id=first_env_id,
+                                 pool_mb=pool_mb, algorithm=algorithm)
     if resident:        # controller state on the GPU, torch tensors in / out (no host round trip per step)
         return DeviceKBRLControl(learners, sc['n_prbs'], ia, sec, alfa=alfa, accuracy_range=accuracy_range)
     return KBRLControl(learners, sc['n_prbs'], ia, sec, alfa=alfa, accuracy_range=accuracy_range)

@@ -35,8 +35,15 @@ typedef struct orc_kb {
     int64_t *action, *sec, *margins;
     double *acc;     /* [S][n_prbs] accuracies (kbrl_control.py:38-39) */
     int adjusted;
-    long tie_breaks; /* kernel.py:26-27 random tie break; never expected with D > 0 */
+    long tie_breaks; /* kernel.py:26-27 random tie breaks taken (f == 0 with a non-empty dictionary) */
+    /* tie-break stream: np.random.choice([-1, 1]) -> Philox (key = seed, counter = (n, STREAM_KBRL = 5, learner, env id)),
+     * integers(2) -> index (RNG contract: network-slicing_b200/philox.py); off until orc_kb_set_tie_stream */
+    int tie_on; uint32_t tie_key[2], tie_env; uint32_t *tie_ctr; /* [S] */
+    int cur;         /* learner whose predict() is running */
+    int plus;        /* 1: ProjectronPlus.update (algorithms/projectron.py:66-107) instead of Projectron.update */
 } orc_kb;
+
+void orc_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   /* ranslice_oracle.c */
 
 static double sq_dist(const double *l, const double *x, int n) {   /* ((l - x)**2).sum(): numpy pairwise order */
     double a[16];
@@ -85,12 +92,19 @@ static int predict(orc_kb *kb, learner_t *h, const double *x) {
     if (h->f > 0) return 1;
     if (h->f < 0) return -1;
     kb->tie_breaks++;                                        /* np.random.choice([-1,1]) in the reference */
+    if (kb->tie_on) {
+        uint32_t c[4] = {kb->tie_ctr[kb->cur]++, 5u, (uint32_t)kb->cur, kb->tie_env}, out[4];
+        orc_philox(c, kb->tie_key, out);
+        return (((uint64_t)out[0] * 2u) >> 32) ? 1 : -1;     /* [-1, 1][integers(2)] */
+    }
     return -1;
 }
 
 /* Projectron.update (projectron.py:39-60) */
 static void update(orc_kb *kb, learner_t *h, const double *x, int y) {
-    if (!(h->f * y <= 0)) return;
+    const double margin = (double)y * h->f;                  /* np.int64 * float32 / float64 -> float64 */
+    const int inside = kb->plus && margin < 1 && margin > 0; /* ProjectronPlus: right side of the margin (projectron.py:72) */
+    if (!inside && !(margin <= 0)) return;
     const double Kii = 1.0;                                  /* k_eval(x, x) = exp(-gamma * 0) */
     int D = h->D;
     if (D + 1 >= h->cap) grow(h);
@@ -111,6 +125,21 @@ static void update(orc_kb *kb, learner_t *h, const double *x, int y) {
     }
     double delta = Kii - dot;
     if (delta < 0) delta = 0;
+    if (inside) {                                            /* projectron.py:73-84 (never extends the dictionary) */
+        const double loss = 1 - margin;
+        double norm_xt = Kii - delta;
+        if (norm_xt < 0) norm_xt = 0;
+        if (loss - delta / kb->eta > 0) {
+            double alpha = loss / norm_xt;
+            if (alpha > 1) alpha = 1;
+            const double a2 = 2 * (loss - delta / kb->eta) / norm_xt;
+            if (a2 < alpha) alpha = a2;
+            const double ay = alpha * y;                     /* alpha * y * d_star: float64 products; float32 coeff += rounds once */
+            if (D <= 1) h->coeff[0] = (double)(float)(h->coeff[0] + ay * dstar[0]);
+            else for (int i = 0; i < D; ++i) h->coeff[i] += ay * dstar[i];
+        }
+        return;
+    }
     if (delta <= kb->eta) {                                  /* sv.update(y * d_star) */
         if (D <= 1) h->coeff[0] = (double)(float)((float)h->coeff[0] + (float)y * (float)dstar[0]);
         else for (int i = 0; i < D; ++i) h->coeff[i] += y * dstar[i];
@@ -137,6 +166,7 @@ orc_kb *orc_kb_create(int S, const int32_t *dims, const int32_t *offsets, int n_
     kb->sec = (int64_t *)calloc(S, sizeof(int64_t));
     kb->margins = (int64_t *)calloc(S, sizeof(int64_t));
     kb->acc = (double *)calloc((size_t)S * n_prbs, sizeof(double));
+    kb->tie_ctr = (uint32_t *)calloc(S, sizeof(uint32_t));
     for (int s = 0; s < S; ++s) {
         kb->L[s].d = dims[s]; kb->L[s].off = offsets[s];
         grow(&kb->L[s]);
@@ -149,7 +179,14 @@ orc_kb *orc_kb_create(int S, const int32_t *dims, const int32_t *offsets, int n_
 void orc_kb_destroy(orc_kb *kb) {
     if (!kb) return;
     for (int s = 0; s < kb->S; ++s) { free(kb->L[s].lm); free(kb->L[s].coeff); free(kb->L[s].kinv); free(kb->L[s].kf); }
+    free(kb->tie_ctr);
     free(kb->L); free(kb->action); free(kb->sec); free(kb->margins); free(kb->acc); free(kb);
+}
+
+void orc_kb_set_algorithm(orc_kb *kb, int plus) { kb->plus = plus; }
+
+void orc_kb_set_tie_stream(orc_kb *kb, uint64_t seed, uint32_t env_id) {
+    kb->tie_on = 1; kb->tie_key[0] = (uint32_t)seed; kb->tie_key[1] = (uint32_t)(seed >> 32); kb->tie_env = env_id;
 }
 
 static void make_x(const learner_t *h, const float *state, int64_t a, int n_prbs, double *x) {
@@ -163,6 +200,7 @@ void orc_kb_update_control(orc_kb *kb, const float *state, const int64_t *action
     int n = kb->n_prbs;
     for (int i = 0; i < kb->S; ++i) {
         learner_t *h = &kb->L[i];
+        kb->cur = i;
         int64_t a0 = action[i];
         make_x(h, state, a0, n, x);
         int y_pred = predict(kb, h, x);
@@ -196,6 +234,7 @@ void orc_kb_select_action(orc_kb *kb, const float *state, int64_t *action_out, i
     int64_t assigned = 0;
     for (int i = 0; i < kb->S; ++i) {
         learner_t *h = &kb->L[i];
+        kb->cur = i;
         int64_t offset = kb->sec[i], margin = 0, l1 = n;
         for (int64_t c = 0; c <= n; ++c) {
             make_x(h, state, c, n, x);
@@ -245,5 +284,5 @@ int orc_kb_get_learner(const orc_kb *kb, int s, double *lm, double *coeff, doubl
 }
 
 /* single-learner entry points for unit tests of predict / update */
-double orc_kb_predict(orc_kb *kb, int s, const double *x, int32_t *y) { *y = predict(kb, &kb->L[s], x); return kb->L[s].f; }
+double orc_kb_predict(orc_kb *kb, int s, const double *x, int32_t *y) { kb->cur = s; *y = predict(kb, &kb->L[s], x); return kb->L[s].f; }
 void orc_kb_update(orc_kb *kb, int s, const double *x, int32_t y) { update(kb, &kb->L[s], x, y); }

@@ -203,6 +203,8 @@ def _kb_lib():
         L.orc_kb_predict.restype = C.c_double
         L.orc_kb_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_kb_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32]
+        L.orc_kb_set_tie_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.orc_kb_set_algorithm.argtypes = [C.c_void_p, C.c_int]
         L._kb_ready = True
     return L
 
@@ -210,7 +212,8 @@ def _kb_lib():
 class OracleKBRL:
     """One KBRL_Control (kbrl_control.py) with S Projectron learners, CPU oracle."""
 
-    def __init__(self, dims, n_prbs, init_action, init_sec, accuracy_range=(0.99, 0.999), alfa=0.05, gamma=1.0, eta=0.1):
+    def __init__(self, dims, n_prbs, init_action, init_sec, accuracy_range=(0.99, 0.999), alfa=0.05, gamma=1.0, eta=0.1,
+                 tie_seed=None, env_id=0, plus=False):
         self.S = len(dims)
         self.dims = np.ascontiguousarray(dims, np.int32)
         self.offsets = np.ascontiguousarray(np.concatenate([[0], np.cumsum(self.dims - 1)[:-1]]), np.int32)
@@ -219,6 +222,10 @@ class OracleKBRL:
         isec = np.ascontiguousarray(init_sec, np.int64)
         self.h = _kb_lib().orc_kb_create(self.S, _ptr(self.dims), _ptr(self.offsets), n_prbs, alfa, accuracy_range[0],
                                          accuracy_range[1], _ptr(ia), _ptr(isec), gamma, eta)
+        if plus:                       # ProjectronPlus (algorithms/projectron.py:66-107)
+            _kb_lib().orc_kb_set_algorithm(self.h, 1)
+        if tie_seed is not None:       # f == 0 tie-break of GaussianKernel.predict (kernel.py:26-27) from the KBRL Philox stream
+            _kb_lib().orc_kb_set_tie_stream(self.h, C.c_uint64(tie_seed), C.c_uint32(env_id))
 
     def __del__(self):
         if getattr(self, "h", None):

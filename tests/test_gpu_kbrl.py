@@ -3,22 +3,34 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
+from test_kbrl_oracle import check_final_dictionaries
 
 pytestmark = pytest.mark.gpu
 
+FIXTURES = ["K_scn0", "K_scn1", "K_tie", "K_plus", "K_long0"]
+TOL = {"K_long0": (1e-6, 1e-8, 1e-6)}       # rtol, atol coeff, atol K^-1 (3000 steps, dictionaries of 500 landmarks)
 
-def _control(g, n_envs=1, dict_cap=256):
-    from ranslice_b200.kbrl import BatchedProjectron, KBRLControl
-    lrn = BatchedProjectron(int(g["scenario"]), n_envs, dict_cap=dict_cap)
+
+def _learners(g, name, n_envs=1, dict_cap=1024):
+    from ranslice_b200.kbrl import BatchedProjectron
+    return BatchedProjectron(int(g["scenario"]), n_envs, dict_cap=dict_cap, tie_seed=int(g["seed"]),
+                             algorithm="projectron_plus" if name == "K_plus" else "projectron")
+
+
+def _control(g, name, n_envs=1, dict_cap=1024):
+    from ranslice_b200.kbrl import KBRLControl
+    lrn = _learners(g, name, n_envs, dict_cap)
     return KBRLControl(lrn, int(g["n_prbs"]), g["init_action"], g["init_sec"], alfa=float(g["alfa"]),
                        accuracy_range=tuple(g["accuracy_range"]))
 
 
-@pytest.mark.parametrize("name", ["K_scn0", "K_scn1"])
+@pytest.mark.parametrize("name", FIXTURES)
 def test_controller_replays_reference_fixture(golden, name):
-    """CUDA Projectron + host mirror of KBRL_Control vs the unmodified reference controller, step by step."""
+    """CUDA Projectron + host mirror of KBRL_Control vs the unmodified reference controller, step by step.  K_long0 runs
+    the reference's own horizon (3000 steps, dictionaries of ~500 landmarks: pooled growth, both update launches and the
+    hand-over between them), K_tie the random tie-break of kernel.py:26-27, K_plus ProjectronPlus."""
     g = golden(name)
-    ctl = _control(g)
+    ctl = _control(g, name)
     for t in range(len(g["state"])):
         hits = ctl.update_control(g["state"][t][None], g["action"][t][None], g["labels"][t][None])
         assert np.array_equal(hits[0], g["hits"][t]), t
@@ -29,13 +41,13 @@ def test_controller_replays_reference_fixture(golden, name):
         assert np.array_equal(ctl.security_factors[0], g["security_factors"][t]), t
         assert np.array_equal(ctl.margins[0], g["margins"][t]), t
     assert np.allclose(ctl.accuracies[0], g["accuracies"], rtol=0, atol=1e-15)
-    for s in range(len(g["dims"])):
-        lm, cf, ki = ctl.learners.learner(0, s)
-        D, d = len(cf), int(g["dims"][s])
-        assert np.array_equal(lm, g["final_landmarks"][s, :D, :d])
-        assert np.allclose(cf, g["final_coeff"][s, :D], rtol=1e-8, atol=1e-11)
-        assert np.allclose(ki, g["final_kinv"][s, :D, :D], rtol=1e-8, atol=1e-8)
-    assert not ctl.learners.sizes()[1].any()
+    check_final_dictionaries(g, lambda s: ctl.learners.learner(0, s), *TOL.get(name, (1e-8, 1e-11, 1e-8)))
+    assert not ctl.learners.sizes()[1].any()                  # no dictionary cap / pool flag
+    pool = ctl.learners.pool()
+    assert pool["tie_breaks"] == int(g["tie_calls"])          # every np.random.choice of the reference, and no other
+    assert pool["max_dictionary"] == int(g["sizes"].max())
+    rows = (g["sizes"][-1] + 31) // 32                        # bump allocator: exactly the tile rows the dictionaries hold
+    assert pool["used_bytes"] == 8 * int(sum(544 * r + 1024 * r * (r + 1) // 2 for r in rows))
 
 
 def test_batched_learners_match_oracle_on_synthetic_streams():
@@ -45,8 +57,8 @@ def test_batched_learners_match_oracle_on_synthetic_streams():
     N, S, n_prbs, T = 64, 5, 200, 60
     rng = np.random.default_rng(11)
     ia = rng.integers(4, 20, (N, S)); sec = rng.integers(2, 8, (N, S))
-    ctl = KBRLControl(BatchedProjectron(0, N, dict_cap=128), n_prbs, ia, sec, accuracy_range=(0.97, 0.99))
-    orcs = [ol.OracleKBRL([11] * S, n_prbs, ia[e], sec[e], (0.97, 0.99)) for e in range(N)]
+    ctl = KBRLControl(BatchedProjectron(0, N, dict_cap=128, tie_seed=5), n_prbs, ia, sec, accuracy_range=(0.97, 0.99))
+    orcs = [ol.OracleKBRL([11] * S, n_prbs, ia[e], sec[e], (0.97, 0.99), tie_seed=5, env_id=e) for e in range(N)]
     state = rng.random((N, 50)).astype(np.float32)
     action = ia.copy()
     for t in range(T):
@@ -66,15 +78,26 @@ def test_batched_learners_match_oracle_on_synthetic_streams():
     assert sizes.max() > 3
 
 
-def test_dictionary_cap_is_flagged():
+def test_dictionary_cap_and_pool_exhaustion_are_flagged():
+    """dict_cap bounds ONE dictionary (flag 1); an exhausted pool drops the sample and flags 2 -- never a crash."""
     from ranslice_b200.kbrl import BatchedProjectron
-    lrn = BatchedProjectron(0, 2, dict_cap=4)
     rng = np.random.default_rng(0)
-    for t in range(30):
+    lrn = BatchedProjectron(0, 2, dict_cap=32)
+    for t in range(60):
         st = (rng.random((2, 50)) * 3).astype(np.float32)
         lrn.update(st, rng.integers(0, 200, (2, 5)), rng.choice([-1, 1], (2, 5)))
     sizes, flags = lrn.sizes()
-    assert sizes.max() <= 4 and (flags & 1).any()
+    assert sizes.max() == 32 and (flags & 1).any() and not (flags & 2).any()
+    lrn.close()
+    lrn = BatchedProjectron(0, 64, dict_cap=1024, pool_mb=1)      # 1 MiB for 320 learners: 12.6 KB per first tile row -> ~83 rows
+    for t in range(40):
+        st = (rng.random((64, 50)) * 3).astype(np.float32)
+        lrn.update(st, rng.integers(0, 200, (64, 5)), rng.choice([-1, 1], (64, 5)))
+    sizes, flags = lrn.sizes()
+    pool = lrn.pool()
+    assert (flags & 2).any() and pool["used_bytes"] <= pool["total_bytes"] == 1 << 20
+    assert (sizes[(flags & 2) == 0] <= 32 * 8).all()
+    lrn.close()
 
 
 def test_kbrl_in_the_loop_with_the_env():
@@ -93,20 +116,20 @@ def test_kbrl_in_the_loop_with_the_env():
 
 
 # ------------------------------------------------------------------------------------------------ device-resident controller
-def _device_control(g, n_envs=1, dict_cap=256):
-    from ranslice_b200.kbrl import BatchedProjectron, DeviceKBRLControl
-    lrn = BatchedProjectron(int(g["scenario"]), n_envs, dict_cap=dict_cap)
+def _device_control(g, name, n_envs=1, dict_cap=1024):
+    from ranslice_b200.kbrl import DeviceKBRLControl
+    lrn = _learners(g, name, n_envs, dict_cap)
     return DeviceKBRLControl(lrn, int(g["n_prbs"]), g["init_action"], g["init_sec"], alfa=float(g["alfa"]),
                              accuracy_range=tuple(g["accuracy_range"]))
 
 
-@pytest.mark.parametrize("name", ["K_scn0", "K_scn1"])
+@pytest.mark.parametrize("name", FIXTURES)
 def test_device_controller_replays_reference_fixture(golden, name):
     """kb_control_update_device / kb_control_select_device (controller state in HBM) vs the unmodified reference
     KBRL_Control, step by step: hits, next action, adjusted flag, security factors, margins, accuracies."""
     import torch
     g = golden(name)
-    ctl = _device_control(g)
+    ctl = _device_control(g, name)
     dev = ctl.device
     tt = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a[None]).astype(dt)).to(dev)
     for t in range(len(g["state"])):
@@ -120,6 +143,7 @@ def test_device_controller_replays_reference_fixture(golden, name):
             assert np.array_equal(cs["margins"][0], g["margins"][t]), t
             assert np.array_equal(ctl.learners.sizes()[0][0], g["sizes"][t]), t
     assert np.allclose(ctl.control_state()["accuracies"][0], g["accuracies"], rtol=0, atol=1e-15)
+    assert ctl.learners.pool()["tie_breaks"] == int(g["tie_calls"]) and not ctl.learners.sizes()[1].any()
 
 
 def test_device_controller_matches_host_mirror_in_the_loop():

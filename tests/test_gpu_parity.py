@@ -316,3 +316,167 @@ def test_multiplexed_l1_vs_oracle_and_facade(tables):
     o, r, d, info = one.step(np.array([150]))
     assert o.shape == (50,) and len(info["l1_info"]) == 1 and sorted(info["l1_info"][0]) == [0, 1, 2, 3, 4]
     assert len(info["SLA_labels"]) == 1 and info["n_prbs"] == [150]
+
+
+# ------------------------------------------------------------------------------------------------ round 2: routes, steady state, config surface
+def test_every_route_of_the_default_kernel_is_taken_and_exact(tables):
+    """The default kernel routes a unit by its live-UE count: one lane, a pair of lanes (slots 8.. live in the neighbour
+    lane's column), the general kernel for large units, and abort-and-replay when a unit outgrows its slots mid-step.
+    At the shipped limits (6 / 8 / 14 / 16) the last two are rare events; with the limits shrunk every route is taken
+    hundreds of times -- and every env still equals the oracle bit for bit."""
+    scn, N, T, seed = 0, 512, 400, 2468
+    S, n_prbs = SCN[scn]
+    env = make_env(scn, N, seed)
+    env.set_route_limits(single_start_max=2, single_slots=3, pair_start_max=5, pair_slots=10)
+    orc = ol.OracleBatch(tables, scn, N, seed, n_threads=16)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(17)
+    total = dict(single=0, pair=0, general=0, aborted=0)
+    slot9 = 0
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        if t % 13 == 6:
+            a[::4] = a[::4] // 6            # starved periods: deep queues, contended PF loops
+        obs, rew, _, info = env.step(a)
+        for k, v in env.routes().items():
+            total[k] += v
+        o_obs, o_rew, o_lab, o_vio, o_fl = orc.step(a)
+        ok = (info["flags"] == 0) & (o_fl == 0)
+        assert ok.mean() > 0.99
+        assert np.array_equal(obs[ok], o_obs[ok]), t
+        assert np.array_equal(rew[ok].astype(np.float64), o_rew[ok]) and np.array_equal(info["violations"][ok], o_vio[ok]), t
+        if t % 50 == 49:
+            slot9 += int((env.n_ues() > 8).sum())
+    assert min(total.values()) > 200, total
+    assert slot9 > 0                            # pair units that really use the neighbour lane's slots
+    env.close()
+
+
+def test_steady_state_parity_1024_envs_1000_steps(tables):
+    """The bench is timed at the steady-state UE population (>= 600 steps).  1024 envs x 1000 steps against the oracle,
+    every step; the shipped routing limits; pair-of-lanes units with more than 8 UEs occur naturally here."""
+    scn, N, T, seed = 0, 1024, 1000, 1357
+    S, n_prbs = SCN[scn]
+    env = make_env(scn, N, seed)
+    orc = ol.OracleBatch(tables, scn, N, seed, n_threads=16)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(23)
+    pairs = over8 = 0
+    ok = np.ones(N, bool)
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        obs, rew, _, info = env.step(a)
+        o_obs, o_rew, o_lab, o_vio, o_fl = orc.step(a)
+        ok &= (info["flags"] == 0) & (o_fl == 0)
+        assert np.array_equal(obs[ok], o_obs[ok]), t
+        assert np.array_equal(rew[ok].astype(np.float64), o_rew[ok]) and np.array_equal(info["SLA_labels"][ok], o_lab[ok]), t
+        if t % 100 == 99:
+            pairs += env.routes()["pair"]
+            over8 += int((env.n_ues() > 8).sum())
+    assert ok.mean() > 0.999 and pairs > 0 and over8 > 0
+    assert 2.0 < env.n_ues().mean() < 4.5          # steady-state population (SURVEY: ~3.5 nominal, 2.8 measured)
+    env.close()
+
+
+@pytest.mark.parametrize("kw", [dict(propagation_type="macro_cell_urban_900MHz"), dict(propagation_type="macro_cell_rural"),
+                                dict(penalty=1000), dict(slots_per_step=25), dict(slots_per_step=80, penalty=7)])
+def test_config_surface_vs_oracle(tables, kw):
+    """create_env's keyword surface (scenario_creator.py:100): propagation model, penalty (the model-free drivers use
+    1000, experiments_rl.py:34) and slots_per_step, each against the oracle."""
+    scn, N, T, seed = 0, 96, 150, 8642
+    S, n_prbs = SCN[scn]
+    env = make_env(scn, N, seed, **kw)
+    okw = dict(kw)
+    if "propagation_type" in okw:
+        okw["propagation"] = okw.pop("propagation_type")
+    orc = ol.OracleBatch(tables, scn, N, seed, n_threads=8, **okw)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(3)
+    for t in range(T):
+        a = simplex_actions(rng, N, S, n_prbs)
+        obs, rew, _, info = env.step(a)
+        o_obs, o_rew, o_lab, o_vio, o_fl = orc.step(a)
+        ok = (info["flags"] == 0) & (o_fl == 0)
+        assert ok.mean() > 0.95
+        assert np.array_equal(obs[ok], o_obs[ok]), t
+        assert np.array_equal(rew[ok].astype(np.float64), o_rew[ok]) and np.array_equal(info["violations"][ok], o_vio[ok]), t
+    if "penalty" in kw:
+        assert (rew[info["total_violations"] > 0] == -kw["penalty"] * info["total_violations"][info["total_violations"] > 0]).all()
+    env.close()
+
+
+def test_queue_limit_abort_replays_in_the_general_kernel():
+    """The shared-memory kernel keeps ue.queue in 31 bits and aborts a unit whose queue would not fit (replayed by the
+    general kernel, int64 queues).  A queue of 2^30 bits is planted through the checkpoint blob; the default variant must
+    then equal the all-fp64 anchor kernel (variant 1) step for step."""
+    scn, N, seed = 0, 16, 97531
+    S, n_prbs = SCN[scn]
+    envs = [make_env(scn, N, seed, kernel_variant=v) for v in (0, 1)]
+    rng = np.random.default_rng(9)
+    acts = [simplex_actions(rng, N, S, n_prbs) for _ in range(260)]
+    for e in envs:
+        e.reset()
+        for a in acts[:200]:
+            e.step(a)
+    blob = envs[0].get_state()                                  # (both handles continue from this one blob)
+    U, K = N * 5, 16
+    hdr = blob[:U * 32].view(np.int32).reshape(U, 8)
+    ue_off = (U * 32 + 255) // 256 * 256
+    ue = blob[ue_off:ue_off + U * K * 64].view(np.int64).reshape(U, K, 8)
+    planted = 0
+    for u in range(U):
+        if hdr[u, 0] > 0 and planted < 6:
+            ue[u, 0, 4] = (1 << 30) + 12345                     # UeRec::queue (ranslice_state.cuh)
+            planted += 1
+    assert planted == 6
+    for e in envs:
+        e.set_state(blob)
+    aborted = 0
+    for a in acts[200:]:
+        o0, r0, _, i0 = envs[0].step(a)
+        aborted += envs[0].routes()["aborted"]
+        o1, r1, _, i1 = envs[1].step(a)
+        assert np.array_equal(o0, o1) and np.array_equal(r0, r1) and np.array_equal(i0["violations"], i1["violations"])
+    assert aborted >= 6
+    for e in envs:
+        e.close()
+
+
+def test_adjacent_seeds_share_no_streams_and_reset_orders_after_device_steps():
+    """(1) Batches created with adjacent integer seeds -- the reference's replication pattern default_rng(seed=i) -- are
+    independent: no env of seed s+1 repeats an env of seed s (the env id is a Philox counter word, not a key offset).
+    (2) reset() / step() right after asynchronous step_device() calls on the caller's stream are ordered after them."""
+    import torch
+    scn, N = 3, 64
+    S, n_prbs = SCN[scn]
+    rng = np.random.default_rng(4)
+    acts = [simplex_actions(rng, 1, S, n_prbs).repeat(N, axis=0) for _ in range(40)]
+    outs = []
+    for seed in (500, 501):
+        env = make_env(scn, N, seed)
+        env.reset()
+        for a in acts:
+            obs, _, _, _ = env.step(a)
+        outs.append(obs.copy())
+        env.close()
+    same = (outs[0][:, None, :] == outs[1][None, :, :]).all(axis=2)
+    assert not same.any()
+    env = make_env(scn, N, 500)
+    ref = make_env(scn, N, 500)
+    for e in (env, ref):
+        e.reset()
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(dev)
+    for rep in range(3):
+        with torch.cuda.stream(side):
+            out = None
+            for a in acts[:10]:
+                out = env.step_device(torch.from_numpy(a).to(dev), out)
+        env.reset()                                   # must wait for the ten queued steps
+        o1, r1, _, _ = env.step(acts[11])             # host step on the handle's own stream
+        for a in acts[:10]:                           # the second handle goes through the same history synchronously
+            ref.step(a)                               # (reset keeps the RNG counters running, like the reference)
+        ref.reset()
+        o2, r2, _, _ = ref.step(acts[11])
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2), rep
+    env.close(); ref.close()

@@ -21,7 +21,10 @@ CASES = {"K_scn0": (0, 9000, 400, [0.97, 0.99]), "K_scn1": (1, 9100, 300, [0.99,
          "K_long0": (0, 9200, 3000, [0.97, 0.99]),
          # scripted states (no env) that put whole dictionaries out of reach: f == 0 exactly, so the random tie-break of
          # GaussianKernel.predict (kernel.py:26-27) fires in update_control and in the select_action scan
-         "K_tie": (0, 9300, 80, [0.97, 0.99])}
+         "K_tie": (0, 9300, 80, [0.97, 0.99]),
+         # the learners of create_kbrl_agent swapped for ProjectronPlus (algorithms/projectron.py:66-107; never instantiated by
+         # the reference's own factories): scripted states
+         "K_plus": (0, 9400, 150, [0.97, 0.99])}
 FULL_KINV_MAX_D = 160      # K_long: K^-1 is stored in full only for dictionaries up to this size (diag + row sums for all)
 
 
@@ -74,10 +77,14 @@ def gen(name):
     scn, seed, steps, a_range = CASES[name]
     ref = rh.load_reference()
     tie_calls = []
+    plain = ref.scenario_creator.Projectron
+    if name == "K_plus":
+        ref.scenario_creator.Projectron = ref.projectron.ProjectronPlus
     agent = ref.scenario_creator.create_kbrl_agent(np.random.default_rng(seed), scn, accuracy_range=a_range)
+    ref.scenario_creator.Projectron = plain
     S = agent.n_slices
     _route_tie_break(ref, agent, seed, tie_calls)
-    env = _ScriptedEnv(seed, 10 * S, S) if name == "K_tie" else rh.make_env_philox(seed, scn)[0]
+    env = _ScriptedEnv(seed, 10 * S, S) if name in ("K_tie", "K_plus") else rh.make_env_philox(seed, scn)[0]
     init_action = agent.action.copy()
     init_sec = agent.security_factors.copy()
     rec = {k: [] for k in ("state", "action", "labels", "new_state", "next_action", "adjusted", "hits", "sizes",
