@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2   /* 2: Philox env id in the counter, kb_config (pool, tie-break stream), rs_get_profile */
 
 enum { RS_OK = 0, RS_E_ARG = -1, RS_E_CUDA = -2, RS_E_NOMEM = -3, RS_E_STATE = -4 };
 
@@ -117,11 +117,14 @@ int rs_set_state(rs_handle *h, const void *blob, size_t bytes);
  * the last step summed over envs (B_trace of SURVEY 8d, 0 if the variant does not count) */
 int rs_get_counters(rs_handle *h, uint64_t *kernel_launches, uint64_t *trace_elems_last_step);
 
-/* profiling: when enabled, rs_step_device brackets each of its kernels with CUDA events recorded on
- * the launching stream; rs_get_profile synchronises and returns the summed durations (ms) and the
- * number of profiled steps since the last call (bench.py's roofline.achieved denominator). */
+/* profiling: when enabled, rs_step_device runs its kernels on ONE stream and brackets them with CUDA events recorded on
+ * the launching stream; rs_get_profile synchronises and returns the summed durations (ms) of the profiled steps since the
+ * last call in ms6[6]: [0] sort pre-pass (window / scan / scatter), [1] the dominant eMBB slice kernel ALONE
+ * (embb_step_smem; bench.py's roofline.achieved denominator; 0 for the other variants), [2] the eMBB kernels after it
+ * (general kernel over list L; the whole eMBB part for the other variants), [3] mMTC scan, [4] mMTC FIFO kernel,
+ * [5] reward kernel; *steps = profiled steps. */
 int rs_set_profiling(rs_handle *h, int32_t enable);
-int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *reward_ms, uint64_t *steps);
+int rs_get_profile(rs_handle *h, double *ms6, uint64_t *steps);
 
 /* guard-band validation (tests): with debug_check on, the default eMBB kernel evaluates the exact fp64
  * expression next to every fast-path decision.  rs_get_diag: out[0] max |p64 - p32| / eps over

@@ -9,7 +9,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("RS_B200_LIB") or os.path.join(_PKG, "libranslice_b200.so")   # RS_B200_LIB: experiment builds (tools/sweep_variants.sh)
 
-RS_ABI_VERSION = 1
+RS_ABI_VERSION = 2
 FLAG_UE_CAP, FLAG_BURST_CAP, FLAG_ACTION_CLAMP, FLAG_SAME_SLOT_DEP, FLAG_MTC_QUEUE_CAP = 1, 2, 4, 8, 16
 
 class RsConfig(C.Structure):
@@ -60,8 +60,7 @@ def lib():
     L.rs_set_debug_check.argtypes = [vp, i32]
     L.rs_get_diag.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.rs_set_profiling.argtypes = [vp, i32]
-    L.rs_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
-                                 C.POINTER(C.c_uint64)]
+    L.rs_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.rs_set_route_limits.argtypes = [vp, i32, i32, i32, i32]
     L.rs_get_routes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.rs_last_error.restype = C.c_char_p

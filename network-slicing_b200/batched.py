@@ -190,12 +190,15 @@ class BatchedRanSlice:
         _lib.check(L.rs_set_profiling(self._h, 1))
         for a in actions:
             out = self.step_device(a, out)
-        e, m, r, n = C.c_double(), C.c_double(), C.c_double(), C.c_uint64()
-        _lib.check(L.rs_get_profile(self._h, C.byref(e), C.byref(m), C.byref(r), C.byref(n)))
+        ms, n = (C.c_double * 6)(), C.c_uint64()
+        _lib.check(L.rs_get_profile(self._h, ms, C.byref(n)))
         _lib.check(L.rs_set_profiling(self._h, 0))
         k = max(int(n.value), 1)
-        return {"embb_ms": e.value / k, "mmtc_ms": m.value / k, "reward_ms": r.value / k, "steps": int(n.value),
-                "kernel": self.kernel_variant_name()}
+        names = ("sort_ms", "dominant_ms", "embb_rest_ms", "mmtc_scan_ms", "mmtc_step_ms", "reward_ms")
+        out = {nm: ms[i] / k for i, nm in enumerate(names)}
+        out.update({"embb_ms": (ms[0] + ms[1] + ms[2]) / k, "mmtc_ms": (ms[3] + ms[4]) / k, "steps": int(n.value),
+                    "kernel": self.kernel_variant_name()})
+        return out
 
     def set_route_limits(self, single_start_max=6, single_slots=8, pair_start_max=14, pair_slots=16):
         """Routing limits of the default eMBB kernel (tests; results never depend on them), see rs_set_route_limits."""

@@ -695,7 +695,7 @@ void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ue
 void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream);
 
 // default variant: shared-memory kernel over the sorted front list, general kernel over list L
-int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
     static bool configured = false;
     constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
     static_assert(RS_SM_BLOCKS * (smem_bytes + 2048 + 1024) <= 227 * 1024, "RS_SM_BLOCKS blocks per SM must fit");
@@ -709,8 +709,10 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
     }
     launch_embb_sort(p, st, st.route[2], st.route[0] + 1, stream);
     const int blocks = (st.perm_len + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
+    if (prof) cudaEventRecord(prof[0], stream);               // profiling: events around the dominant kernel alone
     if (st.wide) embb_step_smem<1><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     else embb_step_smem<0><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
+    if (prof) cudaEventRecord(prof[1], stream);
     launch_embb_general(p, st, tb, 1, stream);
     return 6;   // kernels launched
 }

@@ -132,9 +132,10 @@ __device__ __forceinline__ double base_dist(const double *l, const double *x, in
 // shared-memory slice of one group: tile-row pointers of its learner, then the staged dictionary
 __device__ __forceinline__ void carve(unsigned char *raw, int capS, int tmax, int group, double **&rowp, double *&base, double *&cf,
                                       double *&ll, double *&kf, double *&ds, float4 *&fast) {
-    unsigned char *p0 = raw + (size_t)group * ((size_t)tmax * sizeof(double *) + (size_t)capS * GROUP_SMEM_PER_LANDMARK);
+    const size_t rowp_bytes = ((size_t)tmax * sizeof(double *) + 15) & ~size_t(15);     // the float4 plane behind it needs 16-byte alignment
+    unsigned char *p0 = raw + (size_t)group * (rowp_bytes + (size_t)capS * GROUP_SMEM_PER_LANDMARK);
     rowp = reinterpret_cast<double **>(p0);
-    double *p = reinterpret_cast<double *>(p0 + (size_t)tmax * sizeof(double *));
+    double *p = reinterpret_cast<double *>(p0 + rowp_bytes);
     base = p; cf = base + capS; ll = cf + capS; kf = ll + capS; ds = kf + capS;
     fast = reinterpret_cast<float4 *>(ds + capS);            // [capS] fp32 copy of the staged dictionary (guarded fast path)
 }
@@ -691,7 +692,7 @@ static int kb_create_impl(kb_handle *h, const kb_config *cfg, const int32_t *dim
     KCU(cudaMalloc(&h->d_out, L * sizeof(int32_t)));
     KCU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->cap_small = std::min(cap, kb::SMALL_CAP);
-    const size_t rowp = (size_t)st.tmax * sizeof(double *);
+    const size_t rowp = ((size_t)st.tmax * sizeof(double *) + 15) & ~size_t(15);
     h->smem_update_small = (size_t)UG * (rowp + (size_t)h->cap_small * kb::GROUP_SMEM_PER_LANDMARK);
     h->smem_update_big = (size_t)UG * (rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK);
     h->smem_predict_small = (size_t)PG * (rowp + (size_t)std::min(cap, kb::SMALL_CAP_PREDICT) * kb::GROUP_SMEM_PER_LANDMARK);
@@ -766,12 +767,12 @@ static int launch_update(kb_handle *h, const float *d_state, const int32_t *d_ac
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
     KCU(cudaMemsetAsync(h->st.pend, 0xFF, (size_t)h->st.L * sizeof(int), st));            // PEND_FRESH
     const int blocks = (h->st.L + UG - 1) / UG, threads = kb::Cfg<KB_GROUP_UPDATE>::THREADS;
-    kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, 0, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
-    h->launches += 1;
-    if (h->st.cap > h->cap_small) {
-        kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_big, st>>>(h->st, h->st.cap, 1, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+    if (h->st.cap > h->cap_small) {                            // (with dict_cap <= SMALL_CAP the second launch alone does everything)
+        kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, 0, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
         h->launches += 1;
     }
+    kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_big, st>>>(h->st, h->st.cap, 1, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+    h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
 }

@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(256) reward_kernel(const __grid_constant__ Ste
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
     mmtc_reset_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
 }
-int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream) {
+int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream, cudaEvent_t *prof) {
     if (st.U % 4 == 0) mmtc_scan_kernel_v4<<<dim3((st.U / 4 + 127) / 128, MTC_STRIPS_V4), 128, 0, stream>>>(p, st);
     else mmtc_scan_kernel<<<dim3((st.U + 127) / 128, MTC_STRIPS), 128, 0, stream>>>(p, st);
+    if (prof) cudaEventRecord(prof[0], stream);               // profiling: end of the scan kernel
     mmtc_step_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
     return 2;   // kernels launched
 }

@@ -16,10 +16,10 @@
 namespace rs {
 void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
-int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof);
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
-int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream);
+int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream, cudaEvent_t *prof);
 void launch_embb_mux(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 void launch_embb_mux_reset(const EmbbState &st, cudaStream_t stream);
 void launch_reward(const StepParams &p, cudaStream_t stream);
@@ -34,6 +34,7 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(RS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));            \
     } while (0)
 
+constexpr int PROF_EVENTS = 7;
 struct rs_handle {
     rs_config cfg;
     rs::StepParams p;
@@ -73,7 +74,7 @@ struct rs_handle {
     uint64_t launches;
     bool was_reset;
     bool profiling;
-    std::vector<cudaEvent_t> *prof_events;   // 4 per profiled step
+    std::vector<cudaEvent_t> *prof_events;   // PROF_EVENTS per profiled step
 };
 
 namespace {
@@ -359,7 +360,9 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     p.violations = d_violations ? d_violations : h->d_violations;
     p.flags = d_flags ? d_flags : h->d_flags;
     CU(cudaMemsetAsync(h->d_trace_elems, 0, 3 * sizeof(unsigned long long), st));
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // profiling events of one step: [0] start, [1] / [2] around the dominant eMBB kernel, [3] end of the eMBB kernels,
+    // [4] end of the mMTC scan, [5] end of the mMTC kernels, [6] end of the step
+    cudaEvent_t ev[PROF_EVENTS] = {};
     if (h->profiling) {
         for (auto &e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], st));
@@ -368,26 +371,33 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     // mMTC kernels run on a side stream next to the eMBB kernels and join before the reward reduction.  With
     // per-kernel profiling on, everything stays on one stream so that the events bracket single kernels.
     const bool fork = h->embb.U && h->mmtc.U && !h->profiling;
+    bool dominant = false;
     if (fork) {
         CU(cudaEventRecord(h->ev_fork, st));
         CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-        h->launches += rs::launch_mmtc_step(p, h->mmtc, h->side_stream);
+        h->launches += rs::launch_mmtc_step(p, h->mmtc, h->side_stream, nullptr);
         CU(cudaEventRecord(h->ev_join, h->side_stream));
     }
     if (h->embb.U) {
         if (h->cfg.l1_mux) { rs::launch_embb_mux(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->cfg.kernel_variant == 2 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
-        else h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st);
+        else { h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st, h->profiling ? ev + 1 : nullptr); dominant = true; }
     }
-    if (h->profiling) CU(cudaEventRecord(ev[1], st));
+    if (h->profiling) {
+        if (!dominant) { CU(cudaEventRecord(ev[1], st)); CU(cudaEventRecord(ev[2], st)); }   // other variants: no single dominant kernel
+        CU(cudaEventRecord(ev[3], st));
+    }
     if (fork) CU(cudaStreamWaitEvent(st, h->ev_join, 0));
-    else if (h->mmtc.U) h->launches += rs::launch_mmtc_step(p, h->mmtc, st);
-    if (h->profiling) CU(cudaEventRecord(ev[2], st));
+    else if (h->mmtc.U) h->launches += rs::launch_mmtc_step(p, h->mmtc, st, h->profiling ? ev + 4 : nullptr);
+    if (h->profiling) {
+        if (!h->mmtc.U) CU(cudaEventRecord(ev[4], st));
+        CU(cudaEventRecord(ev[5], st));
+    }
     rs::launch_reward(p, st);
     h->launches += 1;
     if (h->profiling) {
-        CU(cudaEventRecord(ev[3], st));
+        CU(cudaEventRecord(ev[6], st));
         for (auto &e : ev) h->prof_events->push_back(e);
     }
     CU(cudaGetLastError());
@@ -577,16 +587,16 @@ int rs_set_profiling(rs_handle *h, int32_t enable) {
     return RS_OK;
 }
 
-int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *reward_ms, uint64_t *steps) {
-    if (!h) return fail(RS_E_ARG, "null handle");
+int rs_get_profile(rs_handle *h, double *ms6, uint64_t *steps) {
+    if (!h || !ms6) return fail(RS_E_ARG, "null argument");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    double s[3] = {0, 0, 0};
+    double s[PROF_EVENTS - 1] = {};
     uint64_t n = 0;
     if (h->prof_events) {
         std::vector<cudaEvent_t> &v = *h->prof_events;
-        for (size_t i = 0; i + 3 < v.size(); i += 4) {
-            for (int j = 0; j < 3; ++j) {
+        for (size_t i = 0; i + PROF_EVENTS <= v.size(); i += PROF_EVENTS) {
+            for (int j = 0; j + 1 < PROF_EVENTS; ++j) {
                 float ms = 0.f;
                 CU(cudaEventElapsedTime(&ms, v[i + j], v[i + j + 1]));
                 s[j] += ms;
@@ -596,9 +606,7 @@ int rs_get_profile(rs_handle *h, double *embb_ms, double *mmtc_ms, double *rewar
         for (auto e : v) cudaEventDestroy(e);
         v.clear();
     }
-    if (embb_ms) *embb_ms = s[0];
-    if (mmtc_ms) *mmtc_ms = s[1];
-    if (reward_ms) *reward_ms = s[2];
+    for (int j = 0; j + 1 < PROF_EVENTS; ++j) ms6[j] = s[j];
     if (steps) *steps = n;
     return RS_OK;
 }

@@ -9,6 +9,7 @@
 * :func:`create_kbrl_agent` -- ``scenario_creator.create_kbrl_agent`` (scenario_creator.py:197-238).
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -57,6 +58,22 @@ def _bind(L):
         getattr(L, n).restype = C.c_int
     L._kb_bound = True
     return L
+
+
+def _report_flags(owner, env_flags, learners):
+    """Deviation flags are never silent: the OR over the run is kept on the agent (``env_flags`` uint32 [N] of the env,
+    ``learner_flags`` uint32 [N,S] of the dictionaries) and a warning names what fired."""
+    owner.env_flags = np.asarray(env_flags).astype(np.uint32)
+    owner.learner_flags = learners.sizes()[1]
+    names = {1: 'UE cap', 2: 'burst cap', 4: 'action clamped', 8: 'same-slot departure', 16: 'mMTC backlog / arrival cap'}
+    hit = [n for b, n in names.items() if (owner.env_flags & b).any()]
+    if (owner.learner_flags & 1).any():
+        hit.append('KBRL dictionary cap')
+    if (owner.learner_flags & 2).any():
+        hit.append('KBRL dictionary pool exhausted')
+    if hit:
+        warnings.warn('ranslice_b200: deviation flags raised during run(): %s (see agent.env_flags / agent.learner_flags)'
+                      % ', '.join(hit))
 
 
 class BatchedProjectron:
@@ -217,8 +234,10 @@ class KBRLControl:
         resources_history = np.zeros((N, steps), np.int16)
         hits_history = np.zeros((N, S, steps), np.int16)
         state = system.reset()
+        flags = np.zeros(N, np.uint32)
         for i in range(steps):
             new_state, reward, _, info = system.step(action)
+            flags |= info['flags']
             SLA_labels = info['SLA_labels']
             hits = self.update_control(state, action, SLA_labels)
             action, self.adjusted = self.select_action(new_state)
@@ -229,6 +248,7 @@ class KBRLControl:
             resources_history[:, i] = action.sum(axis=1)
             adjusted_actions[:, i] = self.adjusted
             hits_history[:, :, i] = hits
+        _report_flags(self, flags, self.learners)
         return {'reward': reward_history, 'resources': resources_history, 'hits': hits_history,
                 'adjusted': adjusted_actions, 'SLA': SLA_history, 'violation': violation_history}
 
@@ -305,9 +325,11 @@ class DeviceKBRLControl:
         bufs = [None, None]                                                                 # two output sets (state / new_state)
         action = self.action
         hits = torch.zeros((N, S), dtype=torch.int32, device=dev)
+        flags = torch.zeros(N, dtype=torch.int32, device=dev)
         for i in range(steps):
             out = system.step_device(action, bufs[i & 1])
             bufs[i & 1] = out
+            flags |= out['flags']
             if learning_time < steps:
                 self.update_control(state, action, out['labels'], hits_out=hits)
             nxt = torch.empty_like(action)
@@ -320,6 +342,7 @@ class DeviceKBRLControl:
             adjusted_actions[i] = self.adjusted
             hits_history[i] = hits
         torch.cuda.synchronize(dev)
+        _report_flags(self, flags.cpu().numpy().view(np.uint32), self.learners)
         t = lambda x: x.transpose(0, 1).cpu().numpy()
         return {'reward': t(reward_history), 'resources': t(resources_history), 'hits': hits_history.permute(1, 2, 0).cpu().numpy(),
                 'adjusted': t(adjusted_actions), 'SLA': t(SLA_history), 'violation': t(violation_history)}

@@ -73,6 +73,7 @@ class BatchedReportWrapper:
         self._out = None
         self._prbs = torch.zeros((self.n_envs, self.n_slices), dtype=torch.int32, device=self.device)
         self.obs = torch.zeros((self.n_envs, self.n_variables), dtype=torch.float32, device=self.device)
+        self._flags = torch.zeros(self.n_envs, dtype=torch.int32, device=self.device)   # OR of the env's RS_FLAG_* bits over all steps
         self.reset_history()
 
     # ------------------------------------------------------------------ histories (wrapper.py:57-60)
@@ -94,6 +95,12 @@ class BatchedReportWrapper:
     @property
     def action_history(self):
         return self._action.transpose(0, 1).cpu().numpy()
+
+    @property
+    def flags_seen(self):
+        """OR of the per-env deviation flags (RS_FLAG_* in include/ranslice_b200.h: UE / burst / mMTC backlog caps, clamped
+        actions) over every step so far, uint32 [N].  Non-zero means that env left the reference's trajectory at a cap."""
+        return self._flags.cpu().numpy().view(np.uint32)
 
     # ------------------------------------------------------------------ gym-like API
     def reset(self):
@@ -132,10 +139,11 @@ class BatchedReportWrapper:
             _lib.check(self._L.rs_wrap_record_device(_ptr(out['violations']), _ptr(out['reward']), _ptr(prbs), self.n_envs,
                                                      self.n_slices, self.step_counter, _ptr(self._violation),
                                                      _ptr(self._reward), _ptr(self._action), st))
+        self._flags |= out['flags']
         self.step_counter += 1
         if self.step_counter % self.control_steps == 0:
             self.save_results()
-        return self.obs, out['reward'], False, {0: 0}
+        return self.obs, out['reward'], False, {0: 0, 'flags': out['flags']}        # (the reference's info is {0: 0})
 
     # ------------------------------------------------------------------ result files (wrapper.py:119-134)
     def _file(self, e):

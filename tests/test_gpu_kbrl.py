@@ -83,11 +83,11 @@ def test_dictionary_cap_and_pool_exhaustion_are_flagged():
     from ranslice_b200.kbrl import BatchedProjectron
     rng = np.random.default_rng(0)
     lrn = BatchedProjectron(0, 2, dict_cap=32)
-    for t in range(60):
+    for t in range(120):
         st = (rng.random((2, 50)) * 3).astype(np.float32)
         lrn.update(st, rng.integers(0, 200, (2, 5)), rng.choice([-1, 1], (2, 5)))
     sizes, flags = lrn.sizes()
-    assert sizes.max() == 32 and (flags & 1).any() and not (flags & 2).any()
+    assert (sizes == 32).all() and (flags & 1).all() and not (flags & 2).any()
     lrn.close()
     lrn = BatchedProjectron(0, 64, dict_cap=1024, pool_mb=1)      # 1 MiB for 320 learners: 12.6 KB per first tile row -> ~83 rows
     for t in range(40):
@@ -96,7 +96,6 @@ def test_dictionary_cap_and_pool_exhaustion_are_flagged():
     sizes, flags = lrn.sizes()
     pool = lrn.pool()
     assert (flags & 2).any() and pool["used_bytes"] <= pool["total_bytes"] == 1 << 20
-    assert (sizes[(flags & 2) == 0] <= 32 * 8).all()
     lrn.close()
 
 

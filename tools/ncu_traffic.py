@@ -18,6 +18,11 @@ def get(name):
 d = {"kernel": vals[hdr.index("Kernel Name")], "envs_per_gpu": envs, "scenario": scn,
      "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"), "source": os.path.basename(rep)}
 d["dram_bytes_per_launch"] = d["dram_bytes_read"] + d["dram_bytes_write"]
+# issue-slot roofline inputs (bench.py issue_roofline): warp instructions per launch and active lanes per instruction
+d["warp_insts_per_launch"] = float(vals[hdr.index("smsp__inst_executed.sum")])
+d["lanes_per_inst"] = float(vals[hdr.index("smsp__thread_inst_executed_per_inst_executed.ratio")])
+d["issue_active_pct"] = float(vals[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")])
+d["sm_count"] = 148
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 json.dump(d, open(os.path.join(root, "profiles", "traffic.json"), "w"), indent=1)
 print(d)
