@@ -59,9 +59,12 @@ namespace kb {
 #ifndef KB_GROUP_PREDICT_BIG
 #define KB_GROUP_PREDICT_BIG 128
 #endif
+#ifndef KB_GROUP_UPDATE_BIG
+#define KB_GROUP_UPDATE_BIG 1024     // large dictionaries: the K^-1 mat-vec / extension stream megabytes, one CTA per SM pulls them with every lane
+#endif
 constexpr size_t GROUP_SMEM_PER_LANDMARK = 5 * sizeof(double) + sizeof(float4);   // base, coeff, last coord, k, d*, fp32 copy
 template <int G> struct Cfg {
-    static_assert(G == 32 || G == 64 || G == 128 || G == 256, "threads per learner: 32, 64, 128 or 256");
+    static_assert(G == 32 || G == 64 || G == 128 || G == 256 || G == 512 || G == 1024, "threads per learner: 32 .. 1024");
     static constexpr int THREADS = G < 128 ? 128 : G;        // threads per block
     static constexpr int GROUPS = THREADS / G;               // learners per block
 };
@@ -80,6 +83,7 @@ constexpr int ROW_HDR = TILE * MAX_DIM + TILE;         // doubles ahead of the t
 constexpr int MAX_CAP = 2048;                          // landmarks per learner the staging in shared memory can hold
 constexpr int SMALL_CAP = 256;                         // staging capacity of the first (small-dictionary) update launch
 constexpr int SMALL_CAP_PREDICT = 128;                 // dictionaries up to this size are scanned by one warp each
+constexpr int MID_CAP_PREDICT = 512;                   // ... up to this size by a 128-thread group with a 20 KB staging area
 __host__ __device__ inline unsigned long long row_doubles(int I) { return (unsigned long long)ROW_HDR + (unsigned long long)(I + 1) * TILE_ELEMS; }
 
 constexpr int PEND_FRESH = -1, PEND_DONE = -2;         // State::pend: >= 0 = resume the augmentation loop at this allocation
@@ -98,6 +102,10 @@ struct State {
     uint32_t *flags;                 // [L]
     unsigned long long *updates;     // [1]
     int *pend;                       // [L] hand-over between the two update launches of a step (small / large dictionaries)
+    int *big_list;                   // [L] learners handed to the large-dictionary update launch of this step ...
+    int *big_ctl;                    // [2] ... their count and the work cursor of that (persistent) launch
+    int *pred_list;                  // [2][L] learners of the select_action scan with a mid-size / large dictionary ...
+    int *pred_ctl;                   // [4] ... {mid count, mid cursor, large count, large cursor}
     uint32_t *tie_ctr;               // [L] draws taken from the learner's tie-break stream
     int *max_d;                      // [1] largest dictionary seen
     uint32_t k0, k1, env0;           // tie-break stream: Philox key = seed, counter = (n, STREAM_KBRL, slice, env0 + env)
@@ -130,14 +138,17 @@ __device__ __forceinline__ double base_dist(const double *l, const double *x, in
 }
 
 // shared-memory slice of one group: tile-row pointers of its learner, then the staged dictionary
+constexpr size_t PREDICT_SMEM_PER_LANDMARK = 3 * sizeof(double) + sizeof(float4);  // the scan needs no k / d* planes
+template <bool UPDATE>
 __device__ __forceinline__ void carve(unsigned char *raw, int capS, int tmax, int group, double **&rowp, double *&base, double *&cf,
                                       double *&ll, double *&kf, double *&ds, float4 *&fast) {
     const size_t rowp_bytes = ((size_t)tmax * sizeof(double *) + 15) & ~size_t(15);     // the float4 plane behind it needs 16-byte alignment
-    unsigned char *p0 = raw + (size_t)group * (rowp_bytes + (size_t)capS * GROUP_SMEM_PER_LANDMARK);
+    unsigned char *p0 = raw + (size_t)group * (rowp_bytes + (size_t)capS * (UPDATE ? GROUP_SMEM_PER_LANDMARK : PREDICT_SMEM_PER_LANDMARK));
     rowp = reinterpret_cast<double **>(p0);
     double *p = reinterpret_cast<double *>(p0 + rowp_bytes);
-    base = p; cf = base + capS; ll = cf + capS; kf = ll + capS; ds = kf + capS;
-    fast = reinterpret_cast<float4 *>(ds + capS);            // [capS] fp32 copy of the staged dictionary (guarded fast path)
+    base = p; cf = base + capS; ll = cf + capS;
+    kf = UPDATE ? ll + capS : nullptr; ds = UPDATE ? kf + capS : nullptr;
+    fast = reinterpret_cast<float4 *>(UPDATE ? ds + capS : ll + capS);   // [capS] fp32 copy of the staged dictionary (guarded fast path)
 }
 // per-group scalars
 struct GroupVars { double xs[MAX_DIM]; double delta, fa0; unsigned long long minb; int first, D, sf, ok; };
@@ -249,24 +260,14 @@ __device__ __forceinline__ void load_rows(const State &kb, int l, int D, double 
 }
 
 // ---------------------------------------------------------------------------------------------
-// select_action scan (kbrl_control.py:54-61): first allocation whose prediction is +1.  big == 0: dictionaries of at most
-// capS landmarks; big == 1: the larger ones (one wider group per learner).  A candidate with f == 0 exactly draws its
-// prediction from the tie-break stream, in scan order.
+// select_action scan (kbrl_control.py:54-61) of one learner: first allocation whose prediction is +1.  A candidate with
+// f == 0 exactly draws its prediction from the tie-break stream, in scan order.
 template <int GROUP>
-__global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const State kb, const int capS, const int big,
-                                                                      const float *__restrict__ state, int32_t *first_pos) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
-    __shared__ GroupVars gv[GROUPS];
-    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
-    const int l = blockIdx.x * GROUPS + group;
-    if (l >= kb.L) return;                                    // whole group
-    const int D = kb.D[l];
-    if (big ? D <= SMALL_CAP_PREDICT : D > SMALL_CAP_PREDICT) return;     // the other launch scans this learner
+__device__ void predict_learner(const State &kb, const int capS, const int l, const int D, const float *__restrict__ state,
+                                int32_t *first_pos, unsigned char *raw, GroupVars &g, const int group, const int gt) {
     double **rowp, *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
-    GroupVars &g = gv[group];
+    carve<false>(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
     const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s];
     if (gt < d - 1) g.xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
     if (gt == 0) g.first = 1 << 30;
@@ -298,6 +299,49 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const Stat
     }
 }
 
+// Three launches per scan, by dictionary size: one warp per learner up to SMALL_CAP_PREDICT landmarks (most learners for
+// the first ~1000 steps); the others are listed by that kernel and scanned by two persistent launches with wider groups
+// and larger staging areas (mid: up to MID_CAP_PREDICT, large: up to dict_cap).
+template <int GROUP>
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS) predict_kernel(const State kb, const int capS, const float *__restrict__ state,
+                                                                      int32_t *first_pos) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
+    __shared__ GroupVars gv[GROUPS];
+    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+    const int l = blockIdx.x * GROUPS + group;
+    if (l >= kb.L) return;                                    // whole group
+    const int D = kb.D[l];
+    if (D > capS) {                                           // listed for the mid / large launch
+        if (gt == 0) {
+            const int which = D > MID_CAP_PREDICT;
+            kb.pred_list[(size_t)which * kb.L + atomicAdd(&kb.pred_ctl[2 * which], 1)] = l;
+        }
+        return;
+    }
+    predict_learner<GROUP>(kb, capS, l, D, state, first_pos, raw, gv[group], group, gt);
+}
+template <int GROUP>
+__global__ void __launch_bounds__(GROUP) predict_list_kernel(const State kb, const int capS, const int which,
+                                                             const float *__restrict__ state, int32_t *first_pos) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    __shared__ GroupVars g;
+    __shared__ int s_idx;
+    const int *list = kb.pred_list + (size_t)which * kb.L;
+    int *ctl = kb.pred_ctl + 2 * which;
+    const int count = ctl[0];
+    for (;;) {
+        if (threadIdx.x == 0) s_idx = atomicAdd(&ctl[1], 1);
+        __syncthreads();
+        const int idx = s_idx;
+        __syncthreads();
+        if (idx >= count) return;
+        const int l = list[idx];
+        predict_learner<GROUP>(kb, capS, l, kb.D[l], state, first_pos, raw, g, 0, threadIdx.x);
+        __syncthreads();
+    }
+}
+
 // d* = K^-1 k for the staged k (kf): thread i sums row i of the symmetric matrix in index order -- row i of the tiles
 // left of the diagonal, then column i of the diagonal tile and of the tiles below it (K^-1[i][j] == K^-1[j][i]).
 template <int GROUP>
@@ -309,7 +353,7 @@ __device__ __forceinline__ void kinv_matvec(double *const *rowp, int D, const do
         for (int J = 0; J < I; ++J) {
             const double2 *p = reinterpret_cast<const double2 *>(rowI + (size_t)J * TILE_ELEMS);
             const double *k = kf + J * TILE;
-#pragma unroll 4
+#pragma unroll 8
             for (int c = 0; c < TILE / 2; ++c) {
                 const double2 v = p[c];
                 acc += v.x * k[2 * c];
@@ -320,7 +364,7 @@ __device__ __forceinline__ void kinv_matvec(double *const *rowp, int D, const do
             const double *q = rowp[J] + ROW_HDR + (size_t)I * TILE_ELEMS + r;
             const double *k = kf + J * TILE;
             const int nj = min(TILE, D - J * TILE);
-#pragma unroll 4
+#pragma unroll 8
             for (int jr = 0; jr < nj; ++jr) acc += q[jr * TILE] * k[jr];
         }
         ds[i] = acc;
@@ -363,30 +407,23 @@ __device__ __forceinline__ double *alloc_row(const State &kb, int l, int I) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Projectron part of update_control (+ the E-learner when ctl.acc != nullptr).  Two launches per step: stage 0 stages at
-// most capS = SMALL_CAP landmarks (14 KB of shared memory, four learners per SM... per 256 threads) and hands a learner
-// whose dictionary reaches that size to stage 1 (capS = cap), which starts it (pend == PEND_FRESH) or resumes its
-// augmentation loop at allocation `pend`.
+// Projectron part of update_control (+ the E-learner when ctl.acc != nullptr) for one learner.  Two launches per step:
+// the first (hand_over = true) stages at most capS = SMALL_CAP landmarks (14 KB of shared memory per learner, 256 threads)
+// and lists a learner whose dictionary has reached that size for the second, which starts it (pend == PEND_FRESH) or
+// resumes its augmentation loop at allocation `pend` with capS = dict_cap and 1024 threads.
 template <int GROUP>
-__global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) update_kernel(const State kb, const int capS, const int stage,
-                                                         const float *__restrict__ state,
-                                                         const int32_t *__restrict__ action,
-                                                         const int32_t *__restrict__ labels, int32_t *y_pred,
-                                                         const Control ctl, int32_t *hits) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
-    __shared__ GroupVars gv[GROUPS];
-    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
-    const int l = blockIdx.x * GROUPS + group;
-    if (l >= kb.L) return;                                    // whole group
-    const int pend = kb.pend[l];                              // stage 0: PEND_FRESH for every learner (set by the host)
-    if (stage && pend == PEND_DONE) return;
+__device__ void update_learner(const State &kb, const int capS, const bool hand_over, const int l, const int pend,
+                               const float *__restrict__ state, const int32_t *__restrict__ action,
+                               const int32_t *__restrict__ labels, int32_t *y_pred, const Control &ctl, int32_t *hits,
+                               unsigned char *raw, GroupVars &g, const int group, const int gt) {
     int D = kb.D[l];
-    if (!stage && D >= capS) return;                          // large dictionary: stage 1 takes it (pend stays PEND_FRESH)
+    if (hand_over && D >= capS) {                             // large dictionary: the second launch takes it from the start
+        if (gt == 0) { kb.pend[l] = PEND_FRESH; kb.big_list[atomicAdd(&kb.big_ctl[0], 1)] = l; }
+        return;
+    }
     double **rowp, *base, *cf, *ll, *kf, *ds;
     float4 *fast;
-    carve(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
-    GroupVars &g = gv[group];
+    carve<true>(raw, capS, kb.tmax, group, rowp, base, cf, ll, kf, ds, fast);
     double *xs = g.xs;
     const int env = l / kb.S, s = l - env * kb.S, d = kb.dims[s], n = kb.n_prbs;
     if (gt < d - 1) xs[gt] = (double)state[(size_t)env * kb.V + kb.offs[s] + gt];
@@ -455,7 +492,7 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
         const int key = g.first;
         if (key == (1 << 30)) break;
         const int astar = key >> 1;
-        if (!stage && D >= capS) { handed_over = astar; break; }   // staging is full: stage 1 resumes at astar
+        if (hand_over && D >= capS) { handed_over = astar; break; }   // staging is full: the second launch resumes at astar
         // ---- Projectron.update at x = [s, astar / n] (projectron.py:41-60); its predict drew a tie-break if f == 0
         const double xa = (double)astar / (double)n;
         ++n_updates;
@@ -578,9 +615,44 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
     if (gt == 0) {
         kb.D[l] = D;
         kb.tie_ctr[l] = tie_n;
-        kb.pend[l] = handed_over >= 0 ? handed_over : PEND_DONE;
+        if (handed_over >= 0) { kb.pend[l] = handed_over; kb.big_list[atomicAdd(&kb.big_ctl[0], 1)] = l; }
         if (n_updates) atomicAdd(kb.updates, (unsigned long long)n_updates);
         if (D > *kb.max_d) atomicMax(kb.max_d, D);
+    }
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) update_kernel(const State kb, const int capS, const int hand_over,
+                                                         const float *__restrict__ state,
+                                                         const int32_t *__restrict__ action,
+                                                         const int32_t *__restrict__ labels, int32_t *y_pred,
+                                                         const Control ctl, int32_t *hits) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    constexpr int GROUPS = Cfg<GROUP>::GROUPS;
+    __shared__ GroupVars gv[GROUPS];
+    const int group = threadIdx.x / GROUP, gt = threadIdx.x % GROUP;
+    const int l = blockIdx.x * GROUPS + group;
+    if (l >= kb.L) return;                                    // whole group
+    update_learner<GROUP>(kb, capS, hand_over != 0, l, PEND_FRESH, state, action, labels, y_pred, ctl, hits, raw, gv[group], group, gt);
+}
+// the learners listed by update_kernel, one CTA at a time (persistent: the list is short and its entries are uneven)
+template <int GROUP>
+__global__ void __launch_bounds__(GROUP, 1) update_list_kernel(const State kb, const int capS, const float *__restrict__ state,
+                                                               const int32_t *__restrict__ action, const int32_t *__restrict__ labels,
+                                                               int32_t *y_pred, const Control ctl, int32_t *hits) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    __shared__ GroupVars g;
+    __shared__ int s_idx;
+    const int count = kb.big_ctl[0];
+    for (;;) {
+        if (threadIdx.x == 0) s_idx = atomicAdd(&kb.big_ctl[1], 1);
+        __syncthreads();
+        const int idx = s_idx;
+        __syncthreads();
+        if (idx >= count) return;
+        const int l = kb.big_list[idx];
+        update_learner<GROUP>(kb, capS, false, l, kb.pend[l], state, action, labels, y_pred, ctl, hits, raw, g, 0, threadIdx.x);
+        __syncthreads();
     }
 }
 
@@ -635,7 +707,8 @@ struct kb_handle {
     kb::State st;
     kb::Control ctl;
     int cap_small;                           // staging capacity of the small-dictionary update launch
-    size_t smem_update_small, smem_update_big, smem_predict_small, smem_predict_big;
+    int sm_count;
+    size_t smem_update_small, smem_update_big, smem_predict_small, smem_predict_mid, smem_predict_big;
     cudaStream_t stream;
     float *d_state;
     int32_t *d_action, *d_labels, *d_out;
@@ -647,7 +720,8 @@ struct kb_handle {
 // error text is shared with ranslice_cabi.cu through rs_set_error
 extern "C" void rs_set_error(const char *msg);
 namespace {
-constexpr int UG = kb::Cfg<KB_GROUP_UPDATE>::GROUPS, PG = kb::Cfg<KB_GROUP_PREDICT>::GROUPS, PGB = kb::Cfg<KB_GROUP_PREDICT_BIG>::GROUPS;
+constexpr int UG = kb::Cfg<KB_GROUP_UPDATE>::GROUPS, PG = kb::Cfg<KB_GROUP_PREDICT>::GROUPS;
+constexpr int PREDICT_MID_GROUP = KB_GROUP_PREDICT_BIG, PREDICT_BIG_GROUP = 256;
 int kfail(int code, const std::string &m) { rs_set_error(m.c_str()); return code; }
 }
 #define KCU(call)                                                                                  \
@@ -673,6 +747,11 @@ static int kb_create_impl(kb_handle *h, const kb_config *cfg, const int32_t *dim
     KCU(cudaMalloc(&st.updates, sizeof(unsigned long long)));
     KCU(cudaMalloc(&st.cursor, sizeof(unsigned long long)));
     KCU(cudaMalloc(&st.max_d, sizeof(int)));
+    KCU(cudaMalloc(&st.big_list, L * sizeof(int)));
+    KCU(cudaMalloc(&st.big_ctl, 2 * sizeof(int)));
+    KCU(cudaMalloc(&st.pred_list, 2 * L * sizeof(int)));
+    KCU(cudaMalloc(&st.pred_ctl, 4 * sizeof(int)));
+    KCU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
     {   // dictionary pool: what every learner would need at full size, capped by pool_mb or (by default) 70 % of the free memory
         unsigned long long full = 0;
         for (int I = 0; I < st.tmax; ++I) full += kb::row_doubles(I);
@@ -694,12 +773,15 @@ static int kb_create_impl(kb_handle *h, const kb_config *cfg, const int32_t *dim
     h->cap_small = std::min(cap, kb::SMALL_CAP);
     const size_t rowp = ((size_t)st.tmax * sizeof(double *) + 15) & ~size_t(15);
     h->smem_update_small = (size_t)UG * (rowp + (size_t)h->cap_small * kb::GROUP_SMEM_PER_LANDMARK);
-    h->smem_update_big = (size_t)UG * (rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK);
-    h->smem_predict_small = (size_t)PG * (rowp + (size_t)std::min(cap, kb::SMALL_CAP_PREDICT) * kb::GROUP_SMEM_PER_LANDMARK);
-    h->smem_predict_big = (size_t)PGB * (rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK);
-    KCU(cudaFuncSetAttribute(kb::update_kernel<KB_GROUP_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update_big));
+    h->smem_update_big = rowp + (size_t)cap * kb::GROUP_SMEM_PER_LANDMARK;
+    h->smem_predict_small = (size_t)PG * (rowp + (size_t)std::min(cap, kb::SMALL_CAP_PREDICT) * kb::PREDICT_SMEM_PER_LANDMARK);
+    h->smem_predict_mid = rowp + (size_t)std::min(cap, kb::MID_CAP_PREDICT) * kb::PREDICT_SMEM_PER_LANDMARK;
+    h->smem_predict_big = rowp + (size_t)cap * kb::PREDICT_SMEM_PER_LANDMARK;
+    KCU(cudaFuncSetAttribute(kb::update_kernel<KB_GROUP_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update_small));
+    KCU(cudaFuncSetAttribute(kb::update_list_kernel<KB_GROUP_UPDATE_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_update_big));
     KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_small));
-    KCU(cudaFuncSetAttribute(kb::predict_kernel<KB_GROUP_PREDICT_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_big));
+    KCU(cudaFuncSetAttribute(kb::predict_list_kernel<PREDICT_MID_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_mid));
+    KCU(cudaFuncSetAttribute(kb::predict_list_kernel<PREDICT_BIG_GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_predict_big));
     return kb_reset(h);
 }
 
@@ -752,7 +834,8 @@ int kb_destroy(kb_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(h->st.D); cudaFree(h->st.rows); cudaFree(h->st.pool); cudaFree(h->st.flags); cudaFree(h->st.pend); cudaFree(h->st.tie_ctr);
-    cudaFree(h->st.cursor); cudaFree(h->st.max_d);
+    cudaFree(h->st.cursor); cudaFree(h->st.max_d); cudaFree(h->st.big_list); cudaFree(h->st.big_ctl); cudaFree(h->st.pred_list);
+    cudaFree(h->st.pred_ctl);
     cudaFree(h->ctl.acc); cudaFree(h->ctl.sec); cudaFree(h->ctl.margins); cudaFree(h->ctl.adjusted); cudaFree(h->ctl.action);
     cudaFree(h->ctl.first);
     cudaFree(h->st.updates); cudaFree(h->d_state); cudaFree(h->d_action); cudaFree(h->d_labels); cudaFree(h->d_out); cudaFree(h->d_gather);
@@ -761,28 +844,35 @@ int kb_destroy(kb_handle *h) {
     return RS_OK;
 }
 
-// the two launches of an update step: dictionaries below cap_small with a small staging area, then the rest
+// the two launches of an update step: dictionaries below cap_small with a small staging area (it lists the others and
+// those that outgrow it), then a persistent launch over that list with dict_cap staging and 1024 threads per learner
 static int launch_update(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels, int32_t *d_y_pred,
                          const kb::Control &ctl, int32_t *d_hits, cudaStream_t st) {
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    KCU(cudaMemsetAsync(h->st.pend, 0xFF, (size_t)h->st.L * sizeof(int), st));            // PEND_FRESH
+    KCU(cudaMemsetAsync(h->st.big_ctl, 0, 2 * sizeof(int), st));
     const int blocks = (h->st.L + UG - 1) / UG, threads = kb::Cfg<KB_GROUP_UPDATE>::THREADS;
-    if (h->st.cap > h->cap_small) {                            // (with dict_cap <= SMALL_CAP the second launch alone does everything)
-        kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, 0, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+    const int two = h->st.cap > h->cap_small;                  // (with dict_cap <= SMALL_CAP the first launch does everything)
+    kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, two, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+    h->launches += 1;
+    if (two) {
+        kb::update_list_kernel<KB_GROUP_UPDATE_BIG><<<h->sm_count, KB_GROUP_UPDATE_BIG, h->smem_update_big, st>>>(h->st, h->st.cap, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
         h->launches += 1;
     }
-    kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_big, st>>>(h->st, h->st.cap, 1, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
-    h->launches += 1;
     KCU(cudaGetLastError());
     return RS_OK;
 }
 
 static int launch_predict(kb_handle *h, const float *d_state, int32_t *d_first, cudaStream_t st) {
-    const int cs = std::min(h->st.cap, kb::SMALL_CAP_PREDICT);
-    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict_small, st>>>(h->st, cs, 0, d_state, d_first);
+    const int cs = std::min(h->st.cap, kb::SMALL_CAP_PREDICT), cm = std::min(h->st.cap, kb::MID_CAP_PREDICT);
+    KCU(cudaMemsetAsync(h->st.pred_ctl, 0, 4 * sizeof(int), st));
+    kb::predict_kernel<KB_GROUP_PREDICT><<<(h->st.L + PG - 1) / PG, kb::Cfg<KB_GROUP_PREDICT>::THREADS, h->smem_predict_small, st>>>(h->st, cs, d_state, d_first);
     h->launches += 1;
     if (h->st.cap > cs) {
-        kb::predict_kernel<KB_GROUP_PREDICT_BIG><<<(h->st.L + PGB - 1) / PGB, kb::Cfg<KB_GROUP_PREDICT_BIG>::THREADS, h->smem_predict_big, st>>>(h->st, h->st.cap, 1, d_state, d_first);
+        kb::predict_list_kernel<PREDICT_MID_GROUP><<<8 * h->sm_count, PREDICT_MID_GROUP, h->smem_predict_mid, st>>>(h->st, cm, 0, d_state, d_first);
+        h->launches += 1;
+    }
+    if (h->st.cap > cm) {
+        kb::predict_list_kernel<PREDICT_BIG_GROUP><<<2 * h->sm_count, PREDICT_BIG_GROUP, h->smem_predict_big, st>>>(h->st, h->st.cap, 1, d_state, d_first);
         h->launches += 1;
     }
     KCU(cudaGetLastError());

@@ -71,48 +71,64 @@ __global__ void __launch_bounds__(128) mmtc_scan_kernel(const __grid_constant__ 
 }
 
 // The same scan for U % 4 == 0 (every BASELINE size): a thread owns FOUR consecutive units and reads their next-arrival
-// words with one 128-bit load per device, eight devices (128 bytes per thread) in flight -- the scalar version above kept
-// five 4-byte loads in flight and reached 1.7 TB/s, 26 % of the HBM peak, long-scoreboard bound
-// (profiles/r01l_mmtc_scan_65536_full.txt).
+// words with one 128-bit load per device, ten devices (160 bytes per thread) in flight.  The scalar version above kept
+// five 4-byte loads in flight and reached 1.7 TB/s, 26 % of the HBM peak (profiles/r01l_mmtc_scan_65536_full.txt); a first
+// 128-bit version that handled an arrival where it found it was no faster (147 us): about ten lanes per warp-iteration find
+// one, and each handler is a chain of L2 round trips (atomicAdd -> store, period load -> store) executed under divergence.
+// So the scan only records WHERE arrivals are (one 50-bit mask per unit), and the arrivals are handled after the
+// loop: one atomicAdd per unit reserves the list entries, then the independent loads / stores of all arrivals overlap.
 constexpr int MTC_STRIPS_V4 = 20;  // 50 devices per strip
-__device__ __forceinline__ void mmtc_arrival(const StepParams &p, const MmtcState &st, int U, int u, int i, uint32_t d, bool &overflow) {
-    const uint32_t k = atomicAdd(&st.arr_n[u], 1u);
-    if (k < (uint32_t)MTC_MAX_ARR) st.arr[(size_t)k * U + u] = (d << 16) | (uint32_t)i;
-    else overflow = true;
-    st.next_abs[(size_t)i * U + u] += (uint32_t)c_PERIOD_SET[st.period_ix[(size_t)i * U + u]];      // period >= 1000 > slots
-}
 __global__ void __launch_bounds__(128) mmtc_scan_kernel_v4(const __grid_constant__ StepParams p,
                                                            const __grid_constant__ MmtcState st) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int U = st.U;
     if (4 * q >= U) return;
     constexpr int PER = N_MTC_DEV / MTC_STRIPS_V4;
-    static_assert(PER * MTC_STRIPS_V4 == N_MTC_DEV && PER % 10 == 0, "strip geometry");
+    static_assert(PER * MTC_STRIPS_V4 == N_MTC_DEV && PER % 10 == 0 && PER <= 64, "strip geometry");
     const int i0 = blockIdx.y * PER;
     const uint4 t0 = *reinterpret_cast<const uint4 *>(st.time + 4 * q);
     const uint32_t slots = (uint32_t)p.slots;
     const uint4 *row = reinterpret_cast<const uint4 *>(st.next_abs + (size_t)i0 * U) + q;
     const size_t stride = (size_t)U / 4;
-    bool overflow = false;
+    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;           // arrival masks of the four units over the strip
 #pragma unroll 1
     for (int i = 0; i < PER; i += 10) {
         uint4 v[10];
 #pragma unroll
-        for (int j = 0; j < 10; ++j) v[j] = __ldcs(row + (size_t)(i + j) * stride);     // streamed once per step: evict first
+        for (int j = 0; j < 10; ++j) v[j] = __ldg(row + (size_t)(i + j) * stride);
 #pragma unroll
-        for (int j = 0; j < 10; ++j) {
-            const uint32_t dx = v[j].x - t0.x, dy = v[j].y - t0.y, dz = v[j].z - t0.z, dw = v[j].w - t0.w;   // wrap-safe: periods << 2^31
-            if (((dx - 1u < slots) | (dy - 1u < slots)) | ((dz - 1u < slots) | (dw - 1u < slots))) {
-                const int dev = i0 + i + j;
-                if (dx - 1u < slots) mmtc_arrival(p, st, U, 4 * q + 0, dev, dx, overflow);
-                if (dy - 1u < slots) mmtc_arrival(p, st, U, 4 * q + 1, dev, dy, overflow);
-                if (dz - 1u < slots) mmtc_arrival(p, st, U, 4 * q + 2, dev, dz, overflow);
-                if (dw - 1u < slots) mmtc_arrival(p, st, U, 4 * q + 3, dev, dw, overflow);
-            }
+        for (int j = 0; j < 10; ++j) {                           // d in [1, slots]  <=>  d - 1 < slots (wrap-safe: periods << 2^31)
+            const unsigned long long bit = 1ull << (i + j);
+            m0 |= (v[j].x - t0.x - 1u < slots) ? bit : 0ull;
+            m1 |= (v[j].y - t0.y - 1u < slots) ? bit : 0ull;
+            m2 |= (v[j].z - t0.z - 1u < slots) ? bit : 0ull;
+            m3 |= (v[j].w - t0.w - 1u < slots) ? bit : 0ull;
         }
     }
-    if (overflow)                                                // (which of the four units overflowed is not tracked: flag their envs)
-        for (int k = 0; k < 4; ++k) if (st.arr_n[4 * q + k] > (uint32_t)MTC_MAX_ARR) atomicOr(p.flags_acc + (4 * q + k) / p.n_mmtc, 16u);
+    if ((m0 | m1 | m2 | m3) == 0ull) return;
+    const unsigned long long mk[4] = {m0, m1, m2, m3};
+    const uint32_t tt[4] = {t0.x, t0.y, t0.z, t0.w};
+    uint32_t base[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) base[k] = mk[k] ? atomicAdd(&st.arr_n[4 * q + k], (uint32_t)__popcll(mk[k])) : 0u;   // independent: in flight together
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        unsigned long long m = mk[k];
+        const int u = 4 * q + k;
+        uint32_t pos = base[k];
+        bool overflow = false;
+        while (m) {
+            const int i = i0 + __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const size_t ix = (size_t)i * U + u;
+            const uint32_t nx = st.next_abs[ix];                 // (L1 / L2 hit: read a moment ago)
+            if (pos < (uint32_t)MTC_MAX_ARR) st.arr[(size_t)pos * U + u] = ((nx - tt[k]) << 16) | (uint32_t)i;
+            else overflow = true;
+            ++pos;
+            st.next_abs[ix] = nx + (uint32_t)c_PERIOD_SET[st.period_ix[ix]];      // period >= 1000 > slots
+        }
+        if (overflow) atomicOr(p.flags_acc + u / p.n_mmtc, 16u);
+    }
 }
 
 // Phase 2: the 50 slots of one mMTC slice.  Thread per unit.
