@@ -128,7 +128,7 @@ int rs_get_profile(rs_handle *h, double *ms6, uint64_t *steps);
 
 /* guard-band validation (tests): with debug_check on, the default eMBB kernel evaluates the exact fp64
  * expression next to every fast-path decision.  rs_get_diag: out[0] max |p64 - p32| / eps over
- * reception decisions, out[1] max |mean64 - mean_fast| / 1e-6 over SNR estimates, out[2] decisions
+ * reception decisions, out[1] max |mean64 - mean_fast| / guard over SNR estimates (guard = 2.5 x the fixed-point representation error), out[2] decisions
  * that would have differed (must be 0), out[3] / out[4] fp64 re-evaluations taken in the last step
  * (SNR rounding guard / reception guard). */
 int rs_set_debug_check(rs_handle *h, int32_t enable);

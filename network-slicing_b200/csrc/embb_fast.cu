@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
     double a_queue[2] = {0.0, 0.0}, a_snr[2] = {0.0, 0.0};
     unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
     const float Af = (float)tb.A, Bf = (float)tb.B;
+#ifdef RS_WSUM_QUADS
     const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * FIX_ONE) : 0.0;
+#else
+    const double inv_n = n_prbs > 0 ? tb.pre_inv / (double)n_prbs : 0.0;
+#endif
 
     // per-UE scratch of one TTI (local memory, only the first n_ues entries are touched)
     long long qq[K];
@@ -294,14 +298,21 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
                 r.meta = pack_meta((int)(r.meta & 1u), fading, step, index);
                 const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
                 coloff[k] = col_off;
-                const long long isum = window_sum_fix(tb.trace_fix + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
+#ifdef RS_WSUM_QUADS
+                const long long isum = window_sum_fix(tb.trace_fix + col_off, row_base, n_prbs);
                 double mean = (double)isum * inv_n + r.nominal;  // |mean - reference mean| < 2^-25 + few ulp
+                const double guard = SNR_ROUND_GUARD;
+#else
+                const int isum = window_sum_prefix(tb.trace_pre + (fading * N_SAMPLES + index) * PRE_STRIDE, row_base, n_prbs);
+                double mean = (double)isum * inv_n + r.nominal;  // |mean - reference mean| <= 2^-(pre_bits + 1) + few ulp
+                const double guard = tb.pre_guard;
+#endif
                 const double fr = mean - floor(mean);
-                const bool near = fabs(fr - 0.5) < SNR_ROUND_GUARD;         // within the guard of a rounding boundary
+                const bool near = fabs(fr - 0.5) < guard;        // within the guard of a rounding boundary
                 if (near || p.debug_check) {
                     const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, r.nominal);
-                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / SNR_ROUND_GUARD));
+                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / guard));
                     if (near) { mean = exact; ++slow_snr; }
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45

@@ -197,6 +197,20 @@ __device__ __forceinline__ long long window_sum_fix(const int32_t *col, int row0
 }
 #endif
 
+// Window sum from the per-column prefix table (Tables::trace_pre): rows [row0, row0 + n) with row0 < 100, n <= 200, rows
+// wrapping at 100 (channel_models.py:144-148).  E(x) = (x / 100) T + pre[x % 100] with T = pre[100] is the prefix over the
+// wrapped rows, so the sum is E(row0 + n) - E(row0): two loads, plus T when the window wraps.  int32 arithmetic is
+// modular; the true sum fits (checked when the table is built), so the difference is exact.
+__device__ __forceinline__ int window_sum_prefix(const int32_t *pre, int row0, int n) {
+    const int hi = row0 + n;                                 // <= 299
+    const int wraps = (hi >= TRACE_ROWS) + (hi >= 2 * TRACE_ROWS);
+    const int lo_v = __ldg(pre + row0);
+    const int hi_v = __ldg(pre + (hi - wraps * TRACE_ROWS));
+    int sum = hi_v - lo_v;
+    if (wraps) sum += wraps * __ldg(pre + TRACE_ROWS);
+    return sum;
+}
+
 // exact fp64 window mean (same operation order as embb_step.cu); rare
 static __device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
     double sum = 0.0;

@@ -326,7 +326,11 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
     double a_queue_c = 0.0, a_queue_v = 0.0, a_snr_c = 0.0, a_snr_v = 0.0;
     unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;
     const float Af = (float)tb.A, Bf = (float)tb.B;
+#ifdef RS_WSUM_QUADS
     const double inv_n = n_prbs > 0 ? 1.0 / ((double)n_prbs * FIX_ONE) : 0.0;
+#else
+    const double inv_n = n_prbs > 0 ? tb.pre_inv / (double)n_prbs : 0.0;
+#endif
 
     for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
         __syncwarp(warp_mask);
@@ -379,15 +383,22 @@ __global__ void __launch_bounds__(SM_THREADS, WIDE ? RS_WIDE_BLOCKS : RS_SM_BLOC
                 meta = pack_meta(ty, fading, step, index);
                 v.meta[SIX(k)] = meta;
                 const int col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
-                const long long isum = window_sum_fix<WIDE>(tb.trace_fix + col_off, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
                 const double nominal = v.nominal[SIX(k)];
+#ifdef RS_WSUM_QUADS
+                const long long isum = window_sum_fix<WIDE>(tb.trace_fix + col_off, row_base, n_prbs);
                 double mean = (double)isum * inv_n + nominal;    // |mean - reference mean| < 2^-25 + few ulp
+                const double guard = SNR_ROUND_GUARD;
+#else
+                const int isum = window_sum_prefix(tb.trace_pre + (fading * N_SAMPLES + index) * PRE_STRIDE, row_base, n_prbs);
+                double mean = (double)isum * inv_n + nominal;    // |mean - reference mean| <= 2^-(pre_bits + 1) + few ulp
+                const double guard = tb.pre_guard;
+#endif
                 const double fr = mean - floor(mean);
-                const bool near = fabs(fr - 0.5) < SNR_ROUND_GUARD;         // within the guard of a rounding boundary
+                const bool near = fabs(fr - 0.5) < guard;        // within the guard of a rounding boundary
                 if (near || p.debug_check) {
                     const double exact = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, nominal);
-                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / SNR_ROUND_GUARD));
+                    if (p.debug_check) atomic_max_float(st.dbg + 1, (float)(fabs(exact - mean) / guard));
                     if (near) { mean = exact; ++slow_snr; }
                 }
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45

@@ -77,20 +77,22 @@ __global__ void __launch_bounds__(128) mmtc_scan_kernel(const __grid_constant__ 
 // one, and each handler is a chain of L2 round trips (atomicAdd -> store, period load -> store) executed under divergence.
 // So the scan only records WHERE arrivals are (one 50-bit mask per unit), and the arrivals are handled after the
 // loop: one atomicAdd per unit reserves the list entries, then the independent loads / stores of all arrivals overlap.
-constexpr int MTC_STRIPS_V4 = 20;  // 50 devices per strip
+constexpr int MTC_STRIPS_V4 = 10;  // blockIdx.y: two half-strips of 50 devices each (65 536 units: 1280 blocks = one wave of 10 blocks per SM)
 __global__ void __launch_bounds__(128) mmtc_scan_kernel_v4(const __grid_constant__ StepParams p,
                                                            const __grid_constant__ MmtcState st) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int U = st.U;
     if (4 * q >= U) return;
-    constexpr int PER = N_MTC_DEV / MTC_STRIPS_V4;
-    static_assert(PER * MTC_STRIPS_V4 == N_MTC_DEV && PER % 10 == 0 && PER <= 64, "strip geometry");
-    const int i0 = blockIdx.y * PER;
+    constexpr int PER = N_MTC_DEV / MTC_STRIPS_V4 / 2;
+    static_assert(PER * MTC_STRIPS_V4 * 2 == N_MTC_DEV && PER % 10 == 0 && PER <= 64, "strip geometry");
     const uint4 t0 = *reinterpret_cast<const uint4 *>(st.time + 4 * q);
     const uint32_t slots = (uint32_t)p.slots;
-    const uint4 *row = reinterpret_cast<const uint4 *>(st.next_abs + (size_t)i0 * U) + q;
     const size_t stride = (size_t)U / 4;
-    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;           // arrival masks of the four units over the strip
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int i0 = (blockIdx.y * 2 + half) * PER;
+    const uint4 *row = reinterpret_cast<const uint4 *>(st.next_abs + (size_t)i0 * U) + q;
+    unsigned long long m0 = 0, m1 = 0, m2 = 0, m3 = 0;           // arrival masks of the four units over the half-strip
 #pragma unroll 1
     for (int i = 0; i < PER; i += 10) {
         uint4 v[10];
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(128) mmtc_scan_kernel_v4(const __grid_constant
             m3 |= (v[j].w - t0.w - 1u < slots) ? bit : 0ull;
         }
     }
-    if ((m0 | m1 | m2 | m3) == 0ull) return;
+    if ((m0 | m1 | m2 | m3) == 0ull) continue;
     const unsigned long long mk[4] = {m0, m1, m2, m3};
     const uint32_t tt[4] = {t0.x, t0.y, t0.z, t0.w};
     uint32_t base[4];
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(128) mmtc_scan_kernel_v4(const __grid_constant
         }
         if (overflow) atomicOr(p.flags_acc + u / p.n_mmtc, 16u);
     }
+  }
 }
 
 // Phase 2: the 50 slots of one mMTC slice.  Thread per unit.

@@ -47,7 +47,7 @@ struct rs_handle {
     size_t arena_bytes;
     // tables + I/O staging
     double *d_trace;
-    int32_t *d_trace_fix;
+    int32_t *d_trace_fix, *d_trace_pre;
     char *scratch;
     unsigned long long *d_slow_paths;
     int32_t *d_action;
@@ -230,6 +230,36 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
     }
     build_tables(tables, h->tb);
     h->tb.trace = h->d_trace; h->tb.trace_fix = h->d_trace_fix;
+    {   // per-column prefix sums for the PRB-window mean (embb_fastmath.cuh window_sum_prefix): the largest fixed-point scale
+        // that keeps every window sum of up to 300 wrapped rows inside int32, at most 2^22
+        const size_t n_cols = (size_t)3 * rs::N_SAMPLES;
+        double span = 0.0;                                    // max over columns of (max - min) of the prefix over 3 wraps
+        for (size_t c = 0; c < n_cols; ++c) {
+            const double *col = tables->trace + c * rs::TRACE_ROWS;
+            if (std::isnan(col[0])) continue;
+            double acc = 0.0, lo = 0.0, hi = 0.0;
+            for (int r = 0; r < 3 * rs::TRACE_ROWS; ++r) { acc += col[r % rs::TRACE_ROWS]; lo = std::min(lo, acc); hi = std::max(hi, acc); }
+            span = std::max(span, hi - lo);
+        }
+        int bits = 22;
+        while (bits > 8 && (span + 300.0) * std::ldexp(1.0, bits) >= 2147483647.0) --bits;   // + 300: half a unit of rounding per row
+        h->tb.pre_bits = bits; h->tb.pre_inv = std::ldexp(1.0, -bits); h->tb.pre_guard = 2.5 * std::ldexp(1.0, -(bits + 1));
+        std::vector<int32_t> pre(n_cols * rs::PRE_STRIDE, 0);
+        const double scale = std::ldexp(1.0, bits);
+        for (size_t c = 0; c < n_cols; ++c) {
+            const double *col = tables->trace + c * rs::TRACE_ROWS;
+            if (std::isnan(col[0])) continue;
+            uint32_t acc = 0;                                  // modular: only differences of prefixes are used
+            for (int r = 0; r < rs::TRACE_ROWS; ++r) {
+                pre[c * rs::PRE_STRIDE + r] = (int32_t)acc;
+                acc += (uint32_t)(int32_t)std::llrint(col[r] * scale);
+            }
+            pre[c * rs::PRE_STRIDE + rs::TRACE_ROWS] = (int32_t)acc;
+        }
+        CU(cudaMalloc(&h->d_trace_pre, pre.size() * sizeof(int32_t)));
+        CU(cudaMemcpy(h->d_trace_pre, pre.data(), pre.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        h->tb.trace_pre = h->d_trace_pre;
+    }
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
@@ -304,7 +334,7 @@ int rs_destroy(rs_handle *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
+    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->d_trace_pre); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
     cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
     cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
     if (h->mmtc.U) { cudaFree(h->mmtc.arr_n); cudaFree(h->mmtc.arr); }

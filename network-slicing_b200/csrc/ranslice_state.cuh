@@ -11,6 +11,7 @@ constexpr int N_SAMPLES = 10001;   // channel_models.py:165 (time columns incl. 
 constexpr int TRACE_ROWS = 100;    // PRB rows of the trace files; rows >= 100 wrap (channel_models.py:144-148)
 constexpr int N_MTC_DEV = 1000;    // scenario_creator.py:87
 constexpr int MAX_SLICES = 8;
+constexpr int PRE_STRIDE = 104;   // int32 words per column of the prefix table (101 used; 416 bytes = 13 sectors)
 
 // meta word of a UE: bit0 type (0 CBR / 1 VBR), bits1-2 fading trace, bit3 step (+1 -> 1), bits4.. index
 __host__ __device__ inline uint32_t pack_meta(int type, int fading, int step, int index) {
@@ -108,7 +109,11 @@ constexpr int MTC_MAX_ARR = 96;    // arrivals buffered per unit per step (mean 
 
 struct Tables {
     const double *trace;   // [3][N_SAMPLES][TRACE_ROWS] fp64, time-major
-    const int32_t *trace_fix; // same, fixed point round(v * 2^22): exact integer window sums on the fast path
+    const int32_t *trace_fix; // same, fixed point round(v * 2^22): per-PRB values of the MI fast path
+    const int32_t *trace_pre; // [3][N_SAMPLES][PRE_STRIDE] per-column PREFIX sums over the rows of round(v * 2^pre_bits): pre[r] = sum of
+                              // rows < r, pre[100] = the whole column; a PRB-window sum is two or three loads (embb_fastmath.cuh)
+    int pre_bits;             // fractional bits of trace_pre (largest that keeps every window sum of up to 300 rows inside int32; 19 for the shipped traces)
+    double pre_inv, pre_guard; // 2^-pre_bits; rounding guard of the window mean: 2.5 x the representation error 2^-(pre_bits + 1)
     int8_t lut_mcs[256];   // e_snr + 128 -> mcs        (MCSCodeset.mcs_rate_vs_error, channel_models.py:288-295)
     int16_t lut_rate[256]; // e_snr + 128 -> int(158 * rate*order)  (schedulers.py:45)
     double snr_ref[26];    // mcs -> snr_ref

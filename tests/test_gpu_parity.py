@@ -178,8 +178,8 @@ def test_population_statistics_large_batch():
 
 def test_fast_path_guard_bands_hold():
     """debug_check evaluates the exact fp64 expression next to every fast decision of the default
-    kernel: the error bound eps must cover |p64 - p32| (ratio < 1), the fixed-point mean must stay
-    far inside its 1e-6 guard, and no decision may differ."""
+    kernel: the error bound eps must cover |p64 - p32| (ratio < 1), the fixed-point window mean (prefix table, 2^-19
+    units: representation error <= 2^-20) must stay inside its guard of 2.5 x that, and no decision may differ."""
     scn, N, T = 0, 2048, 150
     S, n_prbs = SCN[scn]
     env = make_env(scn, N, 555)
@@ -194,7 +194,7 @@ def test_fast_path_guard_bands_hold():
     print(d, "slow reception paths per env-step: %.4f" % (slow / (N * T)))
     assert d["decision_mismatches"] == 0
     assert d["max_p_err_over_eps"] < 0.6, d
-    assert d["max_mean_err_over_guard"] < 0.1, d
+    assert d["max_mean_err_over_guard"] < 0.5, d
     assert slow / (N * T) < 1.0          # ~500 reception draws per env-step: well under 1 % re-evaluated
     env.close()
 
