@@ -48,7 +48,9 @@ typedef struct rs_config {
     int32_t max_ues;        /* live-UE cap per eMBB slice (<= 32); 0 -> default 16 */
     int32_t max_bursts;     /* active-burst cap per VBR UE (<= 16); 0 -> default 8 */
     int32_t mtc_queue_cap;  /* mMTC backlog cap per slice; 0 -> default 128 */
-    int32_t kernel_variant; /* 0 = default (fastest validated); see DESIGN.md */
+    int32_t kernel_variant; /* 0 = default: the shared-memory kernel (one lane per unit), or the warp-per-unit kernel while the batch
+                             *     leaves the GPU underfilled; 1 all-fp64 anchor kernel; 2 general kernel; 3 warp-per-unit kernel;
+                             *     4 shared-memory kernel whatever the batch size.  Results do not depend on it. */
     int32_t l1_mux;        /* 0: every slice has its own L1 (create_env(L1_level=True), the default);
                             * 1: L1_level=False (scenario_creator.py:168-177): the n_embb eMBB RAN slices share ONE L1 scheduler and ONE
                             *    action entry; action / labels / violations are then [N][(n_embb > 0) + n_mmtc], violations count the
@@ -147,6 +149,8 @@ int rs_get_routes(rs_handle *h, uint64_t *out4);
 int rs_selftest(void);
 
 int rs_n_variables(const rs_handle *h);
+/* the kernel variant that actually steps this handle's eMBB slices (kernel_variant 0 resolved: 3 or 4; 5 = multiplexed L1 kernel) */
+int rs_active_variant(const rs_handle *h);
 const char *rs_last_error(void);
 
 #ifdef __cplusplus

@@ -57,6 +57,8 @@ def lib():
     L.rs_set_state.argtypes = [vp, vp, C.c_size_t]
     L.rs_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.rs_n_variables.argtypes = [vp]
+    L.rs_active_variant.argtypes = [vp]
+    L.rs_active_variant.restype = C.c_int
     L.rs_set_debug_check.argtypes = [vp, i32]
     L.rs_get_diag.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.rs_set_profiling.argtypes = [vp, i32]

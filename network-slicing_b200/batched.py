@@ -177,11 +177,18 @@ class BatchedRanSlice:
         _lib.check(_lib.lib().rs_state_size(self._h, C.byref(n)))
         return int(n.value)
 
-    VARIANT_NAMES = {0: "embb_step_smem (PRB-sorted units, UE table in shared memory, guarded fast math)",
-                     1: "embb_step_unit_thread (all fp64)", 2: "embb_step_fast (PRB-sorted units, guarded fast math)"}
+    VARIANT_NAMES = {1: "embb_step_unit_thread (all fp64)", 2: "embb_step_fast (PRB-sorted units, guarded fast math)",
+                     3: "embb_step_warp (one warp per unit: lanes over UEs / PRB quads, guarded fast math)",
+                     4: "embb_step_smem (PRB-sorted units, UE table in shared memory, guarded fast math)",
+                     5: "embb_step_mux_thread (multiplexed L1, all fp64)"}
+
+    def active_variant(self):
+        """The kernel variant that steps the eMBB slices (``kernel_variant`` 0 resolved by the batch size)."""
+        return int(_lib.lib().rs_active_variant(self._h))
 
     def kernel_variant_name(self):
-        return self.VARIANT_NAMES.get(self._cfg.kernel_variant, str(self._cfg.kernel_variant))
+        v = self.active_variant()
+        return self.VARIANT_NAMES.get(v, str(v))
 
     def profile_steps(self, actions, out=None):
         """Runs step_device over ``actions`` with per-kernel CUDA events (inside the library, on the

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libranslice_b200.so")
-SOURCES = ["ranslice_cabi.cu", "embb_step.cu", "embb_fast.cu", "embb_smem.cu", "mmtc_step.cu", "kbrl.cu", "wrappers.cu"]
+SOURCES = ["ranslice_cabi.cu", "embb_step.cu", "embb_fast.cu", "embb_smem.cu", "embb_warp.cu", "mmtc_step.cu", "kbrl.cu", "wrappers.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=false",           # fp64 decision arithmetic must not be contracted (parity with NumPy)
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -31,6 +31,7 @@
 //    drained (the remaining PRBs go to UE 0 with 0 bits, schedulers.py:52 argmax of all-zero).
 #include "embb_device.cuh"
 #include "embb_fastmath.cuh"
+#include "embb_ran.cuh"
 
 namespace rs {
 
@@ -56,6 +57,11 @@ __device__ __forceinline__ uint32_t sort_key(int n_prbs, uint32_t hint, int n_ue
     return (heavy ? HEAVY_BIT : 0u) | ((uint32_t)min(n_ues, 15) << 11) | ((uint32_t)n_prbs << 3) | contention_class(hint, n_prbs, slots);
 }
 
+// units routed to the warp-per-unit kernel by the default variant (heavy_min_ues < 2^30 marks the shared-memory route)
+__device__ __forceinline__ bool is_heavy(const EmbbState &st, int u, int heavy_min_ues) {
+    return st.heavy_thr > 0 && heavy_min_ues < (1 << 30) && (int)(st.hint[u] >> 8) >= st.heavy_thr;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pre-pass 1: PRB windows of all eMBB units of a step (node_b.py:71-74) + histogram of sort keys.
 // Units whose live-UE count fits ONE lane's slots of the shared-memory kernel (embb_smem.cu) are counting-
@@ -78,7 +84,14 @@ __global__ void __launch_bounds__(256) window_kernel(const __grid_constant__ Ste
         st.win[u] = (uint32_t)off | ((uint32_t)v << 16);
         st.cur_prbs[u] = v;
         const int n_ues = st.hdr[u].n_ues;
-        if (n_ues < heavy_min_ues) {
+        bool to_warp = is_heavy(st, u, heavy_min_ues);          // long PF loop last step: warp-per-unit kernel
+        if (to_warp) {
+            const int pos = atomicAdd(&st.wlist[st.U], 1);
+            if (pos < st.heavy_cap) st.wlist[pos] = u;
+            else { atomicSub(&st.wlist[st.U], 1); st.hint[u] &= 0xFFu; to_warp = false; }   // list full: a normal lane after all (hint cleared so that scatter_kernel agrees)
+        }
+        if (to_warp) {
+        } else if (n_ues < heavy_min_ues) {
             atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots, false)], 1u);
         } else if (n_ues <= max_front_ues) {
             atomicAdd(&st.hist[sort_key(v, st.hint[u], n_ues, p.slots, true)], 2u);      // (unit, pad) pair
@@ -142,72 +155,12 @@ __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ St
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= st.U) return;
     const int n_ues = st.hdr[u].n_ues;
-    if (n_ues > max_front_ues) return;
+    if (n_ues > max_front_ues || is_heavy(st, u, heavy_min_ues)) return;
     const bool heavy = n_ues >= heavy_min_ues;
     const uint32_t key = sort_key((int)(st.win[u] >> 16), st.hint[u], n_ues, p.slots, heavy);
     const uint32_t pos = atomicAdd(&st.hist[KEY_BINS + key], heavy ? 2u : 1u);
     st.perm[pos << st.dil] = u;                                // diluted list: the lanes in between stay -1 (launch_embb_sort)
     if (heavy) st.perm[(pos << st.dil) + 1] = -1;                          // the odd lane only lends its shared-memory slots
-}
-
-// Rare RAN events of a slot, exactly in the reference's order (slice_ran.py:263-268, slice_l1.py:196-198):
-// cbr_arrivals (+CAC), vbr_arrivals, departures, extract_users, add_users -> insert_user.
-__device__ __noinline__ void ran_events(const StepParams &p, const EmbbState &st, UeRec *ue, uint32_t k0, uint32_t k1, uint32_t genv,
-                                        uint32_t s, int t, uint32_t clock, int a_prb0, int a_th0, RanCtx &c) {
-    struct { PhiloxStream ran, chan, vbr; } rng{{k0, k1, s, STREAM_RAN, c.c_ran, genv}, {k0, k1, s, STREAM_CHAN, c.c_chan, genv},
-                                                {k0, k1, s, STREAM_VBR, c.c_vbr, genv}};
-    int n_ues = c.n_ues, cbr_next = c.cbr_next, vbr_next = c.vbr_next;
-    uint32_t next_dep = c.next_dep, flags = c.flags;
-    int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
-    if (cbr_next == 0) {                                                          // slice_ran.py:205-227
-        cbr_next = exp_slots_ms(rng.ran, 1.0 / (2.0 / 60.0));
-        const double cbr_prb = (double)a_prb0 / (double)t;                        // cbr_cac, :195-203
-        const double cbr_th = (double)a_th0 / ((double)t * 1e-3);
-        if (!(cbr_prb >= 20.0 || cbr_th >= 10e6)) {
-            arr_type[n_arr] = 0; arr_vnext[n_arr] = 0;
-            arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
-        }
-    } else cbr_next -= 1;
-    if (vbr_next == 0) {                                                          // :229-249
-        arr_type[n_arr] = 1;
-        arr_vnext[n_arr] = exp_slots(rng.vbr, (1.0 / 1) / 1e-3);                  // VbrSource.__init__, traffic_generators.py:65-66
-        arr_rem[n_arr++] = exp_slots_ms(rng.ran, 30.0);
-        vbr_next = exp_slots_ms(rng.ran, 1.0 / (5.0 / 60.0));
-    } else vbr_next -= 1;
-    if (clock == next_dep) {                                                      // departures, :251-261 (order kept)
-        int w = 0;
-        uint32_t nd = DEP_NEVER;
-        for (int k = 0; k < n_ues; ++k) {
-            const uint32_t d = ue[k].dep_at;
-            if (d != clock) {
-                if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
-                nd = min(nd, d);
-                ++w;
-            }
-        }
-        n_ues = w;
-        next_dep = nd;
-    }
-    for (int a = 0; a < n_arr; ++a) {                                             // slice_l1.py:183-186
-        const int rem = arr_rem[a] - 1;                          // this slot's departures() already ticked it
-        if (rem == 0) { flags |= 8u; continue; }
-        if (n_ues >= st.K) { flags |= 1u; continue; }
-        UeRec r;
-        const int fading = (int)rng.chan.integers(3);                             // channel_models.py:163-169
-        const int index = (int)rng.chan.integers(N_SAMPLES);
-        const int step = rng.chan.integers(2) ? 1 : -1;
-        r.nominal = draw_nominal_sinr(rng.chan, p.prop_A, p.prop_B);
-        r.meta = pack_meta(arr_type[a], fading, step, index);
-        r.dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem;
-        r.vnext = arr_vnext[a]; r.bits = 0; r.th = 0.0; r.queue = 0; r.pe = 0; r.nb = 0;
-#pragma unroll
-        for (int j = 0; j < MAX_BURSTS; ++j) r.togo[j] = 0;
-        store_rec(ue + n_ues, r);
-        next_dep = min(next_dep, r.dep_at);
-        ++n_ues;
-    }
-    c.c_ran = rng.ran.n; c.c_chan = rng.chan.n; c.c_vbr = rng.vbr.n;
-    c.n_ues = n_ues; c.cbr_next = cbr_next; c.vbr_next = vbr_next; c.next_dep = next_dep; c.flags = flags;
 }
 
 template <int K>
@@ -271,7 +224,7 @@ __global__ void __launch_bounds__(128, RS_FAST_MIN_BLOCKS) embb_step_fast(const 
         // ================= slice_ran.slot(): arrivals / departures only on event slots
         if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
             RanCtx c{c_ran, r_chan.n, r_vbr.n, next_dep, flags, n_ues, cbr_next, vbr_next};
-            ran_events(p, st, ue, k0, k1, genv, (uint32_t)s, t, clock, a_prb[0], a_th[0], c);
+            ran_events(p, st.K, ue, k0, k1, genv, (uint32_t)s, t, clock, a_prb[0], a_th[0], c);
             c_ran = c.c_ran; r_chan.n = c.c_chan; r_vbr.n = c.c_vbr; next_dep = c.next_dep; flags = c.flags;
             n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
         } else { cbr_next -= 1; vbr_next -= 1; }
@@ -555,6 +508,7 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream) {
 
 void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream) {
     cudaMemsetAsync(st.hist, 0, (2 * KEY_BINS + 4 + SCAN_BLOCKS) * sizeof(uint32_t), stream);
+    if (st.heavy_thr > 0) cudaMemsetAsync(st.wlist + st.U, 0, sizeof(int32_t), stream);
     if (st.dil) cudaMemsetAsync(st.perm, 0xFF, (size_t)st.perm_len * sizeof(int32_t), stream);   // idle lanes of the diluted list
     window_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, st, max_front_ues, heavy_min_ues);
     scan_local_kernel<<<SCAN_BLOCKS, SCAN_THREADS, 0, stream>>>(st);

@@ -211,6 +211,15 @@ __device__ __forceinline__ int window_sum_prefix(const int32_t *pre, int row0, i
     return sum;
 }
 
+// x / n for a small positive integer count n, exactly rounded: q = RN(x * RN(1/n)), r = x - q n (exact, FMA),
+// q' = RN(q + r * RN(1/n)) (Markstein; rs_selftest samples the identity against IEEE division).
+__device__ __forceinline__ double div_count(double x, int n) {
+    if (n <= 1) return x;
+    const double dn = (double)n, rcp = __drcp_rn(dn);
+    const double q = __dmul_rn(x, rcp);
+    return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
+}
+
 // exact fp64 window mean (same operation order as embb_step.cu); rare
 static __device__ __noinline__ double window_mean_fp64(const double *col, int row0, int n, double nominal) {
     double sum = 0.0;

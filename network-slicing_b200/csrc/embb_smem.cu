@@ -205,15 +205,6 @@ __device__ __noinline__ uint32_t vbr_event(ColdRec *g, uint32_t clock, PhiloxStr
     return next_vbr_event(c);
 }
 
-// x / n for a small positive integer count n, exactly rounded: q = RN(x * RN(1/n)), r = x - q n (exact, FMA),
-// q' = RN(q + r * RN(1/n)) (Markstein; rs_selftest samples the identity against IEEE division).
-__device__ __forceinline__ double div_count(double x, int n) {
-    if (n <= 1) return x;
-    const double dn = (double)n, rcp = __drcp_rn(dn);
-    const double q = __dmul_rn(x, rcp);
-    return __fma_rn(__fma_rn(-q, dn, x), rcp, q);
-}
-
 // PF argmax among the candidates within 1e-6 (relative) of the fp32 maximum: exact fp64 quotients, first maximum
 // (np.argmax, schedulers.py:52).  Taken by 0.6 % of the chunks; out of line to keep the RB loop compact.
 __device__ __noinline__ int pf_exact_argmax(const SmemView &v, int tid, int n_ues, float best) {
@@ -706,7 +697,9 @@ void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ue
 void launch_embb_general(const StepParams &p, const EmbbState &st, const Tables &tb, int back_list, cudaStream_t stream);
 
 // default variant: shared-memory kernel over the sorted front list, general kernel over list L
-int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
+void launch_embb_warp_heavy(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof, const HeavyFork *fork) {
     static bool configured = false;
     constexpr int smem_bytes = SM_THREADS * SM_KS * SM_WORDS * 4;
     static_assert(RS_SM_BLOCKS * (smem_bytes + 2048 + 1024) <= 227 * 1024, "RS_SM_BLOCKS blocks per SM must fit");
@@ -719,13 +712,24 @@ int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb,
         configured = true;
     }
     launch_embb_sort(p, st, st.route[2], st.route[0] + 1, stream);
+    int launched = 6;
+    if (st.heavy_thr > 0) {                                       // heavy list: warp-per-unit kernel, concurrent when a side stream is given
+        if (fork) {
+            cudaEventRecord(fork->fork, stream);
+            cudaStreamWaitEvent(fork->stream, fork->fork, 0);
+            launch_embb_warp_heavy(p, st, tb, fork->stream);
+            cudaEventRecord(fork->join, fork->stream);
+        } else launch_embb_warp_heavy(p, st, tb, stream);
+        ++launched;
+    }
     const int blocks = (st.perm_len + SM_THREADS - 1) / SM_THREADS;   // worst case: every unit owns a pair of lanes
     if (prof) cudaEventRecord(prof[0], stream);               // profiling: events around the dominant kernel alone
     if (st.wide) embb_step_smem<1><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     else embb_step_smem<0><<<blocks, SM_THREADS, smem_bytes, stream>>>(p, st, tb);
     if (prof) cudaEventRecord(prof[1], stream);
     launch_embb_general(p, st, tb, 1, stream);
-    return 6;   // kernels launched
+    if (st.heavy_thr > 0 && fork) cudaStreamWaitEvent(stream, fork->join, 0);
+    return launched;   // kernels launched
 }
 
 }  // namespace rs

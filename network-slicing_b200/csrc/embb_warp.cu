@@ -1,0 +1,386 @@
+// K1 warp-per-unit variant: one WARP steps one (env, eMBB slice) unit through its 50 TTIs.
+//
+// The default kernel (embb_smem.cu) gives every unit one lane; a step then lasts as long as its heaviest lane's serial
+// work (a slice with ~190 PRBs and a deep backlog runs ~95 PF chunks and a 50-quad MI loop per TTI), which is what a
+// batch too small to fill the GPU waits for: 4096 envs took 2.1 ms per step with 94 % of the lanes idle.  Here the
+// lanes of a warp share ONE unit:
+//   * lane k owns UE k (<= 16 live UEs): traffic source, trace walk, window mean (prefix table), MCS lookup, reception,
+//     transmission_step all run in parallel over the UEs; the UE record stays in the lane's registers for the whole step;
+//   * the PF argmax over the UEs of a chunk (schedulers.py:52) is two warp REDUX instructions on the fp32 metric bits
+//     (+ the exact fp64 comparison when the runner-up is within 1e-6, as in the other kernels);
+//   * the per-PRB mutual-information sum of a served UE (channel_models.py:304-310) is spread over all 32 lanes, a quad
+//     of PRBs each, and tree-reduced;
+//   * the end-of-slot accumulators (slice_ran.py:278-305) are integer warp reductions.
+// Draw order is kept exactly: a Philox stream is (key, counter), so lane k takes the counter the sequential code would
+// have reached -- base + (draws of the lanes before it) -- from a ballot; variable-length draws (trace re-draw at a trace
+// end) and RAN events (arrivals / departures, ~0.1 per unit-step) are serialised: for an event slot the lanes park
+// their records in a shared-memory table, lane 0 runs the same ran_events() as the general kernel on it, and the lanes
+// reload.  Results are bit-identical to the other variants (tests/test_gpu_parity.py runs all of them).
+//
+// A warp executes ~3x the warp-instructions of a lane doing the same unit, so this variant only pays while the batch
+// leaves the GPU underfilled; rs_create routes batches of up to RS_WARP_AUTO_UNITS units to it (measured crossover).
+#include "embb_device.cuh"
+#include "embb_fastmath.cuh"
+#include "embb_ran.cuh"
+
+namespace rs {
+
+constexpr int WP_WARPS = 8;        // units per 256-thread block
+constexpr int WP_K = 16;           // UE slots per unit (== the UE cap of the other variants)
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_d(double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(FULL, lo, src); hi = __shfl_sync(FULL, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(FULL, lo, m); hi = __shfl_xor_sync(FULL, hi, m);
+    return __hiloint2double(hi, lo);
+}
+// sum of a non-negative 64-bit quantity over the warp (per-lane values < 2^47): two 32-bit REDUX on 24-bit halves
+__device__ __forceinline__ long long reduce_add_ll(long long v) {
+    const unsigned lo = (unsigned)(v & 0xFFFFFF), hi = (unsigned)(v >> 24);
+    return ((long long)__reduce_add_sync(FULL, hi) << 24) + (long long)__reduce_add_sync(FULL, lo);
+}
+
+struct WarpCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
+
+#ifndef RS_WARP_MIN_BLOCKS
+#define RS_WARP_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_warp(const __grid_constant__ StepParams p,
+                                                               const __grid_constant__ EmbbState st,
+                                                               const __grid_constant__ Tables tb, const int heavy_list) {
+    __shared__ int16_t s_rate[256];
+    __shared__ int8_t s_mcs[256];
+    __shared__ float s_ref[26];
+    __shared__ int8_t s_mod[26];
+    __shared__ float s_mi[3][4];                                 // per modulation: k, x0, c1 = -k log2(e), c0 = k x0 log2(e)
+    __shared__ float s_inv[2 * TRACE_ROWS + 1];
+    __shared__ __align__(16) UeRec s_tbl[WP_WARPS][WP_K];        // RAN-event scratch (8 KB)
+    __shared__ WarpCtx s_ctx[WP_WARPS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += WP_WARPS * 32) { s_rate[i] = tb.lut_rate[i]; s_mcs[i] = tb.lut_mcs[i]; }
+    if (tid < 26) { s_ref[tid] = (float)tb.snr_ref[tid]; s_mod[tid] = tb.mod[tid]; }
+    if (tid < 3) {
+        const float kf = (float)c_MI_K[tid], x0f = (float)c_MI_X0[tid];
+        s_mi[tid][0] = kf; s_mi[tid][1] = x0f; s_mi[tid][2] = -kf * LOG2E_F; s_mi[tid][3] = kf * x0f * LOG2E_F;
+    }
+    for (int i = tid; i <= 2 * TRACE_ROWS; i += WP_WARPS * 32) s_inv[i] = i ? __frcp_rn((float)i) : 0.f;
+    __syncthreads();
+
+    const int lane = tid & 31, w = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int ix = blockIdx.x * WP_WARPS + w;
+    // units: the heavy list of the default route (units whose PF loop was long in the previous step, embb_fast.cu
+    // window_kernel), or every unit, heaviest first (variant 3: sorted front list without pair entries)
+    if (ix >= (int)(heavy_list ? st.wlist[st.U] : st.hist[2 * SORT_BINS + 0])) return;            // whole warp
+    const int u = heavy_list ? st.wlist[ix] : st.perm[ix];
+    const int env = u / p.n_embb, s = u - env * p.n_embb;
+    int i_prb, n_prbs;
+    unpack_window(st.win[u], i_prb, n_prbs);
+    const int row_base = i_prb % TRACE_ROWS;
+    uint32_t flags = 0;
+
+    const UnitHdr hdr = st.hdr[u];
+    UeRec *ue = st.ue + (size_t)u * st.K;
+    UeRec *tbl = s_tbl[w];
+    const uint64_t seed = p.seed0;
+    const uint32_t genv = p.env0 + (uint32_t)env;                // global env id: Philox counter word 3
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t c_ran = hdr.ctr[0], c_chan = hdr.ctr[1], c_rx = hdr.ctr[2], c_vbr = hdr.ctr[3];
+    int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
+    uint32_t clock = hdr.clock;
+
+    UeRec r;                                                     // lane k < n_ues: UE k
+    {
+        int4 *z = reinterpret_cast<int4 *>(&r);
+        z[0] = z[1] = z[2] = z[3] = make_int4(0, 0, 0, 0);
+    }
+    if (lane < n_ues) load_rec(ue + lane, r);
+    uint32_t next_dep = __reduce_min_sync(FULL, lane < n_ues ? r.dep_at : DEP_NEVER);
+
+    // slice_ran.py:270-273 reset_info: (both types, VBR only) pairs, warp-uniform
+    int a_traffic_all = 0, a_traffic_v = 0, a_th_all = 0, a_th_v = 0, a_prb_all = 0, a_prb_v = 0;
+    double a_queue_c = 0.0, a_queue_v = 0.0, a_snr_c = 0.0, a_snr_v = 0.0;
+    unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;      // per lane, reduced at the end
+    const float Af = (float)tb.A, Bf = (float)tb.B;
+    const double inv_n = n_prbs > 0 ? tb.pre_inv / (double)n_prbs : 0.0;
+
+    for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
+        ++clock;
+        // ================= slice_ran.slot(): arrivals / departures only on event slots (serial: lane 0 on the parked table)
+        if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
+            if (lane < n_ues) store_rec(tbl + lane, r);
+            __syncwarp();
+            if (lane == 0) {
+                RanCtx c{c_ran, c_chan, c_vbr, next_dep, flags, n_ues, cbr_next, vbr_next};
+                ran_events(p, min(st.K, WP_K), tbl, k0, k1, genv, (uint32_t)s, t, clock, a_prb_all - a_prb_v, a_th_all - a_th_v, c);
+                s_ctx[w] = WarpCtx{c.c_ran, c.c_chan, c.c_vbr, c.next_dep, c.flags, c.n_ues, c.cbr_next, c.vbr_next};
+            }
+            __syncwarp();
+            const WarpCtx c = s_ctx[w];
+            c_ran = c.c_ran; c_chan = c.c_chan; c_vbr = c.c_vbr; next_dep = c.next_dep;
+            if (lane == 0) flags = c.flags;
+            n_ues = c.n_ues; cbr_next = c.cbr_next; vbr_next = c.vbr_next;
+            if (lane < n_ues) load_rec(tbl + lane, r);
+            __syncwarp();
+        } else { cbr_next -= 1; vbr_next -= 1; }
+
+        // ================= per-UE traffic + SNR estimate (slice_l1.py:200-213), lane = UE
+        const bool live = lane < n_ues;
+        const int ty = (int)(r.meta & 1u);
+        int nb_bits = 0;
+        {
+            const unsigned ev = __ballot_sync(FULL, live && ty && r.vnext - 1 == 0);      // VBR burst arrivals: two draws each, in UE order
+            if (live) {
+                if (ty) {
+                    PhiloxStream rv{k0, k1, (uint32_t)s, STREAM_VBR, c_vbr + 2u * (uint32_t)__popc(ev & lt), genv};
+                    nb_bits = vbr_source_step(r, rv, flags);
+                } else nb_bits = 500;                            // CbrSource: 500000 b/s * 1e-3 every slot
+                r.queue += nb_bits;
+            }
+            c_vbr += 2u * (uint32_t)__popc(ev);
+        }
+        int col_off = 0;
+        if (n_prbs > 0) {                                        // uniform
+            int index = (int)(r.meta >> 4), step = (r.meta & 8u) ? 1 : -1;
+            const int fading = (int)((r.meta >> 1) & 3u);
+            index += step;                                       // channel_models.py:171-191
+            unsigned redraw = __ballot_sync(FULL, live && (index >= N_SAMPLES - 1 || index < 0));
+            while (redraw) {                                     // a trace end: variable number of draws, in UE order
+                const int src = __ffs(redraw) - 1;
+                redraw &= redraw - 1;
+                uint32_t cn = c_chan;
+                if (lane == src) {
+                    PhiloxStream rc{k0, k1, (uint32_t)s, STREAM_CHAN, c_chan, genv};
+                    walk_trace_redraw(rc, index, step);
+                    cn = rc.n;
+                }
+                c_chan = __shfl_sync(FULL, cn, src);
+            }
+            if (live) {
+                r.meta = pack_meta(ty, fading, step, index);
+                col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
+                const int isum = window_sum_prefix(tb.trace_pre + (fading * N_SAMPLES + index) * PRE_STRIDE, row_base, n_prbs);
+                trace_elems += (unsigned)n_prbs;
+                double mean = (double)isum * inv_n + r.nominal;  // |mean - reference mean| <= 2^-(pre_bits + 1) + few ulp
+                const double fr = mean - floor(mean);
+                if (fabs(fr - 0.5) < tb.pre_guard) {             // within the guard of a rounding boundary: exact fp64 mean
+                    mean = window_mean_fp64(tb.trace + col_off, row_base, n_prbs, r.nominal);
+                    ++slow_snr;
+                }
+                const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
+                r.pe = (r.pe & 0xFFFF) | (e_snr << 16);
+            }
+        }
+        // scheduler inputs (schedulers.py:37-45)
+        const int e = min(max(r.pe >> 16, -128), 127) + 128;
+        const int rate = s_rate[e], mcs = s_mcs[e];
+        double thpf = r.th > 1.0 ? r.th : 1.0;
+        float metf = live && r.queue > 0 ? (float)rate * rcp_approx((float)thpf) : 0.0f;
+        // update_info terms that are already final (slice_ran.py:278-305)
+        a_traffic_all += __reduce_add_sync(FULL, nb_bits); a_traffic_v += __reduce_add_sync(FULL, ty ? nb_bits : 0);
+        const int sn_all = __reduce_add_sync(FULL, live ? (r.pe >> 16) : 0), sn_v = __reduce_add_sync(FULL, live && ty ? (r.pe >> 16) : 0);
+        const int cnt_all = n_ues, cnt_v = __popc(__ballot_sync(FULL, live && ty));
+        int n_backlog = __popc(__ballot_sync(FULL, live && r.queue > 0));
+
+        // ================= scheduling + reception (slice_l1.py:215-224)
+        long long qsum_all, qsum_v;
+        if (n_backlog > 0 && n_prbs > 0) {                       // queued_data > 0 <=> some queue > 0 (uniform)
+            int bits_l = 0, rbs_l = 0;                           // ue_bits, ue_rbs of this lane's UE
+            int rr = 0;
+            // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63), phase 1: contended chunks
+            while (n_backlog >= 2 && rr < n_prbs) {
+                if (RS_EXP & 8) break;
+                ++pf_iters;
+                const int c = min(n_prbs - rr, 2);
+                // argmax of rate * (queue > 0) / th, first maximum: metrics are >= 0, so their bit patterns order like the values
+                const unsigned mb = live ? __float_as_uint(metf) : 0u;
+                const unsigned best_b = __reduce_max_sync(FULL, mb);
+                int idx = __ffs(__ballot_sync(FULL, live && mb == best_b)) - 1;
+                const unsigned second_b = __reduce_max_sync(FULL, live && lane != idx ? mb : 0u);
+                const float best = __uint_as_float(best_b);
+                if (__uint_as_float(second_b) >= best * (1.0f - 1e-6f)) {       // too close for fp32: exact fp64 quotients, first maximum
+                    const float lim = best * (1.0f - 1e-6f);
+                    const bool cand = live && metf >= lim && metf > 0.0f;
+                    const unsigned long long m64 = cand ? (unsigned long long)__double_as_longlong((double)rate / thpf) : 0ull;   // > 0 for a candidate
+                    const unsigned hi = __reduce_max_sync(FULL, (unsigned)(m64 >> 32));
+                    const unsigned lo = __reduce_max_sync(FULL, (unsigned)(m64 >> 32) == hi ? (unsigned)m64 : 0u);
+                    const unsigned win = __ballot_sync(FULL, cand && m64 == (((unsigned long long)hi << 32) | lo));
+                    idx = win ? __ffs(win) - 1 : 0;
+                }
+                // The winner keeps taking chunks on its own while the next warp-wide argmax would pick it again without the
+                // exact comparison, i.e. while the runner-up stays more than 1e-6 (relative) behind its NEW metric -- the
+                // same fp32 test as above, so the sequence of winners is unchanged; 59 % of the chunks repeat the previous UE.
+                int drained = 0, rr_new = rr + 2;
+                if (lane == idx) {
+                    const float second = __uint_as_float(second_b);
+                    int cc = c;
+                    for (;;) {
+                        const long long left_q = r.queue - bits_l;
+                        const int tx = (int)min((long long)(cc * rate), left_q);
+                        bits_l += tx;
+                        rbs_l += cc;
+                        thpf = __dadd_rn(__dmul_rn(PF_A, thpf), b_bits_over_slot(bits_l));
+                        drained = left_q - tx <= 0;
+                        metf = drained ? 0.0f : (float)rate * rcp_approx((float)thpf);
+                        if (drained || rr_new >= n_prbs || !(second < metf * (1.0f - 1e-6f))) break;
+                        cc = min(n_prbs - rr_new, 2);
+                        rr_new += 2;
+                        ++pf_iters;
+                    }
+                }
+                n_backlog -= __shfl_sync(FULL, drained, idx);
+                rr = __shfl_sync(FULL, rr_new, idx);
+                pf_iters = __shfl_sync(FULL, pf_iters, idx);
+            }
+            // phase 2: a single backlogged UE takes chunks until it is drained or the PRBs run out (closed form)
+            if (rr < n_prbs && n_backlog == 1) {
+                const int j = __ffs(__ballot_sync(FULL, live && r.queue - bits_l > 0)) - 1;
+                int rr_new = rr;
+                if (lane == j) {
+                    const int left = n_prbs - rr, full = left >> 1;
+                    const int cap2 = 2 * rate;
+                    const long long q = r.queue - bits_l;
+                    if (q <= (long long)full * cap2) {                          // drained within the 2-PRB chunks
+                        const int need = (int)((q + cap2 - 1) / cap2);
+                        rbs_l += 2 * need; bits_l += (int)q; rr_new = rr + 2 * need;
+                    } else {
+                        long long tx = (long long)full * cap2;
+                        if (left & 1) tx += min((long long)rate, q - tx);       // last, single-PRB chunk
+                        rbs_l += left; bits_l += (int)tx;
+                        rr_new = n_prbs;
+                    }
+                }
+                rr = __shfl_sync(FULL, rr_new, j);
+            }
+            // phase 3: every queue drained -> all metrics 0 -> argmax 0 with 0 bits for the remaining PRBs
+            if (rr < n_prbs && lane == 0) rbs_l += n_prbs - rr;
+
+            // ---- sub-band offsets (PRBs are handed out in UE order, schedulers.py:66-73) and MI sums, one served UE at a time
+            int o = rbs_l;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, o, d); if (lane >= d) o += v; }
+            o -= rbs_l;                                          // exclusive prefix
+            float mavg = 0.f;
+            unsigned multi = (RS_EXP & 4) ? 0u : __ballot_sync(FULL, live && rbs_l >= 2);
+            while (multi) {
+                const int k = __ffs(multi) - 1;
+                multi &= multi - 1;
+                const int rbs_k = __shfl_sync(FULL, rbs_l, k), lo = row_base + __shfl_sync(FULL, o, k), hi = lo + rbs_k;
+                const int coff_k = __shfl_sync(FULL, col_off, k);
+                const int m = s_mod[__shfl_sync(FULL, mcs, k)];
+                const float c1 = s_mi[m][2], c0 = s_mi[m][3], nf = __shfl_sync(FULL, (float)r.nominal, k);
+                const int4 *col4 = reinterpret_cast<const int4 *>(tb.trace_fix + coff_k);
+                const int q0 = lo >> 2, nq = ((hi - 1) >> 2) - q0 + 1;
+                double msum = 0.0;
+                for (int qi = lane; qi < nq; qi += 32) {
+                    const int q = q0 + qi, b = q << 2;
+                    const int4 x = LDQ_D(col4 + wrap_quad(q));
+                    const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, FIX_SCALE, nf), c1, c0));
+                    const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, FIX_SCALE, nf), c1, c0));
+                    const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, FIX_SCALE, nf), c1, c0));
+                    const float e3 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.w, FIX_SCALE, nf), c1, c0));
+                    float part = (b + 0 >= lo && b + 0 < hi) ? rcp_approx(1.0f + e0) : 0.f;
+                    part += (b + 1 >= lo && b + 1 < hi) ? rcp_approx(1.0f + e1) : 0.f;
+                    part += (b + 2 >= lo && b + 2 < hi) ? rcp_approx(1.0f + e2) : 0.f;
+                    part += (b + 3 >= lo && b + 3 < hi) ? rcp_approx(1.0f + e3) : 0.f;
+                    msum += (double)part;
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) msum += shfl_xor_d(msum, d);
+                if (lane == k) mavg = (float)msum * s_inv[rbs_k];            // mean MI of this UE's sub-band
+            }
+            // ---- per-UE reception (schedulers.py:66-76, slice_l1.py:219-224) + transmission_step (slice_ran.py:51-55)
+            const unsigned served = __ballot_sync(FULL, live && rbs_l > 0);
+            int b = 0;
+            if (live && rbs_l > 0) {
+                PhiloxStream rx{k0, k1, (uint32_t)s, STREAM_L1RX, c_rx + (uint32_t)__popc(served & lt), genv};
+                const double u01 = rx.u01();
+                trace_elems += (unsigned)rbs_l;
+                bool received = false, need_exact = false;
+                if (rbs_l == 1) need_exact = true;                           // single RB: no MI averaging, one fp64 sigmoid
+                else {
+                    if (mavg >= 1.0f - 1e-4f) received = true;               // p == 1.0 exactly in fp64
+                    else if (mavg <= 1e-4f) received = false;                // p < 2^-53
+                    else {
+                        const int md = s_mod[mcs];
+                        const float kf = s_mi[md][0], x0f = s_mi[md][1];
+                        const float rrm = rcp_approx(mavg) - 1.0f;
+                        const float seff = x0f - __logf(rrm) / kf;          // inv_sigmoid, channel_models.py:39-41
+                        const float L = Af * (seff - s_ref[mcs]) - Bf;
+                        const float p32 = rcp_approx(1.0f + __expf(-L));
+                        const float epsL = 2e-5f / (kf * mavg * (1.0f - mavg)) + 4e-5f;   // 8 dm / (k m (1-m)), dm <= 2.5e-6
+                        const float eps = 1.1f * p32 * (1.0f - p32) * epsL + 5e-7f;
+                        const double d = u01 - (double)p32;
+                        received = d < 0.0;
+                        need_exact = fabs(d) <= (double)eps;
+                    }
+                }
+                if (need_exact) {
+                    const double pr = response_exact(tb, mcs, (size_t)col_off, (row_base + o) % TRACE_ROWS, rbs_l, r.nominal);
+                    received = u01 < pr;
+                    slow_rx += rbs_l > 1;
+                }
+                b = received ? bits_l : 0;
+            }
+            c_rx += (uint32_t)__popc(served);
+            if (live) {
+                r.queue -= b;                                    // max(queue - bits, 0): bits never exceed the queue
+                r.th = __dadd_rn(__dmul_rn(PF_A, r.th), b_bits_over_slot(b));
+                r.bits = b;
+                r.pe = (r.pe & (int)0xFFFF0000) | rbs_l;
+            }
+            a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
+            a_prb_all += __reduce_add_sync(FULL, rbs_l); a_prb_v += __reduce_add_sync(FULL, ty ? rbs_l : 0);
+        } else {                                                 // nothing touched: stale bits / prbs accumulate
+            const int b = live ? r.bits : 0, prbs = live ? (r.pe & 0xFFFF) : 0;
+            a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
+            a_prb_all += __reduce_add_sync(FULL, prbs); a_prb_v += __reduce_add_sync(FULL, ty ? prbs : 0);
+        }
+        qsum_all = reduce_add_ll(live ? r.queue : 0); qsum_v = reduce_add_ll(live && ty ? r.queue : 0);
+        // ================= update_info means (slice_ran.py:290-291, 304-305)
+        a_queue_c += div_count((double)(qsum_all - qsum_v), cnt_all - cnt_v);
+        a_snr_c += div_count((double)(sn_all - sn_v), cnt_all - cnt_v);
+        a_queue_v += div_count((double)qsum_v, cnt_v);
+        a_snr_v += div_count((double)sn_v, cnt_v);
+    }
+
+    // ---- write the records back (once per step) and persist the slice scalars
+    if (lane < n_ues) store_rec(ue + lane, r);
+    flags = __reduce_or_sync(FULL, flags);
+    trace_elems = __reduce_add_sync(FULL, trace_elems); slow_snr = __reduce_add_sync(FULL, slow_snr); slow_rx = __reduce_add_sync(FULL, slow_rx);
+    if (lane != 0) return;
+    UnitHdr h2 = hdr;
+    h2.n_ues = n_ues; h2.cbr_next = cbr_next; h2.vbr_next = vbr_next; h2.clock = clock;
+    h2.ctr[0] = c_ran; h2.ctr[1] = c_chan; h2.ctr[2] = c_rx; h2.ctr[3] = c_vbr;
+    st.hdr[u] = h2;
+    st.hint[u] = (pf_iters << 8) | (uint32_t)n_prbs;
+    // ---- end of observation period: state, SLA label (slice_ran.py:307-325, slice_l1.py:160-171)
+    const double acc[10] = {(double)(a_traffic_all - a_traffic_v), (double)(a_th_all - a_th_v), (double)(a_prb_all - a_prb_v), a_queue_c, a_snr_c,
+                            (double)a_traffic_v, (double)a_th_v, (double)a_prb_v, a_queue_v, a_snr_v};
+    finish_embb_unit(p, st, env, s, u, acc, flags);
+    if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
+    if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
+    if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
+}
+
+void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream);
+
+// variant 3 (and the automatic route for small batches): every unit through the warp-per-unit kernel, heaviest first
+int launch_embb_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
+    launch_embb_sort(p, st, 1 << 30, 1 << 30, stream);
+    if (prof) cudaEventRecord(prof[0], stream);
+    embb_step_warp<<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 0);
+    if (prof) cudaEventRecord(prof[1], stream);
+    return 5;   // kernels launched
+}
+// the heavy list of the default route (at most heavy_cap units), concurrent with the shared-memory kernel on another stream
+void launch_embb_warp_heavy(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
+    embb_step_warp<<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 1);
+}
+
+}  // namespace rs

@@ -16,7 +16,8 @@
 namespace rs {
 void launch_embb_unit_thread(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 int launch_embb_fast(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
-int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof);
+int launch_embb_smem(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof, const HeavyFork *fork);
+int launch_embb_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof);
 void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream, cudaEvent_t *prof);
@@ -35,6 +36,9 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
     } while (0)
 
 constexpr int PROF_EVENTS = 7;
+#ifndef RS_HEAVY_PF_DEFAULT
+#define RS_HEAVY_PF_DEFAULT 0     // contended PF chunks per step above which a unit goes to the warp-per-unit kernel (0: off until measured)
+#endif
 struct rs_handle {
     rs_config cfg;
     rs::StepParams p;
@@ -66,6 +70,8 @@ struct rs_handle {
     uint32_t *a_flags[2];
     int async_slot;
     cudaEvent_t ev_fork, ev_join;
+    cudaStream_t warp_stream;                // heavy list of the default route (warp-per-unit kernel) next to the shared-memory kernel
+    cudaEvent_t ev_wfork, ev_wjoin;
     // ordering between entry points that launch on different streams (rs_step_device on a caller stream, then rs_reset /
     // rs_step / rs_step_async on the handle's own stream, or the other way round): the last step's stream and an event at its end
     cudaEvent_t ev_last;
@@ -73,6 +79,7 @@ struct rs_handle {
     bool has_last;
     uint64_t launches;
     bool was_reset;
+    bool use_warp;                           // eMBB slices stepped by the warp-per-unit kernel (variant 3, or a batch too small to fill the GPU)
     bool profiling;
     std::vector<cudaEvent_t> *prof_events;   // PROF_EVENTS per profiled step
 };
@@ -142,6 +149,14 @@ const char *rs_last_error(void) { return g_err.c_str(); }
 void rs_set_error(const char *msg) { g_err = msg ? msg : ""; }   // shared with kbrl.cu (internal)
 
 int rs_n_variables(const rs_handle *h) { return h ? h->p.V : 0; }
+int rs_active_variant(const rs_handle *h) {                  // the kernel that steps the eMBB slices of this handle (1..4; 5 = multiplexed L1)
+    if (!h) return -1;
+    if (h->cfg.l1_mux) return 5;
+    if (h->use_warp) return 3;
+    if (h->cfg.kernel_variant == 1) return 1;
+    if (h->cfg.kernel_variant == 2 || h->cfg.kernel_variant == 3 || h->embb.K > 16) return 2;
+    return 4;
+}
 
 static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tables);
 
@@ -154,6 +169,7 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     if (cfg->n_prbs <= 0 || cfg->n_prbs > 2 * rs::TRACE_ROWS)
         return fail(RS_E_ARG, "n_prbs must be in [1, 200] (the trace rows wrap once, channel_models.py:144-148)");
     if (cfg->slots_per_step <= 0 || cfg->slots_per_step > 255) return fail(RS_E_ARG, "slots_per_step must be in [1,255]");
+    if (cfg->kernel_variant < 0 || cfg->kernel_variant > 4) return fail(RS_E_ARG, "kernel_variant must be in [0, 4]");
     const bool mux = cfg->l1_mux != 0;
     const int K = mux ? 32 : (cfg->max_ues ? cfg->max_ues : 16), MB = cfg->max_bursts ? cfg->max_bursts : 8;   // a multiplexed L1 holds the UEs of all its RAN slices
     const int Q = cfg->mtc_queue_cap ? cfg->mtc_queue_cap : 128;
@@ -266,8 +282,14 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         // lane dilution of the shared-memory kernel (ranslice_state.cuh): while the diluted list (with ~10 % of pair
         // entries) stays within 2.5x the lanes the GPU keeps resident (4 blocks of 128 threads per SM).  Measured on B200:
         // 4096 envs 3.20 -> 2.78 ms/step at dil 2, 16384 envs 3.69 -> 3.43 at dil 1 (and 4.15 at dil 2), no gain beyond.
+        // warp-per-unit kernel (embb_warp.cu): kernel_variant 3, or automatically while the batch leaves the GPU underfilled
+        // (measured crossover; RS_WARP_AUTO_UNITS overrides)
+        size_t warp_auto = 0;
+        if (const char *e = std::getenv("RS_WARP_AUTO_UNITS")) warp_auto = (size_t)std::atoll(e);
+        h->use_warp = h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux && (h->cfg.kernel_variant == 3 || (h->cfg.kernel_variant == 0 && U <= warp_auto));
         int dil = 0;
-        if (h->cfg.kernel_variant == 0 && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {
+        const bool smem_variant = h->cfg.kernel_variant == 0 || h->cfg.kernel_variant == 4;
+        if (smem_variant && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux && !h->use_warp) {
             const double lanes = 2.5 * 4.0 * 128.0 * (double)h->sm_count;
             while (dil < 2 && 1.1 * (double)U * (double)(2 << dil) <= lanes) ++dil;
             if (const char *e = std::getenv("RS_DILUTION")) dil = std::max(0, std::min(2, std::atoi(e)));
@@ -275,15 +297,24 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         h->embb.dil = dil;
         h->embb.wide = dil == 2;      // smallest batches: latency variant (measured: 4096 envs 2.94 -> 2.74 ms/step; no gain at 16384)
         if (const char *e = std::getenv("RS_WIDE")) h->embb.wide = std::atoi(e) != 0;
+        // heavy list of the default route (ranslice_state.cuh): threshold on last step's contended PF chunks; RS_HEAVY_PF overrides (0 = off)
+        h->embb.heavy_thr = 0;
+        if (smem_variant && !h->use_warp && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {
+            h->embb.heavy_thr = RS_HEAVY_PF_DEFAULT;
+            if (const char *e = std::getenv("RS_HEAVY_PF")) h->embb.heavy_thr = std::max(0, std::atoi(e));
+        }
+        h->embb.heavy_cap = (int)std::min<size_t>(U, (size_t)8 * 4 * (size_t)h->sm_count);   // at most four 8-warp blocks per SM
+        if (const char *e = std::getenv("RS_HEAVY_CAP")) h->embb.heavy_cap = (int)std::min<size_t>(U, (size_t)std::max(8, std::atoi(e)));
         h->embb.perm_len = (int)((2 * U) << dil);
         const size_t perm_len = (size_t)h->embb.perm_len;
-        sc.take<uint32_t>(U); sc.take<int32_t>(perm_len); sc.take<uint32_t>(2 * rs::SORT_BINS + 4 + rs::SCAN_BLOCKS); sc.take<uint32_t>(U); sc.take<float>(8); sc.take<rs::ColdRec>(U * (size_t)h->embb.K);
+        sc.take<uint32_t>(U); sc.take<int32_t>(perm_len); sc.take<uint32_t>(2 * rs::SORT_BINS + 4 + rs::SCAN_BLOCKS); sc.take<uint32_t>(U); sc.take<float>(8); sc.take<rs::ColdRec>(U * (size_t)h->embb.K); sc.take<int32_t>(U + 1);
         CU(cudaMalloc(&h->scratch, sc.off + 256));
         CU(cudaMemset(h->scratch, 0, sc.off + 256));
         Carver rc; rc.base = h->scratch;
         h->embb.win = rc.take<uint32_t>(U); h->embb.perm = rc.take<int32_t>(perm_len);
         h->embb.hist = rc.take<uint32_t>(2 * rs::SORT_BINS + 4 + rs::SCAN_BLOCKS); h->embb.hint = rc.take<uint32_t>(U); h->embb.dbg = rc.take<float>(8);
         h->embb.cold = rc.take<rs::ColdRec>(U * (size_t)h->embb.K);
+        h->embb.wlist = rc.take<int32_t>(U + 1);
     }
     if (h->mmtc.U) {   // arrival scratch of the mMTC scan kernel
         const size_t UM = (size_t)h->mmtc.U;
@@ -323,6 +354,9 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&h->warp_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_wfork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_wjoin, cudaEventDisableTiming));
     p.flags_acc = h->d_flags_acc;
     p.trace_elems = h->d_trace_elems;
     p.slow_paths = h->d_slow_paths;
@@ -347,6 +381,9 @@ int rs_destroy(rs_handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_last) cudaEventDestroy(h->ev_last);
+    if (h->warp_stream) cudaStreamDestroy(h->warp_stream);
+    if (h->ev_wfork) cudaEventDestroy(h->ev_wfork);
+    if (h->ev_wjoin) cudaEventDestroy(h->ev_wjoin);
     if (h->prof_events) { for (auto e : *h->prof_events) cudaEventDestroy(e); delete h->prof_events; }
     delete h;
     return RS_OK;
@@ -411,8 +448,13 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     if (h->embb.U) {
         if (h->cfg.l1_mux) { rs::launch_embb_mux(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
-        else if (h->cfg.kernel_variant == 2 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
-        else { h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st, h->profiling ? ev + 1 : nullptr); dominant = true; }
+        else if (h->use_warp) { h->launches += rs::launch_embb_warp(p, h->embb, h->tb, st, h->profiling ? ev + 1 : nullptr); dominant = true; }
+        else if (h->cfg.kernel_variant == 2 || h->cfg.kernel_variant == 3 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);
+        else {
+            const rs::HeavyFork hf{h->warp_stream, h->ev_wfork, h->ev_wjoin};
+            h->launches += rs::launch_embb_smem(p, h->embb, h->tb, st, h->profiling ? ev + 1 : nullptr, h->profiling ? nullptr : &hf);
+            dominant = true;
+        }
     }
     if (h->profiling) {
         if (!dominant) { CU(cudaEventRecord(ev[1], st)); CU(cudaEventRecord(ev[2], st)); }   // other variants: no single dominant kernel
@@ -583,7 +625,7 @@ int rs_get_routes(rs_handle *h, uint64_t *out4) {
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
     out4[0] = out4[1] = out4[2] = out4[3] = 0;
-    if (!h->embb.U || h->cfg.l1_mux || h->cfg.kernel_variant != 0 || h->embb.K > 16) return RS_OK;   // other variants do not route
+    if (!h->embb.U || h->cfg.l1_mux || (h->cfg.kernel_variant != 0 && h->cfg.kernel_variant != 4) || h->embb.K > 16 || h->use_warp) return RS_OK;   // other variants do not route
     uint32_t t[4];
     CU(cudaMemcpy(t, h->embb.hist + 2 * rs::SORT_BINS, sizeof t, cudaMemcpyDeviceToHost));
     out4[0] = (uint64_t)t[0] - 2ull * t[3]; out4[1] = t[3]; out4[2] = t[2]; out4[3] = (uint64_t)t[1] - t[2];

@@ -4,6 +4,7 @@
 // are independent given their PRB window, so they are the grain of parallelism (one thread each).
 #pragma once
 #include <cstdint>
+#include <cuda_runtime.h>
 
 namespace rs {
 
@@ -69,6 +70,10 @@ struct EmbbState {
     int route[4];          // routing limits of the shared-memory kernel: units starting a step with <= route[0] UEs own one lane and
                            // may grow to route[1] slots, up to route[2] UEs a pair of lanes / route[3] slots, beyond: list L (general
                            // kernel); outgrowing the slots aborts and replays.  Defaults 6 / 8 / 14 / 16; tests shrink them (rs_set_route_limits)
+    int heavy_thr, heavy_cap; // default route: units whose PF loop ran >= heavy_thr contended chunks in the previous step (hint) go to the
+                           // warp-per-unit kernel (at most heavy_cap of them per step), concurrently with the shared-memory kernel: a step
+                           // lasts as long as its slowest lane, and those lanes are these units.  0: off
+    int32_t *wlist;        // [U + 1] the heavy list of this step; wlist[U] = its length (scratch)
     int wide;              // 1: launch the latency variant of the shared-memory kernel (small batches)
     int dil, perm_len;     // lane dilution (log2) of the shared-memory kernel's front list and the length of perm[]: when a batch
                            // cannot fill the GPU, every 2^dil-th lane carries a unit and the rest idle -- fewer divergent units
@@ -106,6 +111,9 @@ struct MmtcState {
     uint32_t *arr;         // [MTC_MAX_ARR][U] slot-in-period << 16 | device index, unordered
 };
 constexpr int MTC_MAX_ARR = 96;    // arrivals buffered per unit per step (mean 8.2, Poisson-like)
+
+// stream / events on which the default route runs its heavy list next to the shared-memory kernel
+struct HeavyFork { cudaStream_t stream; cudaEvent_t fork, join; };
 
 struct Tables {
     const double *trace;   // [3][N_SAMPLES][TRACE_ROWS] fp64, time-major

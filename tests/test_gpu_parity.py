@@ -8,7 +8,7 @@ import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 
 SCN = {0: (5, 200), 1: (5, 150), 2: (5, 100), 3: (2, 70)}
-VARIANTS = [0, 1, 2]      # 0 shared-memory kernel (default), 1 all-fp64 anchor, 2 general fast kernel
+VARIANTS = [0, 1, 2, 3, 4]      # 0 default (automatic route), 1 all-fp64 anchor, 2 general fast kernel, 3 warp per unit, 4 shared-memory kernel
 
 
 def simplex_actions(rng, N, S, n_prbs):
@@ -182,7 +182,7 @@ def test_fast_path_guard_bands_hold():
     units: representation error <= 2^-20) must stay inside its guard of 2.5 x that, and no decision may differ."""
     scn, N, T = 0, 2048, 150
     S, n_prbs = SCN[scn]
-    env = make_env(scn, N, 555)
+    env = make_env(scn, N, 555, kernel_variant=4)
     env.reset()
     env.set_debug_check(True)
     rng = np.random.default_rng(12)
@@ -326,7 +326,7 @@ def test_every_route_of_the_default_kernel_is_taken_and_exact(tables):
     hundreds of times -- and every env still equals the oracle bit for bit."""
     scn, N, T, seed = 0, 512, 400, 2468
     S, n_prbs = SCN[scn]
-    env = make_env(scn, N, seed)
+    env = make_env(scn, N, seed, kernel_variant=4)
     env.set_route_limits(single_start_max=2, single_slots=2, pair_start_max=5, pair_slots=6)     # any arrival on a full unit aborts
     orc = ol.OracleBatch(tables, scn, N, seed, n_threads=16)
     env.reset(); orc.reset()
@@ -353,7 +353,7 @@ def test_steady_state_parity_1024_envs_1000_steps(tables):
     every step; the shipped routing limits; pair-of-lanes units with more than 8 UEs occur naturally here."""
     scn, N, T, seed = 0, 1024, 1000, 1357
     S, n_prbs = SCN[scn]
-    env = make_env(scn, N, seed)
+    env = make_env(scn, N, seed, kernel_variant=4)
     orc = ol.OracleBatch(tables, scn, N, seed, n_threads=16)
     env.reset(); orc.reset()
     rng = np.random.default_rng(23)
@@ -407,7 +407,7 @@ def test_queue_limit_abort_replays_in_the_general_kernel():
     then equal the all-fp64 anchor kernel (variant 1) step for step."""
     scn, N, seed = 0, 16, 97531
     S, n_prbs = SCN[scn]
-    envs = [make_env(scn, N, seed, kernel_variant=v) for v in (0, 1)]
+    envs = [make_env(scn, N, seed, kernel_variant=v) for v in (4, 1)]
     rng = np.random.default_rng(9)
     acts = [simplex_actions(rng, N, S, n_prbs) for _ in range(260)]
     for e in envs:
