@@ -141,9 +141,10 @@ int rs_get_diag(rs_handle *h, double *out, int32_t n);
  * a pair of lanes with pair_slots slots, larger ones by the general kernel; a unit that outgrows its slots during the
  * step aborts untouched and is replayed by the general kernel.  Defaults 6 / 8 / 14 / 16 (the maxima for slots).
  * rs_get_routes: units of the LAST step by route: [0] one lane, [1] pair of lanes, [2] general kernel directly,
- * [3] aborted and replayed. */
+ * [3] aborted and replayed, [4] warp-per-unit kernel (the whole batch when it is small; at lane dilution 2 the units whose PF
+ * loop was long in the previous step). */
 int rs_set_route_limits(rs_handle *h, int32_t single_start_max, int32_t single_slots, int32_t pair_start_max, int32_t pair_slots);
-int rs_get_routes(rs_handle *h, uint64_t *out4);
+int rs_get_routes(rs_handle *h, uint64_t *out5);
 
 /* host-only self test of the exact-arithmetic identities the default kernel relies on */
 int rs_selftest(void);

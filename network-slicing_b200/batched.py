@@ -212,10 +212,10 @@ class BatchedRanSlice:
         _lib.check(_lib.lib().rs_set_route_limits(self._h, single_start_max, single_slots, pair_start_max, pair_slots))
 
     def routes(self):
-        """Units of the last step by route: dict(single, pair, general, aborted)."""
-        out = (C.c_uint64 * 4)()
+        """Units of the last step by route: dict(single, pair, general, aborted, warp)."""
+        out = (C.c_uint64 * 5)()
         _lib.check(_lib.lib().rs_get_routes(self._h, out))
-        return {"single": int(out[0]), "pair": int(out[1]), "general": int(out[2]), "aborted": int(out[3])}
+        return {"single": int(out[0]), "pair": int(out[1]), "general": int(out[2]), "aborted": int(out[3]), "warp": int(out[4])}
 
     def set_debug_check(self, on=True):
         _lib.check(_lib.lib().rs_set_debug_check(self._h, int(bool(on))))

@@ -37,7 +37,13 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 constexpr int PROF_EVENTS = 7;
 #ifndef RS_HEAVY_PF_DEFAULT
-#define RS_HEAVY_PF_DEFAULT 0     // contended PF chunks per step above which a unit goes to the warp-per-unit kernel (0: off until measured)
+#define RS_HEAVY_PF_DEFAULT 600   // contended PF chunks per step above which a unit of a SMALL batch goes to the warp-per-unit kernel; measured at
+                                  // 4096 envs: 2.13 ms/step without, 1.97 / 1.94 / 1.97 at 300 / 600 / 1000; at 16 384 and 65 536 envs any threshold below
+                                  // 2500 costs 5-15 % (a warp executes ~3x the instructions of a lane), so it is only enabled at lane dilution 2
+#endif
+#ifndef RS_WARP_AUTO_UNITS_DEFAULT
+#define RS_WARP_AUTO_UNITS_DEFAULT 16384   // batches of up to this many units run the warp-per-unit kernel: 2048 envs x 5 slices 1.18 vs 1.89 ms/step,
+                                           // 4096 envs 2.05 vs 2.13 (1.94 with the heavy list), 8192 envs 3.9 vs 2.4 (profiles/r02d_*)
 #endif
 struct rs_handle {
     rs_config cfg;
@@ -284,7 +290,7 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         // 4096 envs 3.20 -> 2.78 ms/step at dil 2, 16384 envs 3.69 -> 3.43 at dil 1 (and 4.15 at dil 2), no gain beyond.
         // warp-per-unit kernel (embb_warp.cu): kernel_variant 3, or automatically while the batch leaves the GPU underfilled
         // (measured crossover; RS_WARP_AUTO_UNITS overrides)
-        size_t warp_auto = 0;
+        size_t warp_auto = RS_WARP_AUTO_UNITS_DEFAULT;
         if (const char *e = std::getenv("RS_WARP_AUTO_UNITS")) warp_auto = (size_t)std::atoll(e);
         h->use_warp = h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux && (h->cfg.kernel_variant == 3 || (h->cfg.kernel_variant == 0 && U <= warp_auto));
         int dil = 0;
@@ -299,8 +305,8 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         if (const char *e = std::getenv("RS_WIDE")) h->embb.wide = std::atoi(e) != 0;
         // heavy list of the default route (ranslice_state.cuh): threshold on last step's contended PF chunks; RS_HEAVY_PF overrides (0 = off)
         h->embb.heavy_thr = 0;
-        if (smem_variant && !h->use_warp && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {
-            h->embb.heavy_thr = RS_HEAVY_PF_DEFAULT;
+        if (h->cfg.kernel_variant == 0 && !h->use_warp && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {   // (variant 4 is the pure shared-memory route)
+            h->embb.heavy_thr = dil == 2 ? RS_HEAVY_PF_DEFAULT : 0;      // only where the step is bound by its slowest lanes (smallest batches)
             if (const char *e = std::getenv("RS_HEAVY_PF")) h->embb.heavy_thr = std::max(0, std::atoi(e));
         }
         h->embb.heavy_cap = (int)std::min<size_t>(U, (size_t)8 * 4 * (size_t)h->sm_count);   // at most four 8-warp blocks per SM
@@ -620,15 +626,22 @@ int rs_set_route_limits(rs_handle *h, int32_t single_start_max, int32_t single_s
     return RS_OK;
 }
 
-int rs_get_routes(rs_handle *h, uint64_t *out4) {
+int rs_get_routes(rs_handle *h, uint64_t *out5) {
+    uint64_t *out4 = out5;
     if (!h || !out4) return fail(RS_E_ARG, "null argument");
     CU(cudaSetDevice(h->cfg.device));
     CU(cudaDeviceSynchronize());
-    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    out4[0] = out4[1] = out4[2] = out4[3] = out5[4] = 0;
+    if (h->use_warp) { out5[4] = (uint64_t)h->embb.U; return RS_OK; }
     if (!h->embb.U || h->cfg.l1_mux || (h->cfg.kernel_variant != 0 && h->cfg.kernel_variant != 4) || h->embb.K > 16 || h->use_warp) return RS_OK;   // other variants do not route
     uint32_t t[4];
     CU(cudaMemcpy(t, h->embb.hist + 2 * rs::SORT_BINS, sizeof t, cudaMemcpyDeviceToHost));
     out4[0] = (uint64_t)t[0] - 2ull * t[3]; out4[1] = t[3]; out4[2] = t[2]; out4[3] = (uint64_t)t[1] - t[2];
+    if (h->embb.heavy_thr > 0) {
+        int32_t n = 0;
+        CU(cudaMemcpy(&n, h->embb.wlist + h->embb.U, sizeof n, cudaMemcpyDeviceToHost));
+        out5[4] = (uint64_t)n;
+    }
     return RS_OK;
 }
 

@@ -331,7 +331,7 @@ def test_every_route_of_the_default_kernel_is_taken_and_exact(tables):
     orc = ol.OracleBatch(tables, scn, N, seed, n_threads=16)
     env.reset(); orc.reset()
     rng = np.random.default_rng(17)
-    total = dict(single=0, pair=0, general=0, aborted=0)
+    total = dict(single=0, pair=0, general=0, aborted=0, warp=0)
     for t in range(T):
         a = simplex_actions(rng, N, S, n_prbs)
         if t % 13 == 6:
@@ -344,7 +344,7 @@ def test_every_route_of_the_default_kernel_is_taken_and_exact(tables):
         assert ok.mean() > 0.99
         assert np.array_equal(obs[ok], o_obs[ok]), t
         assert np.array_equal(rew[ok].astype(np.float64), o_rew[ok]) and np.array_equal(info["violations"][ok], o_vio[ok]), t
-    assert min(total.values()) > 200, total
+    assert total.pop("warp") == 0 and min(total.values()) > 200, total      # (variant 4: no warp-per-unit route)
     env.close()
 
 
@@ -476,3 +476,29 @@ def test_adjacent_seeds_share_no_streams_and_reset_orders_after_device_steps():
         o2, r2, _, _ = ref.step(acts[11])
         assert np.array_equal(o1, o2) and np.array_equal(r1, r2), rep
     env.close(); ref.close()
+
+
+def test_automatic_route_by_batch_size_equals_the_shared_memory_kernel():
+    """kernel_variant 0 picks the route by batch size: the warp-per-unit kernel for batches that leave the GPU underfilled,
+    the shared-memory kernel with a heavy list (units with a long PF loop -> warp-per-unit kernel, concurrently) at lane
+    dilution 2, the shared-memory kernel alone above.  Every route gives the results of variant 4 (pinned to the oracle
+    above), step by step."""
+    scn, seed, T = 0, 8086, 120
+    S, n_prbs = SCN[scn]
+    for N, want in ((1024, "all"), (4096, "heavy")):
+        auto, ref = make_env(scn, N, seed), make_env(scn, N, seed, kernel_variant=4)
+        assert auto.active_variant() == (3 if want == "all" else 4) and ref.active_variant() == 4
+        auto.reset(); ref.reset()
+        rng = np.random.default_rng(31)
+        warp_units = 0
+        for t in range(T):
+            a = simplex_actions(rng, N, S, n_prbs)
+            if t % 5 == 2:
+                a[::3] = a[::3] // 5                 # starved slices: long contended PF loops -> heavy list
+            o0, r0, _, i0 = auto.step(a)
+            o1, r1, _, i1 = ref.step(a)
+            assert np.array_equal(o0, o1) and np.array_equal(r0, r1), (N, t)
+            assert np.array_equal(i0["violations"], i1["violations"]) and np.array_equal(i0["flags"], i1["flags"]), (N, t)
+            warp_units += auto.routes()["warp"]
+        assert warp_units == N * 5 * T if want == "all" else 0 < warp_units < N * 5 * T // 2, (N, warp_units)
+        auto.close(); ref.close()
