@@ -47,32 +47,64 @@ __device__ __forceinline__ long long reduce_add_ll(long long v) {
 
 struct WarpCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
 
+// ---- TMA staging of the fading-trace columns.  After the trace walk of a TTI the column of every live UE is
+// known, but its per-PRB values are only read after the PF loop (MI sums of the served sub-bands): each live lane issues one
+// cp.async.bulk.tensor (2-D tensor map over the trace table, box = one whole column of 100 rows = 400 bytes) into its slot of
+// the warp's shared-memory buffer, completion is signalled on the warp's mbarrier (expect_tx = live UEs x 400 bytes), and the
+// warp waits on the barrier's phase right before the MI loop.  SASS: UTMALDG (cuobjdump -sass; profiles/r02e_tma_sass.txt).
+constexpr int TMA_SLOT = 512;                                    // bytes per UE slot (400 used; tensor loads need 128-byte aligned destinations)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int row, int col, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(row), "r"(col), "r"(smem_u32(bar)) : "memory");
+}
+
 #ifndef RS_WARP_MIN_BLOCKS
 #define RS_WARP_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_warp(const __grid_constant__ StepParams p,
                                                                const __grid_constant__ EmbbState st,
                                                                const __grid_constant__ Tables tb, const int heavy_list) {
-    __shared__ int16_t s_rate[256];
-    __shared__ int8_t s_mcs[256];
-    __shared__ float s_ref[26];
-    __shared__ int8_t s_mod[26];
-    __shared__ float s_mi[3][4];                                 // per modulation: k, x0, c1 = -k log2(e), c0 = k x0 log2(e)
-    __shared__ float s_inv[2 * TRACE_ROWS + 1];
+    __shared__ __align__(128) LutBlock s_lut;                    // MCS / rate LUT, snr_ref, modulation, MI constants, 1/n: ONE bulk copy
     __shared__ __align__(16) UeRec s_tbl[WP_WARPS][WP_K];        // RAN-event scratch (8 KB)
     __shared__ WarpCtx s_ctx[WP_WARPS];
+    extern __shared__ __align__(128) unsigned char s_cols[];     // [WP_WARPS][WP_K][TMA_SLOT] staged trace columns
+    __shared__ __align__(8) uint64_t s_bar[WP_WARPS + 1];        // one mbarrier per warp (columns) + one for the lookup tables
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += WP_WARPS * 32) { s_rate[i] = tb.lut_rate[i]; s_mcs[i] = tb.lut_mcs[i]; }
-    if (tid < 26) { s_ref[tid] = (float)tb.snr_ref[tid]; s_mod[tid] = tb.mod[tid]; }
-    if (tid < 3) {
-        const float kf = (float)c_MI_K[tid], x0f = (float)c_MI_X0[tid];
-        s_mi[tid][0] = kf; s_mi[tid][1] = x0f; s_mi[tid][2] = -kf * LOG2E_F; s_mi[tid][3] = kf * x0f * LOG2E_F;
+    if (tid == 0) {                                              // mcs_codeset tables: cp.async.bulk global -> shared, completion on an mbarrier
+        mbar_init(&s_bar[WP_WARPS], 1);
+        mbar_expect_tx(&s_bar[WP_WARPS], (unsigned)sizeof(LutBlock));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(&s_lut)), "l"(tb.lut), "r"((unsigned)sizeof(LutBlock)), "r"(smem_u32(&s_bar[WP_WARPS])) : "memory");
     }
-    for (int i = tid; i <= 2 * TRACE_ROWS; i += WP_WARPS * 32) s_inv[i] = i ? __frcp_rn((float)i) : 0.f;
-    __syncthreads();
+    __syncthreads();                                             // (the barrier is initialised before anybody polls it)
+    mbar_wait(&s_bar[WP_WARPS], 0);
+    const int16_t *s_rate = s_lut.rate;
+    const int8_t *s_mcs = s_lut.mcs, *s_mod = s_lut.mod;
+    const float *s_ref = s_lut.ref, *s_inv = s_lut.inv;
+    const float (*s_mi)[4] = s_lut.mi;
+    const bool use_tma = tb.tmap_ok != 0;                        // fading-trace columns staged by TMA (else read through L1 / L2)
 
     const int lane = tid & 31, w = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
+    unsigned char *my_cols = s_cols + (size_t)w * WP_K * TMA_SLOT;
+    unsigned tma_phase = 0;
+    if (lane == 0) mbar_init(&s_bar[w], 1);
+    __syncwarp();
     const int ix = blockIdx.x * WP_WARPS + w;
     // units: the heavy list of the default route (units whose PF loop was long in the previous step, embb_fast.cu
     // window_kernel), or every unit, heaviest first (variant 3: sorted front list without pair entries)
@@ -175,6 +207,11 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
                 const int e_snr = __double2int_rn(mean);         // round(np.mean(snr)), slice_ran.py:43-45
                 r.pe = (r.pe & 0xFFFF) | (e_snr << 16);
             }
+            if (use_tma && n_ues > 0) {                          // stage this TTI's columns; waited for right before the MI loop
+                if (lane == 0) mbar_expect_tx(&s_bar[w], (unsigned)n_ues * TRACE_ROWS * 4u);
+                __syncwarp();
+                if (live) tma_load_column(my_cols + lane * TMA_SLOT, tb.tmap_fix, 0, col_off / TRACE_ROWS, &s_bar[w]);
+            }
         }
         // scheduler inputs (schedulers.py:37-45)
         const int e = min(max(r.pe >> 16, -128), 127) + 128;
@@ -266,6 +303,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
             for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(FULL, o, d); if (lane >= d) o += v; }
             o -= rbs_l;                                          // exclusive prefix
             float mavg = 0.f;
+            if (use_tma && n_ues > 0) { mbar_wait(&s_bar[w], tma_phase); tma_phase ^= 1u; }
             unsigned multi = (RS_EXP & 4) ? 0u : __ballot_sync(FULL, live && rbs_l >= 2);
             while (multi) {
                 const int k = __ffs(multi) - 1;
@@ -274,12 +312,13 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
                 const int coff_k = __shfl_sync(FULL, col_off, k);
                 const int m = s_mod[__shfl_sync(FULL, mcs, k)];
                 const float c1 = s_mi[m][2], c0 = s_mi[m][3], nf = __shfl_sync(FULL, (float)r.nominal, k);
-                const int4 *col4 = reinterpret_cast<const int4 *>(tb.trace_fix + coff_k);
+                const int4 *col4 = use_tma ? reinterpret_cast<const int4 *>(my_cols + k * TMA_SLOT)
+                                           : reinterpret_cast<const int4 *>(tb.trace_fix + coff_k);
                 const int q0 = lo >> 2, nq = ((hi - 1) >> 2) - q0 + 1;
                 double msum = 0.0;
                 for (int qi = lane; qi < nq; qi += 32) {
                     const int q = q0 + qi, b = q << 2;
-                    const int4 x = LDQ_D(col4 + wrap_quad(q));
+                    const int4 x = col4[wrap_quad(q)];
                     const float e0 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.x, FIX_SCALE, nf), c1, c0));
                     const float e1 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.y, FIX_SCALE, nf), c1, c0));
                     const float e2 = ex2_approx(__fmaf_rn(__fmaf_rn((float)x.z, FIX_SCALE, nf), c1, c0));
@@ -337,6 +376,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
             a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
             a_prb_all += __reduce_add_sync(FULL, rbs_l); a_prb_v += __reduce_add_sync(FULL, ty ? rbs_l : 0);
         } else {                                                 // nothing touched: stale bits / prbs accumulate
+            if (use_tma && n_prbs > 0 && n_ues > 0) { mbar_wait(&s_bar[w], tma_phase); tma_phase ^= 1u; }   // (columns staged but not needed)
             const int b = live ? r.bits : 0, prbs = live ? (r.pe & 0xFFFF) : 0;
             a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
             a_prb_all += __reduce_add_sync(FULL, prbs); a_prb_v += __reduce_add_sync(FULL, ty ? prbs : 0);
@@ -370,17 +410,24 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
 
 void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream);
 
+static size_t warp_dyn_smem() {
+    static bool configured = false;
+    constexpr size_t bytes = (size_t)WP_WARPS * WP_K * TMA_SLOT;
+    if (!configured) { cudaFuncSetAttribute(embb_step_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
+    return bytes;
+}
+
 // variant 3 (and the automatic route for small batches): every unit through the warp-per-unit kernel, heaviest first
 int launch_embb_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
     launch_embb_sort(p, st, 1 << 30, 1 << 30, stream);
     if (prof) cudaEventRecord(prof[0], stream);
-    embb_step_warp<<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 0);
+    embb_step_warp<<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 0);
     if (prof) cudaEventRecord(prof[1], stream);
     return 5;   // kernels launched
 }
 // the heavy list of the default route (at most heavy_cap units), concurrent with the shared-memory kernel on another stream
 void launch_embb_warp_heavy(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    embb_step_warp<<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 1);
+    embb_step_warp<<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 1);
 }
 
 }  // namespace rs

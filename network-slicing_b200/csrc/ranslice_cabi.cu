@@ -1,5 +1,6 @@
 // C ABI of libranslice_b200 (include/ranslice_b200.h): handle lifecycle, HBM state arena, table
 // upload, step orchestration.  No torch types; the Python layer binds it with ctypes.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -58,6 +59,7 @@ struct rs_handle {
     // tables + I/O staging
     double *d_trace;
     int32_t *d_trace_fix, *d_trace_pre;
+    rs::LutBlock *d_lut;
     char *scratch;
     unsigned long long *d_slow_paths;
     int32_t *d_action;
@@ -282,6 +284,44 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         CU(cudaMemcpy(h->d_trace_pre, pre.data(), pre.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         h->tb.trace_pre = h->d_trace_pre;
     }
+    {   // packed lookup tables (one bulk copy per block in embb_warp.cu); same fp32 expressions as the kernels' own staging loops
+        static const double MI_X0[3] = {-0.25040431, 5.12440916, 9.16962738}, MI_K[3] = {0.31591749, 0.25423209, 0.22298101};   // channel_models.py:268-270
+        rs::LutBlock lb;
+        std::memset(&lb, 0, sizeof lb);
+        for (int i = 0; i < 256; ++i) { lb.rate[i] = h->tb.lut_rate[i]; lb.mcs[i] = h->tb.lut_mcs[i]; }
+        for (int m = 0; m < 26; ++m) { lb.ref[m] = (float)h->tb.snr_ref[m]; lb.mod[m] = h->tb.mod[m]; }
+        for (int m = 0; m < 3; ++m) {
+            const float kf = (float)MI_K[m], x0f = (float)MI_X0[m], l2e = 1.4426950408889634f;
+            lb.mi[m][0] = kf; lb.mi[m][1] = x0f; lb.mi[m][2] = -kf * l2e; lb.mi[m][3] = kf * x0f * l2e;
+        }
+        for (int i = 1; i <= 2 * rs::TRACE_ROWS; ++i) lb.inv[i] = 1.0f / (float)i;      // == __frcp_rn((float)i)
+        CU(cudaMalloc(&h->d_lut, sizeof lb));
+        CU(cudaMemcpy(h->d_lut, &lb, sizeof lb, cudaMemcpyHostToDevice));
+        h->tb.lut = h->d_lut;
+    }
+    {   // tensor map of the fixed-point trace table for TMA column loads (embb_warp.cu); the driver API is reached through the
+        // runtime's entry-point query, so the library does not link libcuda
+        std::memset(h->tb.tmap_fix, 0, sizeof h->tb.tmap_fix);
+        h->tb.tmap_ok = 0;
+        typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn && q == cudaDriverEntryPointSuccess) {
+            static_assert(sizeof(CUtensorMap) == sizeof(h->tb.tmap_fix), "CUtensorMap is 128 bytes");
+            CUtensorMap tm;
+            const cuuint64_t dims[2] = {(cuuint64_t)rs::TRACE_ROWS, (cuuint64_t)3 * rs::N_SAMPLES};
+            const cuuint64_t strides[1] = {(cuuint64_t)rs::TRACE_ROWS * sizeof(int32_t)};
+            const cuuint32_t box[2] = {(cuuint32_t)rs::TRACE_ROWS, 1u}, estr[2] = {1u, 1u};
+            if (reinterpret_cast<encode_fn>(fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, h->d_trace_fix, dims, strides, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                std::memcpy(h->tb.tmap_fix, &tm, sizeof tm);
+                h->tb.tmap_ok = 1;
+            }
+        } else cudaGetLastError();
+    }
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
@@ -374,7 +414,7 @@ int rs_destroy(rs_handle *h) {
     if (!h) return RS_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
-    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->d_trace_pre); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
+    cudaFree(h->arena); cudaFree(h->d_trace); cudaFree(h->d_trace_fix); cudaFree(h->d_trace_pre); cudaFree(h->d_lut); cudaFree(h->scratch); cudaFree(h->d_action); cudaFree(h->d_obs);
     cudaFree(h->d_reward); cudaFree(h->d_labels); cudaFree(h->d_violations); cudaFree(h->d_flags);
     cudaFree(h->d_flags_acc); cudaFree(h->d_trace_elems);
     if (h->mmtc.U) { cudaFree(h->mmtc.arr_n); cudaFree(h->mmtc.arr); }

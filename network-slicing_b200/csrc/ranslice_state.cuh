@@ -112,6 +112,19 @@ struct MmtcState {
 };
 constexpr int MTC_MAX_ARR = 96;    // arrivals buffered per unit per step (mean 8.2, Poisson-like)
 
+// The small lookup tables of the eMBB kernels packed for ONE bulk copy into shared memory (cp.async.bulk, embb_warp.cu):
+// MCS / rate LUT over the integer e_snr (MCSCodeset.mcs_rate_vs_error), snr_ref and modulation per MCS, the MI sigmoid
+// constants per modulation in fp32 (k, x0, -k log2 e, k x0 log2 e) and 1/n for the MI mean.
+struct alignas(16) LutBlock {
+    int16_t rate[256];
+    int8_t mcs[256];
+    float ref[32];
+    int8_t mod[32];
+    float mi[3][4];
+    float inv[2 * TRACE_ROWS + 4];
+};
+static_assert(sizeof(LutBlock) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
 // stream / events on which the default route runs its heavy list next to the shared-memory kernel
 struct HeavyFork { cudaStream_t stream; cudaEvent_t fork, join; };
 
@@ -127,6 +140,12 @@ struct Tables {
     double snr_ref[26];    // mcs -> snr_ref
     int8_t mod[26];        // mcs -> modulation class
     double A, B;           // MCSCodeset.compute_factors(0.1)
+    // CUtensorMap (cuTensorMapEncodeTiled) over trace_fix seen as [3 * N_SAMPLES columns][100 rows] int32, box = one whole column
+    // (400 bytes): the warp-per-unit kernel stages the column of every live UE into shared memory with cp.async.bulk.tensor
+    // (TMA) while the PF loop runs (embb_warp.cu, RS_WARP_TMA).  All zero when the driver entry point is unavailable.
+    alignas(64) unsigned char tmap_fix[128];
+    int tmap_ok;
+    const LutBlock *lut;   // device copy of the packed lookup tables
 };
 
 struct StepParams {
