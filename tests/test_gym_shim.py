@@ -1,13 +1,25 @@
 """The ``gym_ran_slice`` shim keeps the reference's id and constructor kwargs (gym-ran_slice/gym_ran_slice/__init__.py:5-8,
 scenario_creator.py:181).  CPU part: import, spec extraction from a NodeB-like object; GPU part: make() -> working env."""
+import importlib.util
+import os
 import types
 
 import numpy as np
 import pytest
 
 
+def _shim():
+    """This repo's ``gym_ran_slice`` package, loaded by path: the test harness of the reference-backed tests puts the
+    REFERENCE's package of the same name (by design) first on sys.path."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gym_ran_slice_b200_shim", os.path.join(root, "gym_ran_slice", "__init__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def test_shim_reads_the_scenario_off_a_nodeb_like_object():
-    import gym_ran_slice as g
+    g = _shim()
     assert g.ENV_ID == "RanSlice-v1"
     l1 = lambda t, n: types.SimpleNamespace(type=t, slices_ran=[object()] * n)
     node = types.SimpleNamespace(n_prbs=150, slots_per_step=25, slices_l1=[l1("eMBB", 1)] * 3 + [l1("mMTC", 1)] * 2)
@@ -25,7 +37,7 @@ def test_shim_reads_the_scenario_off_a_nodeb_like_object():
 
 @pytest.mark.gpu
 def test_make_returns_the_native_env_with_the_reference_kwargs(golden):
-    import gym_ran_slice as g
+    g = _shim()
     gold = golden("B_scn3")
     env = g.make("gym_ran_slice:RanSlice-v1", node_b=g.NodeBSpec(scenario=3, seed=int(gold["base_seed"])), penalty=100)
     assert np.array_equal(env.reset(), gold["obs0"][0])
