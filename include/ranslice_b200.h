@@ -53,8 +53,9 @@ typedef struct rs_config {
                              *     4 shared-memory kernel whatever the batch size.  Results do not depend on it. */
     int32_t l1_mux;        /* 0: every slice has its own L1 (create_env(L1_level=True), the default);
                             * 1: L1_level=False (scenario_creator.py:168-177): the n_embb eMBB RAN slices share ONE L1 scheduler and ONE
-                            *    action entry; action / labels / violations are then [N][(n_embb > 0) + n_mmtc], violations count the
-                            *    RAN slices in breach (0..n_embb), obs keeps its 10 n_embb + 3 n_mmtc columns.  Correctness-first
+                            *    action entry, and so do the n_mmtc mMTC RAN slices (one queue); action / labels / violations are then
+                            *    [N][(n_embb > 0) + (n_mmtc > 0)], violations count the
+                            *    RAN slices in breach per L1, obs keeps its 10 n_embb + 3 n_mmtc columns.  Correctness-first
                             *    kernel (all fp64, one thread per env, at most 32 UEs per env). */
     double penalty;         /* ran_slice.py:19 */
     double prop_A, prop_B;  /* channel_models.py:117-124 */

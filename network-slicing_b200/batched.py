@@ -30,7 +30,8 @@ class BatchedRanSlice:
         # takes one action entry and reports one label; the observation keeps the 10 variables of every RAN slice
         self.l1_level = bool(l1_level)
         self.n_l1_embb = self.n_embb if self.l1_level else int(self.n_embb > 0)
-        self.n_slices = self.n_l1_embb + self.n_mmtc
+        self.n_l1_mmtc = self.n_mmtc if self.l1_level else int(self.n_mmtc > 0)     # ... and so are the mMTC RAN slices (:173-176)
+        self.n_slices = self.n_l1_embb + self.n_l1_mmtc
         self.n_ran = self.n_embb + self.n_mmtc
         self.n_variables = 10 * self.n_embb + 3 * self.n_mmtc
         self.n_envs, self.device, self.penalty = n_envs, device, penalty

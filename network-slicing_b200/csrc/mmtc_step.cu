@@ -223,6 +223,112 @@ __global__ void __launch_bounds__(128) mmtc_step_kernel(const __grid_constant__ 
     if (flags) atomicOr(p.flags_acc + env, flags);
 }
 
+// Phase 2 for a MULTIPLEXED mMTC L1 (create_env(L1_level=False) with several mMTC slices, scenario_creator.py:173-176;
+// slice_l1.py:87-125): the M RAN slices of an env share ONE queue (kept in the arrays of unit env * M) and one action
+// entry.  Per slot the arrivals are appended RAN slice by RAN slice (each in device order), the first n_prbs queued
+// devices transmit whatever their slice, and every RAN slice accumulates the statistics of its own devices.  The RAN
+// slice of a queued device rides in bits 16.. of its repetition word.  Thread per env.
+__global__ void __launch_bounds__(128) mmtc_step_mux_kernel(const __grid_constant__ StepParams p,
+                                                            const __grid_constant__ MmtcState st) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    const int U = st.U, M = p.n_mmtc;
+    if (env >= p.N) return;
+    const int u0 = env * M, s = p.n_l1e;                         // queue unit; L1 / action index of the multiplexed mMTC slice
+    uint32_t flags = 0;
+    int n_prbs;
+    {
+        const int32_t *a = p.action + (size_t)env * p.S;
+        int off = 0, mine = 0;
+        for (int j = 0; j <= s; ++j) {
+            int v = a[j];
+            if (v < 0) { v = 0; flags |= 4u; }
+            if (off + v > p.n_prbs) { v = p.n_prbs - off; flags |= 4u; }
+            if (j == s) mine = v; else off += v;
+        }
+        n_prbs = mine;
+    }
+    const uint32_t t0 = st.time[u0];
+    int n_arr[MAX_SLICES], next_arr[MAX_SLICES];
+    uint32_t next_key[MAX_SLICES];
+    double a_delay[MAX_SLICES], a_rep[MAX_SLICES];
+    long long a_dev[MAX_SLICES];
+    for (int m = 0; m < M; ++m) {                                // order every RAN slice's arrival list by (slot, device)
+        const int u = u0 + m;
+        st.cur_prbs[u] = n_prbs;
+        const int n = (int)min(st.arr_n[u], (uint32_t)MTC_MAX_ARR);
+        st.arr_n[u] = 0u;
+        for (int a = 1; a < n; ++a) {
+            const uint32_t key = st.arr[(size_t)a * U + u];
+            int b = a - 1;
+            while (b >= 0) {
+                const uint32_t kb = st.arr[(size_t)b * U + u];
+                if (kb <= key) break;
+                st.arr[(size_t)(b + 1) * U + u] = kb;
+                --b;
+            }
+            st.arr[(size_t)(b + 1) * U + u] = key;
+        }
+        n_arr[m] = n; next_arr[m] = 0; next_key[m] = n > 0 ? st.arr[u] : 0xFFFFFFFFu;
+        a_delay[m] = 0.0; a_rep[m] = 0.0; a_dev[m] = 0;
+    }
+    int q_n = st.q_n[u0];
+    for (int t = 1; t <= p.slots; ++t) {
+        const uint32_t now = t0 + (uint32_t)t;
+        for (int m = 0; m < M; ++m) {                            // slice_l1.py:91-95: arrivals of RAN slice m, ascending device index
+            const int u = u0 + m;
+            while ((next_key[m] >> 16) == (uint32_t)t) {
+                if (q_n < st.Q) {
+                    st.q_rep[(size_t)q_n * U + u0] = c_REP_SET[st.rep_ix[(size_t)(next_key[m] & 0xFFFFu) * U + u]] | (m << 16);
+                    st.q_t0[(size_t)q_n * U + u0] = now;
+                    ++q_n;
+                } else flags |= 16u;
+                ++next_arr[m];
+                next_key[m] = next_arr[m] < n_arr[m] ? st.arr[(size_t)next_arr[m] * U + u] : 0xFFFFFFFFu;
+            }
+        }
+        const int n_tx = min(n_prbs, q_n);
+        int w = 0;
+        long long sd[MAX_SLICES], sr[MAX_SLICES];
+        int cnt[MAX_SLICES];
+        for (int m = 0; m < M; ++m) { sd[m] = 0; sr[m] = 0; cnt[m] = 0; }
+        for (int k = 0; k < q_n; ++k) {
+            const int word = st.q_rep[(size_t)k * U + u0];
+            int rep = word & 0xFFFF;
+            const int m = word >> 16;
+            if (k < n_tx) rep -= 1;
+            if (rep > 0) {
+                const uint32_t t_start = st.q_t0[(size_t)k * U + u0];
+                if (w != k) st.q_t0[(size_t)w * U + u0] = t_start;
+                st.q_rep[(size_t)w * U + u0] = rep | (m << 16);
+                sd[m] += (long long)(now - t_start);
+                sr[m] += rep;
+                cnt[m] += 1;
+                ++w;
+            }
+        }
+        q_n = w;
+        for (int m = 0; m < M; ++m)
+            if (cnt[m] > 0) {
+                a_delay[m] += (double)sd[m] / (double)cnt[m];
+                a_rep[m] += rint((double)sr[m] / (double)cnt[m]);
+                a_dev[m] += cnt[m];
+            }
+    }
+    st.q_n[u0] = q_n;
+    int l1_viol = 0;
+    for (int m = 0; m < M; ++m) {
+        const int u = u0 + m;
+        st.time[u] = t0 + (uint32_t)p.slots;                     // (the scan kernel reads every unit's own clock)
+        const double acc[3] = {(double)a_dev[m], a_rep[m], a_delay[m]};
+        float *obs = p.obs + (size_t)env * p.V + p.n_embb * 10 + m * 3;
+        for (int j = 0; j < 3; ++j) { obs[j] = (float)(acc[j] / p.norm_mmtc[j]); st.acc[(size_t)u * 3 + j] = acc[j]; }
+        l1_viol += !(a_delay[m] / (double)p.slots < 300.0);
+    }
+    p.violations[(size_t)env * p.S + s] = l1_viol;              // slice_l1.py:65-75: the L1 adds its RAN slices' violations up
+    p.labels[(size_t)env * p.S + s] = l1_viol ? -1 : 1;
+    if (flags) atomicOr(p.flags_acc + env, flags);
+}
+
 // RanSlice.step epilogue (ran_slice.py:45-54): one thread per env
 __global__ void __launch_bounds__(256) reward_kernel(const __grid_constant__ StepParams p) {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,7 +352,8 @@ int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stre
     if (st.U % 4 == 0) mmtc_scan_kernel_v4<<<dim3((st.U / 4 + 127) / 128, MTC_STRIPS_V4), 128, 0, stream>>>(p, st);
     else mmtc_scan_kernel<<<dim3((st.U + 127) / 128, MTC_STRIPS), 128, 0, stream>>>(p, st);
     if (prof) cudaEventRecord(prof[0], stream);               // profiling: end of the scan kernel
-    mmtc_step_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
+    if (p.n_l1m < p.n_mmtc) mmtc_step_mux_kernel<<<(p.N + 127) / 128, 128, 0, stream>>>(p, st);   // several RAN slices in one L1
+    else mmtc_step_kernel<<<(st.U + 127) / 128, 128, 0, stream>>>(p, st);
     return 2;   // kernels launched
 }
 void launch_reward(const StepParams &p, cudaStream_t stream) {

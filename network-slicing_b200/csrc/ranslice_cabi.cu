@@ -182,9 +182,6 @@ int rs_create(const rs_config *cfg, const rs_tables *tables, rs_handle **out) {
     const int K = mux ? 32 : (cfg->max_ues ? cfg->max_ues : 16), MB = cfg->max_bursts ? cfg->max_bursts : 8;   // a multiplexed L1 holds the UEs of all its RAN slices
     const int Q = cfg->mtc_queue_cap ? cfg->mtc_queue_cap : 128;
     if (K < 2 || K > 32 || MB < 1 || MB > 16 || Q < 1) return fail(RS_E_ARG, "caps out of range");
-    if (mux && cfg->n_mmtc > 1)
-        return fail(RS_E_ARG, "l1_mux with n_mmtc > 1 is not supported: the reference multiplexes all mMTC RAN slices into ONE "
-                              "SliceL1mMTC (scenario_creator.py:173-176), this library keeps one L1 per mMTC slice");
     if (!tables->trace || !tables->mcs_rate || !tables->mcs_snr || !tables->mcs_order || !tables->mcs_mod)
         return fail(RS_E_ARG, "null table pointer");
     int ndev = 0;
@@ -212,7 +209,8 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
     rs::StepParams &p = h->p;
     p.N = cfg->n_envs; p.n_embb = cfg->n_embb; p.n_mmtc = cfg->n_mmtc;
     p.n_l1e = mux ? (cfg->n_embb > 0 ? 1 : 0) : cfg->n_embb;
-    p.S = p.n_l1e + cfg->n_mmtc;
+    p.n_l1m = mux ? (cfg->n_mmtc > 0 ? 1 : 0) : cfg->n_mmtc;   // L1_level=False also multiplexes the mMTC RAN slices (scenario_creator.py:173-176)
+    p.S = p.n_l1e + p.n_l1m;
     p.n_prbs = cfg->n_prbs; p.slots = cfg->slots_per_step; p.V = 10 * cfg->n_embb + 3 * cfg->n_mmtc;
     p.penalty = cfg->penalty; p.prop_A = cfg->prop_A; p.prop_B = cfg->prop_B;
     p.seed0 = cfg->base_seed; p.env0 = (uint32_t)cfg->first_env_id;
@@ -590,7 +588,7 @@ int rs_get_info(rs_handle *h, int32_t env, double *acc, int32_t *n_prbs) {
     }
     if (n_prbs) {
         if (nl) CU(cudaMemcpy(n_prbs, h->embb.cur_prbs + (size_t)env * nl, sizeof(int32_t) * nl, cudaMemcpyDeviceToHost));
-        if (nm) CU(cudaMemcpy(n_prbs + nl, h->mmtc.cur_prbs + (size_t)env * nm, sizeof(int32_t) * nm, cudaMemcpyDeviceToHost));
+        if (nm) CU(cudaMemcpy(n_prbs + nl, h->mmtc.cur_prbs + (size_t)env * nm, sizeof(int32_t) * h->p.n_l1m, cudaMemcpyDeviceToHost));
     }
     return RS_OK;
 }

@@ -151,6 +151,7 @@ struct Tables {
 struct StepParams {
     int N, S, n_embb, n_mmtc, n_prbs, slots, V;   // S = action entries = L1 slices; n_embb / n_mmtc = RAN slices (V = 10 n_embb + 3 n_mmtc)
     int n_l1e;                     // eMBB L1 slices: n_embb, or 1 when they are multiplexed (L1_level=False)
+    int n_l1m;                     // mMTC L1 slices: n_mmtc, or 1 when they are multiplexed (one queue and one action entry for all of them)
     double penalty, prop_A, prop_B;
     double norm_embb[10], norm_mmtc[3];
     double obs_time;               // slots_per_step * slot_length (slice_ran.py:165)

@@ -60,8 +60,8 @@ class RanSlice(_Base):
         else:                                                                           # slice_l1.py:178-181: {i: slice_ran.info}
             if b.n_embb:
                 l1_info.append({r: {n: acc[r, j] for j, n in enumerate(state_variables_embb)} for r in range(b.n_embb)})
-            for m in range(b.n_mmtc):
-                l1_info.append({0: {n: acc[b.n_embb + m, j] for j, n in enumerate(state_variables_mmtc)}})
+            if b.n_mmtc:
+                l1_info.append({m: {n: acc[b.n_embb + m, j] for j, n in enumerate(state_variables_mmtc)} for m in range(b.n_mmtc)})
         info = {'l1_info': l1_info, 'SLA_labels': binfo['SLA_labels'][0].astype(np.int64),
                 'violations': binfo['violations'][0].astype(np.int64), 'n_prbs': [int(x) for x in prbs],
                 'total_violations': int(binfo['total_violations'][0]), 'flags': int(binfo['flags'][0])}

@@ -96,6 +96,7 @@ typedef struct {                /* SliceL1eMBB (slice_l1.py:128-228): one RAN sl
 typedef struct {
     int32_t period[N_MTC_DEV], t_arr[N_MTC_DEV], reps[N_MTC_DEV];
     int64_t *q_rep, *q_t0; int q_n, q_cap;
+    int32_t *q_id;               /* multiplexed mMTC L1 (L1_level=False): RAN slice of every queued device (slice_l1.py:33,80) */
     int64_t time;
     double a_delay, a_rep; int64_t a_dev;
     int n_prbs;
@@ -106,6 +107,7 @@ struct orc_env {
     orc_tables tbl;
     int S;                       /* L1 slices = action entries */
     int n_l1_embb;               /* eMBB L1 slices: n_embb, or 1 when they are multiplexed (scenario_creator.py:156-177) */
+    int n_l1_mmtc;               /* mMTC L1 slices: n_mmtc, or 1 when they are multiplexed (scenario_creator.py:173-176; queue in mmtc[0]) */
     double acc_ran[ORC_MAX_RAN * 2][10];   /* raw accumulators of every RAN slice after the last step, L1-major */
     embb_t *embb; mmtc_t *mmtc;
     orc_rng rng; philox_ctx px; uint32_t *ctr;
@@ -222,7 +224,8 @@ orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed,
     orc_env *e = (orc_env *)calloc(1, sizeof(orc_env));
     e->cfg = *cfg; e->tbl = *tbl;
     e->n_l1_embb = cfg->l1_mux ? (cfg->n_embb > 0) : cfg->n_embb;
-    e->S = e->n_l1_embb + cfg->n_mmtc;
+    e->n_l1_mmtc = cfg->l1_mux ? (cfg->n_mmtc > 0) : cfg->n_mmtc;
+    e->S = e->n_l1_embb + e->n_l1_mmtc;
     e->embb = (embb_t *)calloc(e->n_l1_embb > 0 ? e->n_l1_embb : 1, sizeof(embb_t));
     for (int s = 0; s < e->n_l1_embb; ++s) {
         e->embb[s].ues = (ue_t *)calloc(MAX_UE, sizeof(ue_t));
@@ -247,7 +250,7 @@ orc_env *orc_create(const orc_config *cfg, const orc_tables *tbl, uint64_t seed,
 void orc_destroy(orc_env *e) {
     if (!e) return;
     for (int s = 0; s < e->n_l1_embb; ++s) free(e->embb[s].ues);
-    for (int s = 0; s < e->cfg.n_mmtc; ++s) { free(e->mmtc[s].q_rep); free(e->mmtc[s].q_t0); }
+    for (int s = 0; s < e->cfg.n_mmtc; ++s) { free(e->mmtc[s].q_rep); free(e->mmtc[s].q_t0); free(e->mmtc[s].q_id); }
     free(e->embb); free(e->mmtc); free(e->ctr); free(e);
 }
 
@@ -484,6 +487,44 @@ static void mmtc_slot(mmtc_t *m) {                                          /* s
     m->a_delay += delay; m->a_rep += avg_rep; m->a_dev += w;               /* slice_ran.py:139-142 */
 }
 
+/* SliceL1mMTC.slot with SEVERAL RAN slices (create_env(L1_level=False), scenario_creator.py:173-176; slice_l1.py:87-125): one
+ * queue for all of them (kept in mmtc[0]), arrivals appended RAN slice by RAN slice, the first n_prbs queued devices
+ * transmit whatever their slice, statistics per RAN slice over its own devices. */
+static void mmtc_slot_mux(orc_env *e) {
+    const int M = e->cfg.n_mmtc;
+    mmtc_t *q = &e->mmtc[0];
+    q->time += 1;
+    for (int m = 0; m < M; ++m) {
+        mmtc_t *sl = &e->mmtc[m];
+        for (int i = 0; i < N_MTC_DEV; ++i) sl->t_arr[i] -= 1;
+        for (int i = 0; i < N_MTC_DEV; ++i)
+            if (sl->t_arr[i] == 0) {
+                if (q->q_n == q->q_cap) {
+                    q->q_cap = q->q_cap ? 2 * q->q_cap : 256;
+                    q->q_rep = (int64_t *)realloc(q->q_rep, sizeof(int64_t) * q->q_cap);
+                    q->q_t0 = (int64_t *)realloc(q->q_t0, sizeof(int64_t) * q->q_cap);
+                    q->q_id = (int32_t *)realloc(q->q_id, sizeof(int32_t) * q->q_cap);
+                }
+                q->q_rep[q->q_n] = sl->reps[i]; q->q_t0[q->q_n] = q->time; q->q_id[q->q_n] = m; q->q_n++;
+                sl->t_arr[i] = sl->period[i];
+            }
+    }
+    int n_tx = q->n_prbs < q->q_n ? q->n_prbs : q->q_n;
+    for (int k = 0; k < n_tx; ++k) q->q_rep[k] -= 1;
+    int w = 0;
+    for (int k = 0; k < q->q_n; ++k)
+        if (q->q_rep[k] > 0) { q->q_rep[w] = q->q_rep[k]; q->q_t0[w] = q->q_t0[k]; q->q_id[w] = q->q_id[k]; ++w; }
+    q->q_n = w;
+    for (int m = 0; m < M; ++m) {
+        int64_t sd = 0, sr = 0; int n = 0;
+        for (int k = 0; k < w; ++k)
+            if (q->q_id[k] == m) { int64_t d = q->time - q->q_t0[k]; sd += d > 0 ? d : 0; sr += q->q_rep[k]; ++n; }
+        double delay = 0, avg_rep = 0;
+        if (n > 0) { delay = (double)sd / (double)n; avg_rep = rint((double)sr / (double)n); }
+        e->mmtc[m].a_delay += delay; e->mmtc[m].a_rep += avg_rep; e->mmtc[m].a_dev += n;
+    }
+}
+
 /* ------------------------------------------------------------------ step */
 uint32_t orc_step(orc_env *e, const int64_t *action, float *obs, double *reward, int32_t *labels,
                   int32_t *violations, double *acc) {
@@ -497,12 +538,13 @@ uint32_t orc_step(orc_env *e, const int64_t *action, float *obs, double *reward,
         if (a < 0) { a = 0; e->flags |= 4u; }
         if (i_prb + a > c->n_prbs) { a = c->n_prbs - i_prb; e->flags |= 4u; }   /* reference: undefined */
         if (s < e->n_l1_embb) { e->embb[s].i_prb = (int)i_prb; e->embb[s].n_prbs = (int)a; }
-        else e->mmtc[s - e->n_l1_embb].n_prbs = (int)a;
+        else e->mmtc[s - e->n_l1_embb].n_prbs = (int)a;                   /* (a multiplexed mMTC L1 keeps its PRBs in mmtc[0]) */
         i_prb += a;
     }
     for (int t = 0; t < c->slots_per_step; ++t) {                           /* node_b.py:77-78, 35-38 */
         for (int s = 0; s < e->n_l1_embb; ++s) embb_slot(e, s);
-        for (int s = 0; s < c->n_mmtc; ++s) mmtc_slot(&e->mmtc[s]);
+        if (c->l1_mux && c->n_mmtc > 1) mmtc_slot_mux(e);
+        else for (int s = 0; s < c->n_mmtc; ++s) mmtc_slot(&e->mmtc[s]);
     }
     int64_t tv = 0; int v = 0;
     const double obs_time = c->slots_per_step * 1e-3;                       /* slice_ran.py:165 */
@@ -521,16 +563,20 @@ uint32_t orc_step(orc_env *e, const int64_t *action, float *obs, double *reward,
         }
         violations[s] = l1_viol; labels[s] = l1_viol ? -1 : 1; tv += l1_viol;   /* slice_l1.py:160-171: sum of the RAN slices' violations */
     }
+    const int mtc_mux = c->l1_mux && c->n_mmtc > 1;
+    int mux_viol = 0;
     for (int s = 0; s < c->n_mmtc; ++s) {                                   /* slice_ran.py:133-148 */
-        mmtc_t *m = &e->mmtc[s]; int gs = e->n_l1_embb + s;
+        mmtc_t *m = &e->mmtc[s]; int gs = e->n_l1_embb + (mtc_mux ? 0 : s);     /* L1 row of this RAN slice */
         double a[3] = {(double)m->a_dev, m->a_rep, m->a_delay};
         for (int j = 0; j < 10; ++j) e->acc_ran[row][j] = j < 3 ? a[j] : 0.0;
         ++row;
-        for (int j = 0; j < 3; ++j) { obs[v++] = (float)(a[j] / e->norm_mmtc[j]); if (acc) acc[gs * 10 + j] = a[j]; }
-        if (acc) for (int j = 3; j < 10; ++j) acc[gs * 10 + j] = 0;
+        for (int j = 0; j < 3; ++j) { obs[v++] = (float)(a[j] / e->norm_mmtc[j]); if (acc && (!mtc_mux || s == 0)) acc[gs * 10 + j] = a[j]; }
+        if (acc && (!mtc_mux || s == 0)) for (int j = 3; j < 10; ++j) acc[gs * 10 + j] = 0;
         int viol = !(m->a_delay / c->slots_per_step < 300);
-        violations[gs] = viol; labels[gs] = viol ? -1 : 1; tv += viol;
+        if (mtc_mux) mux_viol += viol;                                      /* slice_l1.py:65-75: the L1 adds its RAN slices' violations up */
+        else { violations[gs] = viol; labels[gs] = viol ? -1 : 1; tv += viol; }
     }
+    if (mtc_mux) { int gs = e->n_l1_embb; violations[gs] = mux_viol; labels[gs] = mux_viol ? -1 : 1; tv += mux_viol; }
     if (tv > 0) *reward = -1 * c->penalty * (double)tv;                     /* ran_slice.py:45-52 */
     else *reward = (double)(c->n_prbs - asum > 0 ? c->n_prbs - asum : 0);
     return e->flags;

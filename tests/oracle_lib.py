@@ -121,12 +121,10 @@ class OracleEnv:
     def __init__(self, tables, scenario, seed, slots_per_step=50, penalty=100.0,
                  propagation="macro_cell_urban_2GHz", numpy_rng=None, l1_mux=False, env_id=0):
         n_prbs, n_embb, n_mmtc = SCENARIOS[scenario]
-        if l1_mux and n_mmtc > 1:      # the reference puts all mMTC RAN slices into ONE SliceL1mMTC (scenario_creator.py:173-176)
-            raise ValueError("l1_mux with n_mmtc > 1 is not restated by the oracle")
         A, B = PROPAGATION[propagation]
         self.cfg = OrcConfig(n_prbs, n_embb, n_mmtc, slots_per_step, penalty, A, B, int(bool(l1_mux)), 0)
         self.tbl = c_tables(tables)
-        self.S = (int(n_embb > 0) if l1_mux else n_embb) + n_mmtc      # L1 slices = action entries (create_env(L1_level=False))
+        self.S = (int(n_embb > 0) + int(n_mmtc > 0)) if l1_mux else n_embb + n_mmtc   # L1 slices = action entries (create_env(L1_level=False))
         self.n_ran = n_embb + n_mmtc
         self.V = 10 * n_embb + 3 * n_mmtc
         self.n_prbs = n_prbs

@@ -184,8 +184,11 @@ def make_env_philox(seed, scenario, env_id=0, **kw):
             gen.nominal_sinr.rng = st["chan"]
             l1.snr_generator = gen
         else:
-            st["mtc"] = px.PhiloxStream(seed, i, px.STREAM_MTC, env=env_id)
-            l1.slices_ran[0].rng = st["mtc"]
+            # one stream per mMTC RAN slice: slice id = L1 index + position inside the L1 (a multiplexed L1 holds all of them)
+            st["mtc_all"] = [px.PhiloxStream(seed, i + m, px.STREAM_MTC, env=env_id) for m in range(len(l1.slices_ran))]
+            st["mtc"] = st["mtc_all"][0]
+            for m, sr in enumerate(l1.slices_ran):
+                sr.rng = st["mtc_all"][m]
         streams.append(st)
         orig_slot = l1.slot
 

@@ -42,7 +42,7 @@ def test_golden_B_philox_streams(tables, golden, name, scn):
         assert np.array_equal(lab, g["labels"][:, t]) and np.array_equal(vio, g["violations"][:, t])
 
 
-@pytest.mark.parametrize("name,scn", [("B_mux0", 0), ("B_mux3", 3)])
+@pytest.mark.parametrize("name,scn", [("B_mux0", 0), ("B_mux3", 3), ("B_mux1", 1), ("B_mux2", 2)])
 def test_golden_multiplexed_l1(tables, golden, name, scn):
     """create_env(L1_level=False) (scenario_creator.py:168-177): the eMBB RAN slices share ONE L1 scheduler.
     Oracle (l1_mux) vs the unmodified reference with injected Philox streams: obs, reward, per-L1 labels / violation
@@ -63,6 +63,8 @@ def test_golden_multiplexed_l1(tables, golden, name, scn):
             assert np.array_equal(env.acc_ran(), g["acc_ran"][e, t]), (e, t)
     if scn == 0:
         assert g["violations"].max() > 1            # several RAN slices of one L1 violating in the same period
+    if scn in (1, 2):                               # several mMTC RAN slices in ONE SliceL1mMTC (one queue, one action entry)
+        assert S == 2 and g["violations"][:, :, 1].max() > 1
 
 
 def test_known_answers_mcs_lut(tables, golden):

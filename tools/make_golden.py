@@ -25,7 +25,9 @@ SCN = {0: (5, 200), 1: (5, 150), 2: (5, 100), 3: (2, 70)}   # index -> (S, n_prb
 A_CASES = {"A_scn0": (0, 0, 2000), "A_scn1": (1, 0, 400), "A_scn3": (3, 0, 2000)}
 B_CASES = {"B_scn0": (0, 7000, 8, 300), "B_scn1": (1, 7100, 4, 200), "B_scn3": (3, 7200, 8, 300)}
 # create_env(L1_level=False): the eMBB RAN slices multiplexed in one L1 (scenario_creator.py:168-177); name -> (scn, seed, envs, steps)
-M_CASES = {"B_mux0": (0, 7300, 4, 200), "B_mux3": (3, 7400, 2, 120)}
+M_CASES = {"B_mux0": (0, 7300, 4, 200), "B_mux3": (3, 7400, 2, 120),
+           # scenarios with several mMTC slices: they too share ONE L1 (one queue, one action entry)
+           "B_mux1": (1, 7500, 3, 150), "B_mux2": (2, 7600, 3, 150)}
 
 
 def gen_A(name):
@@ -55,12 +57,13 @@ def _gen_M_env(args):
     import refharness as rh
     scn, base, e, steps = args
     seed = base + e
-    n_embb = SCN[scn][0] - (1 if scn == 3 else 0)
-    S = 1 + (1 if scn == 3 else 0)                           # L1 slices: one multiplexed eMBB L1 (+ the mMTC L1)
+    S = 1 + (1 if scn in (1, 2, 3) else 0)                   # L1 slices: one multiplexed eMBB L1 (+ one mMTC L1)
     env, _ = rh.make_env_philox(base, scn, env_id=e, L1_level=False)
     assert env.n_slices == S
     act = rh.simplex_actions(seed, S, SCN[scn][1], steps)
     act[::9] = act[::9] // 8                                 # starved periods: deep backlogs, contended PF over all RAN slices
+    if scn in (1, 2):
+        act[:, 1] = np.minimum(act[:, 1], 3 + (np.arange(steps) % 11))   # few carriers: the shared mMTC queue builds up across slices
     tr = rh.run_trace(env, act)
     tr["actions"] = act
     if "acc_ran" not in tr:                                  # single RAN slice per L1 (scenario_3): same rows as acc
