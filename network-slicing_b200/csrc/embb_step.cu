@@ -13,6 +13,7 @@
 //   ProportionalFair.allocate       schedulers.py:21-76
 //   MCSCodeset.response             channel_models.py:297-313
 #include "embb_device.cuh"
+#include "embb_fastmath.cuh"
 
 namespace rs {
 
@@ -325,15 +326,14 @@ __global__ void __launch_bounds__(128) embb_step_mux_thread(const __grid_constan
                 const int fading = (int)((rec.meta >> 1) & 3u);
                 walk_trace(r_chan, index, step);
                 rec.meta = pack_meta((int)(rec.meta & 1u), fading, step, index) | ran_bits;
-                const double *col = tb.trace + ((size_t)fading * N_SAMPLES + index) * TRACE_ROWS;
-                double sum = 0.0;
-                int row = i_prb % TRACE_ROWS;
-                for (int j = 0; j < n_prbs; ++j) {
-                    sum += col[row] + rec.nominal;
-                    row = (row + 1 == TRACE_ROWS) ? 0 : row + 1;
-                }
+                // window mean from the prefix table (two or three loads instead of n_prbs: a multiplexed L1 holds most of the
+                // band and a dozen UEs); inside the rounding guard the reference's fp64 mean, as in the other kernels
+                const int isum = window_sum_prefix(tb.trace_pre + (fading * N_SAMPLES + index) * PRE_STRIDE, i_prb % TRACE_ROWS, n_prbs);
+                double mean = (double)isum * (tb.pre_inv / (double)n_prbs) + rec.nominal;
+                if (fabs(mean - floor(mean) - 0.5) < tb.pre_guard)
+                    mean = window_mean_fp64(tb.trace + ((size_t)fading * N_SAMPLES + index) * TRACE_ROWS, i_prb % TRACE_ROWS, n_prbs, rec.nominal);
                 trace_elems += (unsigned)n_prbs;
-                const int e_snr = __double2int_rn(sum / (double)n_prbs);
+                const int e_snr = __double2int_rn(mean);
                 rec.pe = (rec.pe & 0xFFFF) | (e_snr << 16);
             }
             store_rec(ue + k, rec);

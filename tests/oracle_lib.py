@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_SO = os.path.join(_ROOT, "oracle", "libranslice_oracle.so")
+_SO = os.environ.get("RANSLICE_ORACLE_LIB") or os.path.join(_ROOT, "oracle", "libranslice_oracle.so")   # RANSLICE_ORACLE_LIB: sanitizer builds
 
 PROPAGATION = {"macro_cell_urban_2GHz": (128.1, 37.6), "macro_cell_urban_900MHz": (120.9, 37.6),
                "macro_cell_rural": (95.5, 34.1)}
