@@ -47,6 +47,71 @@ __device__ __forceinline__ long long reduce_add_ll(long long v) {
 
 struct WarpCtx { uint32_t c_ran, c_chan, c_vbr, next_dep, flags; int n_ues, cbr_next, vbr_next; };
 
+// ---- multiplexed L1 (create_env(L1_level=False), scenario_creator.py:168-177): the R eMBB RAN slices of an env share ONE L1
+// scheduler, so one warp steps the whole env's eMBB part: lane k owns UE k of ANY RAN slice (at most 32; the UE's RAN slice
+// rides in bits 28-30 of its meta word), lane r < R also owns RAN slice r's arrival countdowns, RAN Philox counter and
+// accumulators.  Arrivals / departures are per RAN slice (each with its own CAC); scheduling, reception and the channel
+// are the L1's.
+struct MuxPark { int cbr_next, vbr_next; uint32_t c_ran; int a_prb0, a_th0; };           // RAN slice r as lane 0 sees it on an event slot
+struct MuxCtx { uint32_t c_chan, c_vbr, flags, next_dep; int n_ues; };
+static __device__ __noinline__ void mux_ran_events(const StepParams &p, const int K, UeRec *ue, MuxPark *mx, const int R, uint32_t k0,
+                                                   uint32_t k1, uint32_t genv, int t, uint32_t clock, MuxCtx &c) {
+    PhiloxStream r_chan{k0, k1, 0u, STREAM_CHAN, c.c_chan, genv}, r_vbr{k0, k1, 0u, STREAM_VBR, c.c_vbr, genv};
+    int n_ues = c.n_ues;
+    uint32_t flags = c.flags;
+    for (int r = 0; r < R; ++r) {                                // for slice_ran in slices_ran: slot(), extract_users, add_users (slice_l1.py:195-198)
+        PhiloxStream r_ran{k0, k1, (uint32_t)r, STREAM_RAN, mx[r].c_ran, genv};
+        int arr_type[2], arr_rem[2], arr_vnext[2], n_arr = 0;
+        if (mx[r].cbr_next == 0) {                                                   // slice_ran.py:205-227
+            mx[r].cbr_next = exp_slots_ms(r_ran, 1.0 / (2.0 / 60.0));
+            const double cbr_prb = (double)mx[r].a_prb0 / (double)t;                 // cbr_cac of THIS RAN slice, :195-203
+            const double cbr_th = (double)mx[r].a_th0 / ((double)t * 1e-3);
+            if (!(cbr_prb >= 20.0 || cbr_th >= 10e6)) {
+                arr_type[n_arr] = 0; arr_vnext[n_arr] = 0;
+                arr_rem[n_arr++] = exp_slots_ms(r_ran, 30.0);
+            }
+        } else mx[r].cbr_next -= 1;
+        if (mx[r].vbr_next == 0) {                                                   // :229-249
+            arr_type[n_arr] = 1;
+            arr_vnext[n_arr] = exp_slots(r_vbr, (1.0 / 1) / 1e-3);                   // VbrSource.__init__: the L1's VBR stream
+            arr_rem[n_arr++] = exp_slots_ms(r_ran, 30.0);
+            mx[r].vbr_next = exp_slots_ms(r_ran, 1.0 / (5.0 / 60.0));
+        } else mx[r].vbr_next -= 1;
+        mx[r].c_ran = r_ran.n;
+        {   // departures of this RAN slice (slice_ran.py:251-261), order of the rest kept (slice_l1.py:188-191)
+            int w = 0;
+            for (int k = 0; k < n_ues; ++k) {
+                const bool mine = (int)(ue[k].meta >> MUX_RAN_SHIFT) == r;
+                if (!(mine && ue[k].dep_at == clock)) {
+                    if (w != k) { UeRec tmp; load_rec(ue + k, tmp); store_rec(ue + w, tmp); }
+                    ++w;
+                }
+            }
+            n_ues = w;
+        }
+        for (int a = 0; a < n_arr; ++a) {                                            // add_users -> insert_user
+            const int rem = arr_rem[a] - 1;
+            if (rem == 0) { flags |= 8u; continue; }
+            if (n_ues >= K) { flags |= 1u; continue; }
+            UeRec rec;
+            const int fading = (int)r_chan.integers(3);
+            const int index = (int)r_chan.integers(N_SAMPLES);
+            const int step = r_chan.integers(2) ? 1 : -1;
+            rec.nominal = draw_nominal_sinr(r_chan, p.prop_A, p.prop_B);
+            rec.meta = pack_meta(arr_type[a], fading, step, index) | ((uint32_t)r << MUX_RAN_SHIFT);
+            rec.dep_at = arr_rem[a] == 0 ? DEP_NEVER : clock + (uint32_t)rem; rec.vnext = arr_vnext[a];
+            rec.bits = 0; rec.th = 0.0; rec.queue = 0; rec.pe = 0; rec.nb = 0;
+#pragma unroll
+            for (int j = 0; j < MAX_BURSTS; ++j) rec.togo[j] = 0;
+            store_rec(ue + n_ues, rec);
+            ++n_ues;
+        }
+    }
+    uint32_t nd = DEP_NEVER;
+    for (int k = 0; k < n_ues; ++k) nd = min(nd, ue[k].dep_at);
+    c.c_chan = r_chan.n; c.c_vbr = r_vbr.n; c.flags = flags; c.next_dep = nd; c.n_ues = n_ues;
+}
+
 // ---- TMA staging of the fading-trace columns.  After the trace walk of a TTI the column of every live UE is
 // known, but its per-PRB values are only read after the PF loop (MI sums of the served sub-bands): each live lane issues one
 // cp.async.bulk.tensor (2-D tensor map over the trace table, box = one whole column of 100 rows = 400 bytes) into its slot of
@@ -76,12 +141,17 @@ __device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int
 #ifndef RS_WARP_MIN_BLOCKS
 #define RS_WARP_MIN_BLOCKS 2
 #endif
+template <bool MUX>
 __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_warp(const __grid_constant__ StepParams p,
                                                                const __grid_constant__ EmbbState st,
                                                                const __grid_constant__ Tables tb, const int heavy_list) {
     __shared__ __align__(128) LutBlock s_lut;                    // MCS / rate LUT, snr_ref, modulation, MI constants, 1/n: ONE bulk copy
-    __shared__ __align__(16) UeRec s_tbl[WP_WARPS][WP_K];        // RAN-event scratch (8 KB)
+    constexpr int TK = MUX ? 32 : WP_K;                          // UE slots per unit (a multiplexed L1 holds the UEs of all its RAN slices)
+    __shared__ __align__(16) UeRec s_tbl[WP_WARPS][TK];          // RAN-event scratch (8 / 16 KB)
     __shared__ WarpCtx s_ctx[WP_WARPS];
+    __shared__ MuxPark s_mux[MUX ? WP_WARPS : 1][MAX_SLICES];
+    __shared__ int s_racc[MUX ? WP_WARPS : 1][MAX_SLICES][2][5]; // per (RAN slice, UE type) sums of one TTI: traffic, bits, PRBs, e_snr, UEs
+    __shared__ unsigned long long s_rq[MUX ? WP_WARPS : 1][MAX_SLICES][2];   // ... and queues
     extern __shared__ __align__(128) unsigned char s_cols[];     // [WP_WARPS][WP_K][TMA_SLOT] staged trace columns
     __shared__ __align__(8) uint64_t s_bar[WP_WARPS + 1];        // one mbarrier per warp (columns) + one for the lookup tables
     const int tid = threadIdx.x;
@@ -97,7 +167,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
     const int8_t *s_mcs = s_lut.mcs, *s_mod = s_lut.mod;
     const float *s_ref = s_lut.ref, *s_inv = s_lut.inv;
     const float (*s_mi)[4] = s_lut.mi;
-    const bool use_tma = tb.tmap_ok != 0;                        // fading-trace columns staged by TMA (else read through L1 / L2)
+    const bool use_tma = !MUX && tb.tmap_ok != 0;                // fading-trace columns staged by TMA (else read through L1 / L2)
 
     const int lane = tid & 31, w = tid >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -108,13 +178,19 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
     const int ix = blockIdx.x * WP_WARPS + w;
     // units: the heavy list of the default route (units whose PF loop was long in the previous step, embb_fast.cu
     // window_kernel), or every unit, heaviest first (variant 3: sorted front list without pair entries)
-    if (ix >= (int)(heavy_list ? st.wlist[st.U] : st.hist[2 * SORT_BINS + 0])) return;            // whole warp
-    const int u = heavy_list ? st.wlist[ix] : st.perm[ix];
-    const int env = u / p.n_embb, s = u - env * p.n_embb;
+    if (ix >= (MUX ? st.U : (int)(heavy_list ? st.wlist[st.U] : st.hist[2 * SORT_BINS + 0]))) return;            // whole warp
+    const int u = MUX ? ix : (heavy_list ? st.wlist[ix] : st.perm[ix]);
+    const int env = MUX ? u : u / p.n_embb, s = MUX ? 0 : u - env * p.n_embb;
+    const int R = MUX ? st.R : 1;
     int i_prb, n_prbs;
-    unpack_window(st.win[u], i_prb, n_prbs);
-    const int row_base = i_prb % TRACE_ROWS;
     uint32_t flags = 0;
+    if (MUX) {                                                   // no sort pre-pass for the multiplexed L1: window from the action
+        uint32_t wf = 0;
+        slice_window(p, env, 0, i_prb, n_prbs, wf);
+        if (lane == 0) { flags = wf; st.cur_prbs[u] = n_prbs; }
+    } else unpack_window(st.win[u], i_prb, n_prbs);
+    const int row_base = i_prb % TRACE_ROWS;
+    MuxRan *mux = MUX ? st.mux + (size_t)u * R : nullptr;
 
     const UnitHdr hdr = st.hdr[u];
     UeRec *ue = st.ue + (size_t)u * st.K;
@@ -125,6 +201,15 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
     uint32_t c_ran = hdr.ctr[0], c_chan = hdr.ctr[1], c_rx = hdr.ctr[2], c_vbr = hdr.ctr[3];
     int n_ues = hdr.n_ues, cbr_next = hdr.cbr_next, vbr_next = hdr.vbr_next;
     uint32_t clock = hdr.clock;
+    if (MUX) {                                                   // lane r < R: countdowns and RAN counter of RAN slice r
+        cbr_next = vbr_next = 1 << 30; c_ran = 0;
+        if (lane < R) { cbr_next = mux[lane].cbr_next; vbr_next = mux[lane].vbr_next; c_ran = mux[lane].c_ran; }
+        for (int i = lane; i < MAX_SLICES * 2 * 5; i += 32) (&s_racc[w][0][0][0])[i] = 0;
+        if (lane < MAX_SLICES * 2) (&s_rq[w][0][0])[lane] = 0ull;
+        __syncwarp();
+    }
+    int m_tr[2] = {0, 0}, m_th[2] = {0, 0}, m_pr[2] = {0, 0};    // multiplexed L1, lane r < R: accumulators of RAN slice r by UE type
+    double m_q[2] = {0.0, 0.0}, m_s[2] = {0.0, 0.0};
 
     UeRec r;                                                     // lane k < n_ues: UE k
     {
@@ -144,7 +229,27 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
     for (int t = 1; t <= p.slots; ++t) {          // slot_counter == t (zeroed by reset_info each step)
         ++clock;
         // ================= slice_ran.slot(): arrivals / departures only on event slots (serial: lane 0 on the parked table)
-        if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
+        if (MUX) {
+            const bool any = __ballot_sync(FULL, lane < R && (cbr_next == 0 || vbr_next == 0)) != 0u || clock == next_dep;
+            if (any) {
+                if (lane < n_ues) store_rec(tbl + lane, r);
+                if (lane < R) s_mux[w][lane] = MuxPark{cbr_next, vbr_next, c_ran, m_pr[0], m_th[0]};
+                __syncwarp();
+                if (lane == 0) {
+                    MuxCtx c{c_chan, c_vbr, flags, next_dep, n_ues};
+                    mux_ran_events(p, min(st.K, TK), tbl, s_mux[w], R, k0, k1, genv, t, clock, c);
+                    s_ctx[w] = WarpCtx{0u, c.c_chan, c.c_vbr, c.next_dep, c.flags, c.n_ues, 0, 0};
+                }
+                __syncwarp();
+                const WarpCtx c = s_ctx[w];
+                c_chan = c.c_chan; c_vbr = c.c_vbr; next_dep = c.next_dep;
+                if (lane == 0) flags = c.flags;
+                n_ues = c.n_ues;
+                if (lane < R) { cbr_next = s_mux[w][lane].cbr_next; vbr_next = s_mux[w][lane].vbr_next; c_ran = s_mux[w][lane].c_ran; }
+                if (lane < n_ues) load_rec(tbl + lane, r);
+                __syncwarp();
+            } else if (lane < R) { cbr_next -= 1; vbr_next -= 1; }
+        } else if (cbr_next == 0 || vbr_next == 0 || clock == next_dep) {
             if (lane < n_ues) store_rec(tbl + lane, r);
             __syncwarp();
             if (lane == 0) {
@@ -178,7 +283,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
         }
         int col_off = 0;
         if (n_prbs > 0) {                                        // uniform
-            int index = (int)(r.meta >> 4), step = (r.meta & 8u) ? 1 : -1;
+            int index = (int)((r.meta >> 4) & MUX_INDEX_MASK), step = (r.meta & 8u) ? 1 : -1;   // (bits 28-30: RAN slice of a multiplexed L1, else 0)
             const int fading = (int)((r.meta >> 1) & 3u);
             index += step;                                       // channel_models.py:171-191
             unsigned redraw = __ballot_sync(FULL, live && (index >= N_SAMPLES - 1 || index < 0));
@@ -194,7 +299,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
                 c_chan = __shfl_sync(FULL, cn, src);
             }
             if (live) {
-                r.meta = pack_meta(ty, fading, step, index);
+                r.meta = pack_meta(ty, fading, step, index) | (r.meta & (7u << MUX_RAN_SHIFT));
                 col_off = (fading * N_SAMPLES + index) * TRACE_ROWS;
                 const int isum = window_sum_prefix(tb.trace_pre + (fading * N_SAMPLES + index) * PRE_STRIDE, row_base, n_prbs);
                 trace_elems += (unsigned)n_prbs;
@@ -219,13 +324,17 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
         double thpf = r.th > 1.0 ? r.th : 1.0;
         float metf = live && r.queue > 0 ? (float)rate * rcp_approx((float)thpf) : 0.0f;
         // update_info terms that are already final (slice_ran.py:278-305)
-        a_traffic_all += __reduce_add_sync(FULL, nb_bits); a_traffic_v += __reduce_add_sync(FULL, ty ? nb_bits : 0);
-        const int sn_all = __reduce_add_sync(FULL, live ? (r.pe >> 16) : 0), sn_v = __reduce_add_sync(FULL, live && ty ? (r.pe >> 16) : 0);
-        const int cnt_all = n_ues, cnt_v = __popc(__ballot_sync(FULL, live && ty));
+        int sn_all = 0, sn_v = 0, cnt_v = 0;
+        const int cnt_all = n_ues;
+        if (!MUX) {
+            a_traffic_all += __reduce_add_sync(FULL, nb_bits); a_traffic_v += __reduce_add_sync(FULL, ty ? nb_bits : 0);
+            sn_all = __reduce_add_sync(FULL, live ? (r.pe >> 16) : 0); sn_v = __reduce_add_sync(FULL, live && ty ? (r.pe >> 16) : 0);
+            cnt_v = __popc(__ballot_sync(FULL, live && ty));
+        }
         int n_backlog = __popc(__ballot_sync(FULL, live && r.queue > 0));
 
         // ================= scheduling + reception (slice_l1.py:215-224)
-        long long qsum_all, qsum_v;
+        int tti_bits = 0, tti_prbs = 0;                          // this UE's received bits and PRBs of the TTI (stale when unscheduled)
         if (n_backlog > 0 && n_prbs > 0) {                       // queued_data > 0 <=> some queue > 0 (uniform)
             int bits_l = 0, rbs_l = 0;                           // ue_bits, ue_rbs of this lane's UE
             int rr = 0;
@@ -373,26 +482,74 @@ __global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_w
                 r.bits = b;
                 r.pe = (r.pe & (int)0xFFFF0000) | rbs_l;
             }
-            a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
-            a_prb_all += __reduce_add_sync(FULL, rbs_l); a_prb_v += __reduce_add_sync(FULL, ty ? rbs_l : 0);
+            tti_bits = b; tti_prbs = rbs_l;
         } else {                                                 // nothing touched: stale bits / prbs accumulate
             if (use_tma && n_prbs > 0 && n_ues > 0) { mbar_wait(&s_bar[w], tma_phase); tma_phase ^= 1u; }   // (columns staged but not needed)
-            const int b = live ? r.bits : 0, prbs = live ? (r.pe & 0xFFFF) : 0;
-            a_th_all += __reduce_add_sync(FULL, b); a_th_v += __reduce_add_sync(FULL, ty ? b : 0);
-            a_prb_all += __reduce_add_sync(FULL, prbs); a_prb_v += __reduce_add_sync(FULL, ty ? prbs : 0);
+            tti_bits = live ? r.bits : 0; tti_prbs = live ? (r.pe & 0xFFFF) : 0;
         }
-        qsum_all = reduce_add_ll(live ? r.queue : 0); qsum_v = reduce_add_ll(live && ty ? r.queue : 0);
-        // ================= update_info means (slice_ran.py:290-291, 304-305)
-        a_queue_c += div_count((double)(qsum_all - qsum_v), cnt_all - cnt_v);
-        a_snr_c += div_count((double)(sn_all - sn_v), cnt_all - cnt_v);
-        a_queue_v += div_count((double)qsum_v, cnt_v);
-        a_snr_v += div_count((double)sn_v, cnt_v);
+        // ================= update_info (slice_ran.py:278-305): sums over the UEs, means per UE type
+        if (!MUX) {
+            a_th_all += __reduce_add_sync(FULL, tti_bits); a_th_v += __reduce_add_sync(FULL, ty ? tti_bits : 0);
+            a_prb_all += __reduce_add_sync(FULL, tti_prbs); a_prb_v += __reduce_add_sync(FULL, ty ? tti_prbs : 0);
+            const long long qsum_all = reduce_add_ll(live ? r.queue : 0), qsum_v = reduce_add_ll(live && ty ? r.queue : 0);
+            a_queue_c += div_count((double)(qsum_all - qsum_v), cnt_all - cnt_v);
+            a_snr_c += div_count((double)(sn_all - sn_v), cnt_all - cnt_v);
+            a_queue_v += div_count((double)qsum_v, cnt_v);
+            a_snr_v += div_count((double)sn_v, cnt_v);
+        } else {                                                 // every RAN slice over its own UEs: integer atomics (exact in any order), lane r collects
+            if (live) {
+                const int ran = (int)(r.meta >> MUX_RAN_SHIFT);
+                int *A = s_racc[w][ran][ty];
+                atomicAdd(&A[0], nb_bits); atomicAdd(&A[1], tti_bits); atomicAdd(&A[2], tti_prbs); atomicAdd(&A[3], r.pe >> 16); atomicAdd(&A[4], 1);
+                atomicAdd(&s_rq[w][ran][ty], (unsigned long long)r.queue);
+            }
+            __syncwarp();
+            if (lane < R) {
+#pragma unroll
+                for (int y = 0; y < 2; ++y) {
+                    int *A = s_racc[w][lane][y];
+                    m_tr[y] += A[0]; m_th[y] += A[1]; m_pr[y] += A[2];
+                    const double nn = (double)max(A[4], 1);
+                    m_q[y] += (double)(long long)s_rq[w][lane][y] / nn;
+                    m_s[y] += (double)A[3] / nn;
+                    A[0] = A[1] = A[2] = A[3] = A[4] = 0; s_rq[w][lane][y] = 0ull;
+                }
+            }
+            __syncwarp();
+        }
     }
 
     // ---- write the records back (once per step) and persist the slice scalars
     if (lane < n_ues) store_rec(ue + lane, r);
     flags = __reduce_or_sync(FULL, flags);
     trace_elems = __reduce_add_sync(FULL, trace_elems); slow_snr = __reduce_add_sync(FULL, slow_snr); slow_rx = __reduce_add_sync(FULL, slow_rx);
+    if (MUX) {                                                   // state of every RAN slice (slice_ran.py:307-325); the L1 adds their violations up (slice_l1.py:160-171)
+        int viol = 0;
+        if (lane < R) {
+            mux[lane].cbr_next = cbr_next; mux[lane].vbr_next = vbr_next; mux[lane].c_ran = c_ran;
+            const double acc[10] = {(double)m_tr[0], (double)m_th[0], (double)m_pr[0], m_q[0], m_s[0],
+                                    (double)m_tr[1], (double)m_th[1], (double)m_pr[1], m_q[1], m_s[1]};
+            float *obs = p.obs + (size_t)env * p.V + lane * 10;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { obs[j] = (float)(acc[j] / p.norm_embb[j]); st.acc[((size_t)u * R + lane) * 10 + j] = acc[j]; }
+            const double sps = (double)p.slots;
+            const bool cbr_ok = acc[1] / p.obs_time > 10e6 || acc[2] / sps > 20.0 || acc[3] / sps < 10e4;
+            const bool vbr_ok = acc[6] / p.obs_time > 15e6 || acc[7] / sps > 30.0 || acc[8] / sps < 15e4;
+            viol = !(cbr_ok && vbr_ok);
+        }
+        const int l1_viol = __reduce_add_sync(FULL, viol);
+        if (lane != 0) return;
+        UnitHdr hm = hdr;
+        hm.n_ues = n_ues; hm.clock = clock; hm.ctr[1] = c_chan; hm.ctr[2] = c_rx; hm.ctr[3] = c_vbr;
+        st.hdr[u] = hm;
+        p.violations[(size_t)env * p.S] = l1_viol;
+        p.labels[(size_t)env * p.S] = l1_viol ? -1 : 1;
+        if (flags) atomicOr(p.flags_acc + env, flags);
+        if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
+        if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
+        if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
+        return;
+    }
     if (lane != 0) return;
     UnitHdr h2 = hdr;
     h2.n_ues = n_ues; h2.cbr_next = cbr_next; h2.vbr_next = vbr_next; h2.clock = clock;
@@ -413,7 +570,7 @@ void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ue
 static size_t warp_dyn_smem() {
     static bool configured = false;
     constexpr size_t bytes = (size_t)WP_WARPS * WP_K * TMA_SLOT;
-    if (!configured) { cudaFuncSetAttribute(embb_step_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
+    if (!configured) { cudaFuncSetAttribute(embb_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
     return bytes;
 }
 
@@ -421,13 +578,18 @@ static size_t warp_dyn_smem() {
 int launch_embb_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
     launch_embb_sort(p, st, 1 << 30, 1 << 30, stream);
     if (prof) cudaEventRecord(prof[0], stream);
-    embb_step_warp<<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 0);
+    embb_step_warp<false><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 0);
     if (prof) cudaEventRecord(prof[1], stream);
     return 5;   // kernels launched
 }
 // the heavy list of the default route (at most heavy_cap units), concurrent with the shared-memory kernel on another stream
 void launch_embb_warp_heavy(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    embb_step_warp<<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 1);
+    embb_step_warp<false><<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 1);
+}
+
+// multiplexed L1 (L1_level=False): one warp per env
+void launch_embb_mux_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
+    embb_step_warp<true><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 0);
 }
 
 }  // namespace rs

@@ -23,6 +23,7 @@ void launch_embb_reset(const EmbbState &st, cudaStream_t stream);
 void launch_mmtc_reset(const StepParams &p, const MmtcState &st, cudaStream_t stream);
 int launch_mmtc_step(const StepParams &p, const MmtcState &st, cudaStream_t stream, cudaEvent_t *prof);
 void launch_embb_mux(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
+void launch_embb_mux_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream);
 void launch_embb_mux_reset(const EmbbState &st, cudaStream_t stream);
 void launch_reward(const StepParams &p, cudaStream_t stream);
 }  // namespace rs
@@ -490,7 +491,10 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
         CU(cudaEventRecord(h->ev_join, h->side_stream));
     }
     if (h->embb.U) {
-        if (h->cfg.l1_mux) { rs::launch_embb_mux(p, h->embb, h->tb, st); h->launches += 1; }
+        if (h->cfg.l1_mux) {                                        // multiplexed L1: warp per env; kernel_variant 1 = the all-fp64 thread-per-env anchor
+            if (h->cfg.kernel_variant == 1) rs::launch_embb_mux(p, h->embb, h->tb, st); else rs::launch_embb_mux_warp(p, h->embb, h->tb, st);
+            h->launches += 1;
+        }
         else if (h->cfg.kernel_variant == 1) { rs::launch_embb_unit_thread(p, h->embb, h->tb, st); h->launches += 1; }
         else if (h->use_warp) { h->launches += rs::launch_embb_warp(p, h->embb, h->tb, st, h->profiling ? ev + 1 : nullptr); dominant = true; }
         else if (h->cfg.kernel_variant == 2 || h->cfg.kernel_variant == 3 || h->embb.K > 16) h->launches += rs::launch_embb_fast(p, h->embb, h->tb, st);

@@ -263,14 +263,15 @@ def test_pipelined_host_api_matches_blocking_step():
 
 
 # ------------------------------------------------------------------------------------------------ L1_level=False
+@pytest.mark.parametrize("variant", [0, 1])       # 0: warp per env (lanes over the UEs of all RAN slices); 1: all-fp64 thread-per-env anchor
 @pytest.mark.parametrize("name,scn", [("B_mux0", 0), ("B_mux3", 3), ("B_mux1", 1), ("B_mux2", 2)])
-def test_multiplexed_l1_reference_fixture(golden, name, scn):
+def test_multiplexed_l1_reference_fixture(golden, name, scn, variant):
     """create_env(L1_level=False): CUDA (through the C ABI) vs the unmodified reference with injected Philox streams --
     obs, reward, per-L1 labels and violation counts, raw accumulators of every RAN slice, bit-exact."""
     g = golden(name)
     E, T, S = g["actions"].shape
     # (B_mux1 / B_mux2 starve the shared mMTC queue on purpose: thousands of queued devices, the reference is unbounded)
-    env = make_env(scn, E, int(g["base_seed"]), L1_level=False, mtc_queue_cap=8192 if scn in (1, 2) else 0)
+    env = make_env(scn, E, int(g["base_seed"]), L1_level=False, mtc_queue_cap=8192 if scn in (1, 2) else 0, kernel_variant=variant)
     assert env.n_slices == S
     assert np.array_equal(env.reset(), g["obs0"])
     for t in range(T):
