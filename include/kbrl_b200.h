@@ -14,6 +14,7 @@
  */
 #ifndef KBRL_B200_H
 #define KBRL_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -93,6 +94,12 @@ int kb_get_sizes(kb_handle *h, int32_t *sizes, uint32_t *flags);
 int kb_get_pool(kb_handle *h, uint64_t *used_bytes, uint64_t *total_bytes, int32_t *max_dictionary, uint64_t *tie_breaks);
 /* dictionary of one learner, packed: landmarks [D][dims[s]], coeff [D], kinv [D][D]; returns D in *D_out */
 int kb_get_learner(kb_handle *h, int32_t learner, double *landmarks, double *coeff, double *kinv, int32_t *D_out);
+/* checkpoint / restore of the learners (dictionaries: only the part of the pool in use) and, when kb_control_init has been
+ * called, of the controller state; the blob belongs to handles of the same shape (n_envs, n_slices, n_prbs, dict_cap).
+ * kb_state_size synchronises and reports the size the NEXT kb_get_state needs (it grows with the dictionaries). */
+int kb_state_size(kb_handle *h, size_t *bytes);
+int kb_get_state(kb_handle *h, void *blob, size_t bytes);
+int kb_set_state(kb_handle *h, const void *blob, size_t bytes);
 /* Validation switch: with on != 0 every kernel evaluation f(x) is done in fp64 in the reference's operation order;
  * by default f is first summed in guarded fp32 and only re-evaluated in fp64 when its sign is not certain
  * (csrc/kbrl.cu eval_f_guarded).  Decisions are identical either way (tests/test_gpu_kbrl.py). */

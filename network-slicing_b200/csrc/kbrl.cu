@@ -36,6 +36,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -221,6 +222,35 @@ __device__ __forceinline__ double eval_f_guarded(int D, double gamma, const doub
     if (fabsf(f) > (4e-5f + 3e-7f * (float)D) * G) return (double)f;
     if (slow) ++*slow;
     return eval_f(D, gamma, base, cf, ll, xa);
+}
+
+// The same evaluation shared by P adjacent lanes (wide groups: a 1024-thread group has five threads per candidate): lane
+// `part` sums the landmarks j = part (mod P) in fp32, the partial (f, G) are added across the P lanes, and the guard test
+// is made on the totals (its bound covers any summation order of the fp32 terms).  Inside the band -- and for dictionaries
+// of 0 or 1 landmarks -- lane 0 of the P evaluates exactly, in the reference's order, and the others take its value.
+template <int P>
+__device__ __forceinline__ double eval_f_guarded_split(int D, double gamma, const double *base, const double *cf, const double *ll,
+                                                       const float4 *fast, bool fast_ok, double xa, int part) {
+    float f = 0.f, G = 0.f;
+    const bool try_fast = D > 1 && fast_ok;
+    if (try_fast) {
+        const float xf = (float)xa, g2 = (float)gamma * LOG2E;
+        for (int j = part; j < D; j += P) {
+            const float4 e = fast[j];
+            const float t = e.z - xf;
+            const float term = e.y * ex2f(-fmaf(t * t, g2, e.x));
+            f += term;
+            G += fabsf(term);
+        }
+    }
+#pragma unroll
+    for (int d = 1; d < P; d <<= 1) { f += __shfl_xor_sync(0xffffffffu, f, d); G += __shfl_xor_sync(0xffffffffu, G, d); }
+    double r = (double)f;
+    const bool exact = !try_fast || !(fabsf(f) > (4e-5f + 3e-7f * (float)D) * G);
+    if (exact && part == 0) r = eval_f(D, gamma, base, cf, ll, xa);
+    int lo = __double2loint(r), hi = __double2hiint(r);          // (unconditional: every lane of the warp takes part in the shuffle)
+    lo = __shfl_sync(0xffffffffu, lo, 0, P); hi = __shfl_sync(0xffffffffu, hi, 0, P);
+    return __hiloint2double(hi, lo);
 }
 
 // Stages the dictionary of a learner for state xs: exact fp64 (base, coeff, last coordinate) and the fp32 copy of the
@@ -450,6 +480,18 @@ __device__ void update_learner(const State &kb, const int capS, const bool hand_
         if (gt == 0) g.first = 1 << 30;
         gsync<GROUP>(group);
         int first = 1 << 30;                                   // key: a << 1 | (f != 0)
+        if (GROUP >= 1024) {                                   // at most 201 candidates: four threads each (whole warps stay in the loop)
+            constexpr int P = 4;
+            for (int a0w = cur; a0w <= hi; a0w += GROUP / P) {
+                const int a = a0w + gt / P;
+                const double f = eval_f_guarded_split<P>(a <= hi ? D : 0, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)n, gt % P);
+                if (a <= hi && gt % P == 0) {
+                    if (first_round && a == a0) g.fa0 = f;
+                    const bool act = kb.plus ? f * (double)y < 1.0 : f * (double)y <= 0.0;
+                    if (act) first = min(first, (a << 1) | (f != 0.0));
+                }
+            }
+        } else
         for (int a = cur + gt; a <= hi; a += GROUP) {
             const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)n, nullptr);
             if (first_round && a == a0) g.fa0 = f;
@@ -551,9 +593,19 @@ __device__ void update_learner(const State &kb, const int capS, const bool hand_
             gsync<GROUP>(group);
             kinv_matvec<GROUP>(rowp, D, kf, ds, gt);
             gsync<GROUP>(group);
-            if (gt == 0) {                                   // delta = max(Kii - d* . k, 0), index order; f for ProjectronPlus
-                double dot = 0.0;
-                for (int i = 0; i < D; ++i) dot += ds[i] * kf[i];
+            // delta = max(Kii - d* . k, 0): 32 strided partial sums + a shuffle tree in the group's first warp (a serial sum by one
+            // thread was 40 % of an update at D = 500; numpy's own dot is a BLAS ddot with several SIMD accumulators)
+            double dot = 0.0;
+            if (gt < 32) {
+                for (int i = gt; i < D; i += 32) dot += ds[i] * kf[i];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    int lo = __double2loint(dot), hi = __double2hiint(dot);
+                    lo = __shfl_xor_sync(0xffffffffu, lo, d); hi = __shfl_xor_sync(0xffffffffu, hi, d);
+                    dot += __hiloint2double(hi, lo);
+                }
+            }
+            if (gt == 0) {                                   // (f for ProjectronPlus)
                 double delta = 1.0 - dot;
                 g.delta = delta < 0.0 ? 0.0 : delta;
                 g.ok = 1;
@@ -1035,6 +1087,88 @@ int kb_get_learner(kb_handle *h, int32_t l, double *landmarks, double *coeff, do
         if (kinv) KCU(cudaMemcpy(kinv, g_kinv, (size_t)D * D * sizeof(double), cudaMemcpyDeviceToHost));
     }
     if (D_out) *D_out = D;
+    return RS_OK;
+}
+
+// ---- checkpoint / restore (state_dict-style dump): dictionaries (only the part of the pool in use), per-learner
+// bookkeeping and, when kb_control_init has been called, the controller state.  Blob layout: KbBlobHdr, D[L], rows[L][tmax],
+// flags[L], tie_ctr[L], pool[cursor], then acc[L][n_prbs], sec[L], margins[L], action[L], adjusted[N].
+struct KbBlobHdr { uint64_t magic, L, tmax, n_prbs, n_envs, cursor, has_ctl, max_d; };
+static const uint64_t KB_BLOB_MAGIC = 0x4B42524C32303236ull;   // "KBRL2026"
+static size_t kb_blob_bytes(const kb_handle *h, unsigned long long cursor) {
+    const size_t L = (size_t)h->st.L;
+    size_t b = sizeof(KbBlobHdr) + L * sizeof(int) + L * h->st.tmax * sizeof(unsigned long long) + 2 * L * sizeof(uint32_t) + (size_t)cursor * sizeof(double);
+    if (h->ctl.acc) b += L * h->st.n_prbs * sizeof(double) + 3 * L * sizeof(int32_t) + (size_t)h->cfg.n_envs * sizeof(int32_t);
+    return b;
+}
+int kb_state_size(kb_handle *h, size_t *bytes) {
+    if (!h || !bytes) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    unsigned long long cur = 0;
+    KCU(cudaMemcpy(&cur, h->st.cursor, sizeof cur, cudaMemcpyDeviceToHost));
+    *bytes = kb_blob_bytes(h, cur);
+    return RS_OK;
+}
+int kb_get_state(kb_handle *h, void *blob, size_t bytes) {
+    if (!h || !blob) return kfail(RS_E_ARG, "null argument");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    unsigned long long cur = 0;
+    int md = 0;
+    KCU(cudaMemcpy(&cur, h->st.cursor, sizeof cur, cudaMemcpyDeviceToHost));
+    KCU(cudaMemcpy(&md, h->st.max_d, sizeof md, cudaMemcpyDeviceToHost));
+    if (bytes != kb_blob_bytes(h, cur)) return kfail(RS_E_ARG, "bad blob size (call kb_state_size first)");
+    const size_t L = (size_t)h->st.L;
+    char *p = static_cast<char *>(blob);
+    const KbBlobHdr hdr{KB_BLOB_MAGIC, (uint64_t)L, (uint64_t)h->st.tmax, (uint64_t)h->st.n_prbs, (uint64_t)h->cfg.n_envs, cur, h->ctl.acc ? 1ull : 0ull, (uint64_t)md};
+    std::memcpy(p, &hdr, sizeof hdr); p += sizeof hdr;
+    auto out = [&](const void *d, size_t n) -> cudaError_t { cudaError_t e = cudaMemcpy(p, d, n, cudaMemcpyDeviceToHost); p += n; return e; };
+    KCU(out(h->st.D, L * sizeof(int)));
+    KCU(out(h->st.rows, L * h->st.tmax * sizeof(unsigned long long)));
+    KCU(out(h->st.flags, L * sizeof(uint32_t)));
+    KCU(out(h->st.tie_ctr, L * sizeof(uint32_t)));
+    KCU(out(h->st.pool, (size_t)cur * sizeof(double)));
+    if (h->ctl.acc) {
+        KCU(out(h->ctl.acc, L * h->st.n_prbs * sizeof(double)));
+        KCU(out(h->ctl.sec, L * sizeof(int32_t)));
+        KCU(out(h->ctl.margins, L * sizeof(int32_t)));
+        KCU(out(h->ctl.action, L * sizeof(int32_t)));
+        KCU(out(h->ctl.adjusted, (size_t)h->cfg.n_envs * sizeof(int32_t)));
+    }
+    return RS_OK;
+}
+int kb_set_state(kb_handle *h, const void *blob, size_t bytes) {
+    if (!h || !blob || bytes < sizeof(KbBlobHdr)) return kfail(RS_E_ARG, "null argument / short blob");
+    KCU(cudaSetDevice(h->cfg.device));
+    KCU(cudaDeviceSynchronize());
+    KbBlobHdr hdr;
+    std::memcpy(&hdr, blob, sizeof hdr);
+    const size_t L = (size_t)h->st.L;
+    if (hdr.magic != KB_BLOB_MAGIC || hdr.L != L || hdr.tmax != (uint64_t)h->st.tmax || hdr.n_prbs != (uint64_t)h->st.n_prbs ||
+        hdr.n_envs != (uint64_t)h->cfg.n_envs)
+        return kfail(RS_E_ARG, "blob does not belong to a handle of this shape (learners, dict_cap, n_prbs)");
+    if (hdr.cursor > h->st.pool_doubles) return kfail(RS_E_NOMEM, "the dictionary pool of this handle is smaller than the checkpoint");
+    if ((hdr.has_ctl != 0) != (h->ctl.acc != nullptr)) return kfail(RS_E_STATE, "controller state: call kb_control_init on both handles or on neither");
+    if (bytes != kb_blob_bytes(h, hdr.cursor)) return kfail(RS_E_ARG, "bad blob size");
+    const char *p = static_cast<const char *>(blob) + sizeof hdr;
+    auto in = [&](void *d, size_t n) -> cudaError_t { cudaError_t e = cudaMemcpy(d, p, n, cudaMemcpyHostToDevice); p += n; return e; };
+    KCU(in(h->st.D, L * sizeof(int)));
+    KCU(in(h->st.rows, L * h->st.tmax * sizeof(unsigned long long)));
+    KCU(in(h->st.flags, L * sizeof(uint32_t)));
+    KCU(in(h->st.tie_ctr, L * sizeof(uint32_t)));
+    KCU(in(h->st.pool, (size_t)hdr.cursor * sizeof(double)));
+    if (h->ctl.acc) {
+        KCU(in(h->ctl.acc, L * h->st.n_prbs * sizeof(double)));
+        KCU(in(h->ctl.sec, L * sizeof(int32_t)));
+        KCU(in(h->ctl.margins, L * sizeof(int32_t)));
+        KCU(in(h->ctl.action, L * sizeof(int32_t)));
+        KCU(in(h->ctl.adjusted, (size_t)h->cfg.n_envs * sizeof(int32_t)));
+    }
+    const unsigned long long cur = hdr.cursor;
+    const int md = (int)hdr.max_d;
+    KCU(cudaMemcpy(h->st.cursor, &cur, sizeof cur, cudaMemcpyHostToDevice));
+    KCU(cudaMemcpy(h->st.max_d, &md, sizeof md, cudaMemcpyHostToDevice));
     return RS_OK;
 }
 

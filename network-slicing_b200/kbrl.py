@@ -51,10 +51,13 @@ def _bind(L):
     L.kb_get_sizes.argtypes = [vp, vp, vp]
     L.kb_get_learner.argtypes = [vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_int32)]
     L.kb_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.kb_state_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.kb_get_state.argtypes = [vp, vp, C.c_size_t]
+    L.kb_set_state.argtypes = [vp, vp, C.c_size_t]
     L.kb_get_pool.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
     for n in ("kb_create", "kb_destroy", "kb_reset", "kb_update", "kb_predict", "kb_update_device", "kb_predict_device",
               "kb_get_sizes", "kb_get_learner", "kb_get_counters", "kb_control_init", "kb_control_update_device",
-              "kb_control_select_device", "kb_control_get", "kb_set_exact", "kb_get_pool"):
+              "kb_control_select_device", "kb_control_get", "kb_set_exact", "kb_get_pool", "kb_state_size", "kb_get_state", "kb_set_state"):
         getattr(L, n).restype = C.c_int
     L._kb_bound = True
     return L
@@ -159,6 +162,18 @@ class BatchedProjectron:
         Dout = C.c_int32()
         _lib.check(self._L.kb_get_learner(self._h, l, _p(lm), _p(cf), _p(ki), C.byref(Dout)))
         return lm[:D], cf[:D], ki[:D, :D]
+
+    def get_state(self):
+        """Checkpoint of the learners (and of the device-resident controller, if any) as a uint8 array."""
+        n = C.c_size_t()
+        _lib.check(self._L.kb_state_size(self._h, C.byref(n)))
+        blob = np.empty(n.value, np.uint8)
+        _lib.check(self._L.kb_get_state(self._h, _p(blob), n))
+        return blob
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _lib.check(self._L.kb_set_state(self._h, _p(blob), C.c_size_t(blob.size)))
 
     def pool(self):
         """dict(used_bytes, total_bytes, max_dictionary, tie_breaks) of the dictionary pool."""

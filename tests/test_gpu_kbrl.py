@@ -187,3 +187,32 @@ def test_guarded_fp32_evaluation_never_changes_a_decision():
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(sa, sb) and np.array_equal(la, lb) and np.array_equal(ca, cb)
     assert sa.max() >= 20
+
+
+def test_checkpoint_restores_learners_and_controller(golden):
+    """kb_get_state / kb_set_state: replaying the second half of a reference fixture from a checkpoint taken in the middle,
+    on a FRESH handle, gives the reference's decisions (dictionaries in the pool, tie counters, E-learner state)."""
+    import torch
+    g = golden("K_scn0")
+    T = len(g["state"])
+    ctl = _device_control(g, "K_scn0")
+    dev = ctl.device
+    tt = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a[None]).astype(dt)).to(dev)
+
+    def steps(c, lo, hi):
+        for t in range(lo, hi):
+            hits = c.update_control(tt(g["state"][t], np.float32), tt(g["action"][t], np.int32), tt(g["labels"][t], np.int32))
+            assert np.array_equal(hits.cpu().numpy()[0], g["hits"][t]), t
+            a, adj = c.select_action(tt(g["new_state"][t], np.float32))
+            assert np.array_equal(a.cpu().numpy()[0], g["next_action"][t]) and int(adj[0]) == g["adjusted"][t], t
+
+    steps(ctl, 0, T // 2)
+    blob = ctl.learners.get_state()
+    fresh = _device_control(g, "K_scn0")
+    fresh.learners.set_state(blob)
+    assert np.array_equal(fresh.learners.sizes()[0], ctl.learners.sizes()[0])
+    steps(fresh, T // 2, T)
+    assert np.array_equal(fresh.learners.sizes()[0][0], g["sizes"][-1])
+    assert np.allclose(fresh.control_state()["accuracies"][0], g["accuracies"], rtol=0, atol=1e-15)
+    with pytest.raises(RuntimeError):
+        fresh.learners.set_state(blob[:-8])
