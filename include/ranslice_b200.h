@@ -145,6 +145,12 @@ int rs_get_diag(rs_handle *h, double *out, int32_t n);
  * [3] aborted and replayed, [4] warp-per-unit kernel (the whole batch when it is small; at lane dilution 2 the units whose PF
  * loop was long in the previous step). */
 int rs_set_route_limits(rs_handle *h, int32_t single_start_max, int32_t single_slots, int32_t pair_start_max, int32_t pair_slots);
+/* Heavy list of the lane-per-unit route (results never depend on it): units whose PF loop ran at least
+ * contended_chunks_per_step contended chunks in the previous step are stepped by the warp-per-unit kernel, concurrently (at most
+ * max_units of them, 0 = default).  A workload knob: with uniformly random allocations it only pays at the smallest batches
+ * (where it is on by default, 600); a controller that allocates just enough PRBs (KBRL) leaves many slices saturated, and
+ * 1000 takes 24 % off the env step at 16 384 envs.  0 switches it off.  Ignored by the other routes. */
+int rs_set_heavy_threshold(rs_handle *h, int32_t contended_chunks_per_step, int32_t max_units);
 int rs_get_routes(rs_handle *h, uint64_t *out5);
 
 /* host-only self test of the exact-arithmetic identities the default kernel relies on */

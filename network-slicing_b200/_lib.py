@@ -65,11 +65,12 @@ def lib():
     L.rs_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.rs_set_route_limits.argtypes = [vp, i32, i32, i32, i32]
     L.rs_get_routes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.rs_set_heavy_threshold.argtypes = [vp, i32, i32]
     L.rs_last_error.restype = C.c_char_p
     for name in ("rs_create", "rs_destroy", "rs_reset", "rs_step", "rs_step_device", "rs_get_info", "rs_get_n_ues",
                  "rs_state_size", "rs_get_state", "rs_set_state", "rs_get_counters", "rs_n_variables",
                  "rs_set_profiling", "rs_get_profile", "rs_set_debug_check", "rs_get_diag", "rs_step_async", "rs_wait",
-                 "rs_set_route_limits", "rs_get_routes"):
+                 "rs_set_route_limits", "rs_get_routes", "rs_set_heavy_threshold"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -212,6 +212,10 @@ class BatchedRanSlice:
         """Routing limits of the default eMBB kernel (tests; results never depend on them), see rs_set_route_limits."""
         _lib.check(_lib.lib().rs_set_route_limits(self._h, single_start_max, single_slots, pair_start_max, pair_slots))
 
+    def set_heavy_threshold(self, contended_chunks_per_step, max_units=0):
+        """Workload knob of the lane-per-unit route (see rs_set_heavy_threshold); results never depend on it."""
+        _lib.check(_lib.lib().rs_set_heavy_threshold(self._h, int(contended_chunks_per_step), int(max_units)))
+
     def routes(self):
         """Units of the last step by route: dict(single, pair, general, aborted, warp)."""
         out = (C.c_uint64 * 5)()

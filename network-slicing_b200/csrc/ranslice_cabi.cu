@@ -668,6 +668,17 @@ int rs_set_route_limits(rs_handle *h, int32_t single_start_max, int32_t single_s
     return RS_OK;
 }
 
+int rs_set_heavy_threshold(rs_handle *h, int32_t contended_chunks_per_step, int32_t max_units) {
+    if (!h || contended_chunks_per_step < 0 || max_units < 0) return fail(RS_E_ARG, "bad handle / negative argument");
+    // only the lane-per-unit route has a heavy list; the other routes ignore the call
+    if (!h->embb.U || h->cfg.l1_mux || h->cfg.kernel_variant != 0 || h->embb.K > 16 || h->use_warp) return RS_OK;
+    CU(cudaSetDevice(h->cfg.device));
+    CU(cudaDeviceSynchronize());
+    h->embb.heavy_thr = contended_chunks_per_step;
+    h->embb.heavy_cap = (int)std::min<size_t>((size_t)h->embb.U, max_units ? (size_t)max_units : (size_t)32 * (size_t)h->sm_count);
+    return RS_OK;
+}
+
 int rs_get_routes(rs_handle *h, uint64_t *out5) {
     uint64_t *out4 = out5;
     if (!h || !out4) return fail(RS_E_ARG, "null argument");

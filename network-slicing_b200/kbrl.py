@@ -17,6 +17,7 @@ from . import _lib
 from .scenario_creator import scenarios, state_variables_embb, state_variables_mmtc
 
 alfa = 0.05                 # scenario_creator.py:187
+KBRL_HEAVY_THRESHOLD = 1000   # env routing under a KBRL policy (BatchedRanSlice.set_heavy_threshold; measured)
 embb_sec, embb_a = (2, 8), (4, 20)        # :190-191
 mmtc_sec, mmtc_a = (1, 4), (2, 10)        # :192-193
 
@@ -336,6 +337,8 @@ class DeviceKBRLControl:
         resources_history = torch.zeros((steps, N), **i16)
         hits_history = torch.zeros((steps, N, S), **i16)
         system.reset()
+        if hasattr(system, 'set_heavy_threshold'):      # KBRL allocates just enough PRBs: many saturated slices with long PF loops
+            system.set_heavy_threshold(KBRL_HEAVY_THRESHOLD)
         state = torch.zeros((N, system.n_variables), dtype=torch.float32, device=dev)      # reset() returns zeros
         bufs = [None, None]                                                                 # two output sets (state / new_state)
         action = self.action

@@ -28,10 +28,13 @@ ap.add_argument("--warm", type=int, default=20)
 ap.add_argument("--dict-cap", type=int, default=1024)
 ap.add_argument("--pool-mb", type=int, default=0)
 ap.add_argument("--resident", action="store_true")
+ap.add_argument("--heavy", type=int, default=1000, help="heavy-list threshold of the env under the KBRL policy (ranslice_b200.kbrl.KBRL_HEAVY_THRESHOLD); -1: library default")
 ap.add_argument("--report", default="", help="comma-separated step counts at which per-phase times and dictionary statistics are sampled")
 ap.add_argument("--window", type=int, default=20, help="steps averaged ahead of each checkpoint")
 a = ap.parse_args()
 env = create_batched_env(20260000, 0, a.envs)
+if a.heavy >= 0:
+    env.set_heavy_threshold(a.heavy)
 agent = create_kbrl_agent(np.random.default_rng(0), 0, accuracy_range=(0.97, 0.99), n_envs=a.envs, dict_cap=a.dict_cap,
                           resident=a.resident, pool_mb=a.pool_mb)
 res = {"workload": "scenario_0 + KBRL in the loop (BASELINE configs[2])", "envs": a.envs, "steps": a.steps, "warm": a.warm,
