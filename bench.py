@@ -183,8 +183,10 @@ def bind_rank_to_cpus(local, world):
     """One process per GPU: keep each rank (and the pinned buffers it first-touches) on CPUs of its own -- the cores local
     to its GPU when the cgroup allows them, else a private slice of the allowed set.  Returns a description."""
     try:
-        import torch
         allowed = sorted(os.sched_getaffinity(0))
+        if world == 1 or os.environ.get("RS_BENCH_AFFINITY", "auto") == "none":
+            return {"mode": "none", "cpus": len(allowed)}
+        import torch
         prop = torch.cuda.get_device_properties(local)
         node, local_cpus = None, []
         bus = getattr(prop, "pci_bus_id", None)
@@ -197,9 +199,6 @@ def bind_rank_to_cpus(local, world):
                     local_cpus += list(range(int(lo), int(hi or lo) + 1))
             except Exception:
                 pass
-        mode = os.environ.get("RS_BENCH_AFFINITY", "auto")
-        if mode == "none" or world == 1:
-            return {"mode": "none", "gpu_numa_node": node, "cpus": len(allowed)}
         near = [c for c in allowed if c in set(local_cpus)]
         pool = near if len(near) >= 2 else allowed
         ranks_sharing = world                                   # conservative: every rank may share this pool

@@ -26,3 +26,23 @@ def test_reference_arm_other_ranks_exit_without_work():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                        capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_python_reference_leg_times_the_unmodified_reference_when_staged():
+    """cpu_baseline.python_reference: the reference's own create_env / step(), staged under baseline/_ref by build(); None when
+    it has not been staged (the leg is reported, never required)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.python_reference_throughput(0, burn_in=2, steps=3, timeout=300)
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "node_b.py")):
+        assert r is None
+        return
+    assert r["kind"] == "reference" and r["cores"] == 1 and r["value"] > 0, r
+
+
+def test_rank_cpu_binding_is_a_no_op_for_a_single_rank():
+    sys.path.insert(0, ROOT)
+    import bench
+    before = os.sched_getaffinity(0)
+    info = bench.bind_rank_to_cpus(0, 1)
+    assert os.sched_getaffinity(0) == before and info["mode"] == "none"
