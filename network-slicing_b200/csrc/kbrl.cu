@@ -304,13 +304,36 @@ __device__ void predict_learner(const State &kb, const int capS, const int l, co
     load_rows<GROUP>(kb, l, D, rowp, gt);
     gsync<GROUP>(group);
     const bool fast_ok = stage_dictionary<GROUP>(kb, rowp, D, d, g, group, gt, base, cf, ll, fast);
-    int first = 1 << 30;                                      // key: a << 1 | (f > 0); ties (f == 0, D > 0) enter with bit 0 clear
-    for (int a = gt; a <= kb.n_prbs; a += GROUP) {
-        const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, nullptr);
-        if (f > 0.0) first = min(first, (a << 1) | 1);        // prediction == +1 (kernel.py:25)
-        else if (f == 0.0 && D > 0) first = min(first, a << 1);
+    // The scan wants the FIRST allocation predicted +1, so the candidates are taken in ascending passes of GROUP and the scan
+    // stops after the pass that found one (a dictionary of D landmarks costs D ex2 per candidate; f is mostly increasing in
+    // the allocation, so the hit usually comes early).  key: a << 1 | (f > 0); ties (f == 0, D > 0) enter with bit 0 clear.
+    int first = 1 << 30;
+    constexpr int P = GROUP >= 128 ? 4 : 1;                   // wide groups (larger dictionaries): four threads per candidate, shorter passes
+    for (int a0p = 0; a0p <= kb.n_prbs; a0p += GROUP / P) {
+        const int a = a0p + gt / P;
+        if (P > 1) {                                          // (whole warps stay in the shuffles of the split evaluation)
+            const double f = eval_f_guarded_split<P>(a <= kb.n_prbs ? D : 0, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, gt % P);
+            if (a <= kb.n_prbs && gt % P == 0) {
+                if (f > 0.0) first = (a << 1) | 1;
+                else if (f == 0.0 && D > 0) first = a << 1;
+            }
+        } else if (a <= kb.n_prbs) {
+            const double f = eval_f_guarded(D, kb.gamma, base, cf, ll, fast, fast_ok, (double)a / (double)kb.n_prbs, nullptr);
+            if (f > 0.0) first = (a << 1) | 1;                // prediction == +1 (kernel.py:25)
+            else if (f == 0.0 && D > 0) first = a << 1;
+        }
+        if (GROUP == 32) {                                    // warp: no shared memory needed
+            first = (int)__reduce_min_sync(0xffffffffu, (unsigned)first);
+            if (first != (1 << 30)) break;
+        } else {
+            if (first != (1 << 30)) atomicMin(&g.first, first);
+            gsync<GROUP>(group);
+            const bool found = g.first != (1 << 30);
+            gsync<GROUP>(group);                              // (everybody has read the flag before the next pass may change it)
+            if (found) break;
+        }
     }
-    if (first != (1 << 30)) atomicMin(&g.first, first);
+    if (GROUP == 32 && gt == 0) g.first = first;
     gsync<GROUP>(group);
     if (gt == 0) {
         int key = g.first, res = -1;
