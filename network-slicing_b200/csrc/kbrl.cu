@@ -104,7 +104,8 @@ struct State {
     unsigned long long *updates;     // [1]
     int *pend;                       // [L] hand-over between the two update launches of a step (small / large dictionaries)
     int *big_list;                   // [L] learners handed to the large-dictionary update launch of this step ...
-    int *big_ctl;                    // [2] ... their count and the work cursor of that (persistent) launch
+    int *big_ctl;                    // [3] ... {entries from the front (largest dictionaries: taken first), work cursor of that (persistent)
+                                     //      launch, entries from the back}
     int *pred_list;                  // [2][L] learners of the select_action scan with a mid-size / large dictionary ...
     int *pred_ctl;                   // [4] ... {mid count, mid cursor, large count, large cursor}
     uint32_t *tie_ctr;               // [L] draws taken from the learner's tie-break stream
@@ -447,6 +448,15 @@ __device__ __forceinline__ void kinv_extend(double *const *rowp, int D, const do
     }
 }
 
+// hands learner l to the large-dictionary launch.  That launch is persistent and its entries are very uneven (a 1000-landmark
+// dictionary that errs on most of its candidates streams gigabytes), so the largest dictionaries are listed from the front,
+// which is taken first, and the rest from the back.
+constexpr int BIG_FIRST = 640;
+__device__ __forceinline__ void list_big(const State &kb, int l, int D) {
+    if (D >= BIG_FIRST) kb.big_list[atomicAdd(&kb.big_ctl[0], 1)] = l;
+    else kb.big_list[kb.L - 1 - atomicAdd(&kb.big_ctl[2], 1)] = l;
+}
+
 // bump allocation of tile row I of learner l (thread 0 of the group); returns nullptr when the pool is exhausted
 __device__ __forceinline__ double *alloc_row(const State &kb, int l, int I) {
     const unsigned long long need = row_doubles(I);
@@ -471,7 +481,7 @@ __device__ void update_learner(const State &kb, const int capS, const bool hand_
                                unsigned char *raw, GroupVars &g, const int group, const int gt) {
     int D = kb.D[l];
     if (hand_over && D >= capS) {                             // large dictionary: the second launch takes it from the start
-        if (gt == 0) { kb.pend[l] = PEND_FRESH; kb.big_list[atomicAdd(&kb.big_ctl[0], 1)] = l; }
+        if (gt == 0) { kb.pend[l] = PEND_FRESH; list_big(kb, l, D); }
         return;
     }
     double **rowp, *base, *cf, *ll, *kf, *ds;
@@ -690,7 +700,7 @@ __device__ void update_learner(const State &kb, const int capS, const bool hand_
     if (gt == 0) {
         kb.D[l] = D;
         kb.tie_ctr[l] = tie_n;
-        if (handed_over >= 0) { kb.pend[l] = handed_over; kb.big_list[atomicAdd(&kb.big_ctl[0], 1)] = l; }
+        if (handed_over >= 0) { kb.pend[l] = handed_over; list_big(kb, l, D); }
         if (n_updates) atomicAdd(kb.updates, (unsigned long long)n_updates);
         if (D > *kb.max_d) atomicMax(kb.max_d, D);
     }
@@ -712,20 +722,20 @@ __global__ void __launch_bounds__(Cfg<GROUP>::THREADS, GROUP == 256 ? 4 : 1) upd
 }
 // the learners listed by update_kernel, one CTA at a time (persistent: the list is short and its entries are uneven)
 template <int GROUP>
-__global__ void __launch_bounds__(GROUP, 1) update_list_kernel(const State kb, const int capS, const float *__restrict__ state,
+__global__ void __launch_bounds__(GROUP, 1024 / GROUP) update_list_kernel(const State kb, const int capS, const float *__restrict__ state,
                                                                const int32_t *__restrict__ action, const int32_t *__restrict__ labels,
                                                                int32_t *y_pred, const Control ctl, int32_t *hits) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ GroupVars g;
     __shared__ int s_idx;
-    const int count = kb.big_ctl[0];
+    const int front = kb.big_ctl[0], count = front + kb.big_ctl[2];
     for (;;) {
         if (threadIdx.x == 0) s_idx = atomicAdd(&kb.big_ctl[1], 1);
         __syncthreads();
         const int idx = s_idx;
         __syncthreads();
         if (idx >= count) return;
-        const int l = kb.big_list[idx];
+        const int l = kb.big_list[idx < front ? idx : kb.L - 1 - (idx - front)];
         update_learner<GROUP>(kb, capS, false, l, kb.pend[l], state, action, labels, y_pred, ctl, hits, raw, g, 0, threadIdx.x);
         __syncthreads();
     }
@@ -823,7 +833,7 @@ static int kb_create_impl(kb_handle *h, const kb_config *cfg, const int32_t *dim
     KCU(cudaMalloc(&st.cursor, sizeof(unsigned long long)));
     KCU(cudaMalloc(&st.max_d, sizeof(int)));
     KCU(cudaMalloc(&st.big_list, L * sizeof(int)));
-    KCU(cudaMalloc(&st.big_ctl, 2 * sizeof(int)));
+    KCU(cudaMalloc(&st.big_ctl, 3 * sizeof(int)));
     KCU(cudaMalloc(&st.pred_list, 2 * L * sizeof(int)));
     KCU(cudaMalloc(&st.pred_ctl, 4 * sizeof(int)));
     KCU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -924,13 +934,13 @@ int kb_destroy(kb_handle *h) {
 static int launch_update(kb_handle *h, const float *d_state, const int32_t *d_action, const int32_t *d_labels, int32_t *d_y_pred,
                          const kb::Control &ctl, int32_t *d_hits, cudaStream_t st) {
     KCU(cudaMemsetAsync(h->st.updates, 0, sizeof(unsigned long long), st));
-    KCU(cudaMemsetAsync(h->st.big_ctl, 0, 2 * sizeof(int), st));
+    KCU(cudaMemsetAsync(h->st.big_ctl, 0, 3 * sizeof(int), st));
     const int blocks = (h->st.L + UG - 1) / UG, threads = kb::Cfg<KB_GROUP_UPDATE>::THREADS;
     const int two = h->st.cap > h->cap_small;                  // (with dict_cap <= SMALL_CAP the first launch does everything)
     kb::update_kernel<KB_GROUP_UPDATE><<<blocks, threads, h->smem_update_small, st>>>(h->st, h->cap_small, two, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
     h->launches += 1;
     if (two) {
-        kb::update_list_kernel<KB_GROUP_UPDATE_BIG><<<h->sm_count, KB_GROUP_UPDATE_BIG, h->smem_update_big, st>>>(h->st, h->st.cap, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
+        kb::update_list_kernel<KB_GROUP_UPDATE_BIG><<<h->sm_count * (1024 / KB_GROUP_UPDATE_BIG), KB_GROUP_UPDATE_BIG, h->smem_update_big, st>>>(h->st, h->st.cap, d_state, d_action, d_labels, d_y_pred, ctl, d_hits);
         h->launches += 1;
     }
     KCU(cudaGetLastError());
