@@ -310,6 +310,9 @@ static void new_ue(ue_t *u, int type) {                                     /* s
     memset(u, 0, sizeof(*u)); u->type = type;
 }
 
+#ifdef ORC_PF_STATS
+unsigned long long orc_pf_stat[8];
+#endif
 static void pf_allocate(orc_env *e, embb_t *sl) {                           /* schedulers.py:21-76 */
     int n = sl->n_ues, n_prb = sl->n_prbs;
     int rbs[MAX_UE], mcs[MAX_UE]; int64_t queue[MAX_UE], rate[MAX_UE], bits[MAX_UE]; double th[MAX_UE];
@@ -322,6 +325,9 @@ static void pf_allocate(orc_env *e, embb_t *sl) {                           /* s
         int es = u->e_snr < -128 ? -128 : (u->e_snr > 127 ? 127 : u->e_snr);   /* LUT saturates far inside this range */
         mcs[i] = e->lut_mcs[es + 128]; rate[i] = e->lut_rate[es + 128];
     }
+#ifdef ORC_PF_STATS
+    int prev = -1, prev2 = -1, prev3 = -1;                                  /* winner / runner-up / third at the start of the current run */
+#endif
     for (int r = 0; r < n_prb; r += 2) {
         int prbs = n_prb - r < 2 ? n_prb - r : 2;
         int idx = 0; double best = -INFINITY;
@@ -329,6 +335,32 @@ static void pf_allocate(orc_env *e, embb_t *sl) {                           /* s
             double m = (double)(rate[i] * (queue[i] > 0)) / th[i];
             if (m > best) { best = m; idx = i; }
         }
+#ifdef ORC_PF_STATS
+        {   /* statistics for the design of the warp kernel's PF loop: how often could the next winner
+             * and runner-up be told from the top three of the previous warp-wide argmax alone? */
+            extern unsigned long long orc_pf_stat[8];
+            int nb = 0;
+            for (int i = 0; i < n; ++i) nb += queue[i] > 0;
+            orc_pf_stat[0] += 1;                                            /* chunks */
+            if (nb >= 2) orc_pf_stat[1] += 1;                               /* contended chunks */
+            if (nb >= 2 && idx != prev) {
+                orc_pf_stat[2] += 1;                                        /* runs (warp-wide iterations of the current kernel) */
+                if (prev >= 0) {
+                    orc_pf_stat[3] += 1;                                    /* winner changes */
+                    double mp = (double)(rate[prev] * (queue[prev] > 0)) / th[prev], v4 = 0.0;
+                    for (int i = 0; i < n; ++i)
+                        if (i != prev && i != prev2 && i != prev3) { double m = (double)(rate[i] * (queue[i] > 0)) / th[i]; if (m > v4) v4 = m; }
+                    if (idx == prev2) orc_pf_stat[4] += 1;                  /* ... to the old runner-up */
+                    if (idx == prev2 && mp >= v4) orc_pf_stat[5] += 1;      /* ... and the top-3 set is unchanged */
+                }
+                /* top three of this argmax */
+                int i2 = -1, i3 = -1; double b2 = -1.0, b3 = -1.0;
+                for (int i = 0; i < n; ++i) if (i != idx) { double m = (double)(rate[i] * (queue[i] > 0)) / th[i]; if (m > b2) { b2 = m; i2 = i; } }
+                for (int i = 0; i < n; ++i) if (i != idx && i != i2) { double m = (double)(rate[i] * (queue[i] > 0)) / th[i]; if (m > b3) { b3 = m; i3 = i; } }
+                prev = idx; prev2 = i2; prev3 = i3;
+            }
+        }
+#endif
         rbs[idx] += prbs;
         int64_t tx = prbs * rate[idx] < queue[idx] ? prbs * rate[idx] : queue[idx];
         queue[idx] -= tx; bits[idx] += tx;
