@@ -25,7 +25,14 @@
 
 namespace rs {
 
-constexpr int WP_WARPS = 8;        // units per 256-thread block
+// Units (warps) per block.  ONE: a block's registers and shared memory go back to the SM the moment its unit is done, instead
+// of waiting for the slowest of 8 units.  Measured (profiles/r02f_warp_block_geometry.txt), 8 / 4 / 2 / 1 warps per block at 16
+// warps per SM: 2048 envs 1.168 / 1.124 / 1.102 / 1.051 ms/step, 4096 envs 2.043 / 1.926 / 1.862 / 1.751, multiplexed L1 at
+// 16 384 envs 9.50 / 8.36 / 7.88 / 7.20.
+#ifndef RS_WP_WARPS
+#define RS_WP_WARPS 1
+#endif
+constexpr int WP_WARPS = RS_WP_WARPS;
 constexpr int WP_K = 16;           // UE slots per unit (== the UE cap of the other variants)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -138,11 +145,18 @@ __device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(row), "r"(col), "r"(smem_u32(bar)) : "memory");
 }
 
-#ifndef RS_WARP_MIN_BLOCKS
-#define RS_WARP_MIN_BLOCKS 2
+// Resident warps per SM the register budget is sized for.  Whole batches (many waves of units: throughput) run the 96-register
+// instantiation -- 18 warps per SM with the staging buffers: 2048 envs 1.051 -> 0.998 ms/step, 4096 envs 1.751 -> 1.603,
+// multiplexed L1 7.20 -> 6.67 (80 registers: 1.047 / 1.653 / 6.57) --; the heavy list of the default route (one wave of the
+// longest units: latency) keeps 128 registers (env step under the KBRL policy 3.13 vs 3.23 ms, 4096 envs 1.56 vs 1.63).
+#ifndef RS_WARP_BATCH_WARPS
+#define RS_WARP_BATCH_WARPS 20
 #endif
-template <bool MUX>
-__global__ void __launch_bounds__(WP_WARPS * 32, RS_WARP_MIN_BLOCKS) embb_step_warp(const __grid_constant__ StepParams p,
+#ifndef RS_WARP_HEAVY_WARPS
+#define RS_WARP_HEAVY_WARPS 16
+#endif
+template <bool MUX, int MIN_WARPS>
+__global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step_warp(const __grid_constant__ StepParams p,
                                                                const __grid_constant__ EmbbState st,
                                                                const __grid_constant__ Tables tb, const int heavy_list) {
     __shared__ __align__(128) LutBlock s_lut;                    // MCS / rate LUT, snr_ref, modulation, MI constants, 1/n: ONE bulk copy
@@ -570,7 +584,11 @@ void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ue
 static size_t warp_dyn_smem() {
     static bool configured = false;
     constexpr size_t bytes = (size_t)WP_WARPS * WP_K * TMA_SLOT;
-    if (!configured) { cudaFuncSetAttribute(embb_step_warp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured = true; }
+    if (!configured) {
+        cudaFuncSetAttribute(embb_step_warp<false, RS_WARP_BATCH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaFuncSetAttribute(embb_step_warp<false, RS_WARP_HEAVY_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        configured = true;
+    }
     return bytes;
 }
 
@@ -578,18 +596,18 @@ static size_t warp_dyn_smem() {
 int launch_embb_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream, cudaEvent_t *prof) {
     launch_embb_sort(p, st, 1 << 30, 1 << 30, stream);
     if (prof) cudaEventRecord(prof[0], stream);
-    embb_step_warp<false><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 0);
+    embb_step_warp<false, RS_WARP_BATCH_WARPS><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 0);
     if (prof) cudaEventRecord(prof[1], stream);
     return 5;   // kernels launched
 }
 // the heavy list of the default route (at most heavy_cap units), concurrent with the shared-memory kernel on another stream
 void launch_embb_warp_heavy(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    embb_step_warp<false><<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 1);
+    embb_step_warp<false, RS_WARP_HEAVY_WARPS><<<(st.heavy_cap + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, warp_dyn_smem(), stream>>>(p, st, tb, 1);
 }
 
 // multiplexed L1 (L1_level=False): one warp per env
 void launch_embb_mux_warp(const StepParams &p, const EmbbState &st, const Tables &tb, cudaStream_t stream) {
-    embb_step_warp<true><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 0);
+    embb_step_warp<true, RS_WARP_BATCH_WARPS><<<(st.U + WP_WARPS - 1) / WP_WARPS, WP_WARPS * 32, 0, stream>>>(p, st, tb, 0);
 }
 
 }  // namespace rs

@@ -39,9 +39,11 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 constexpr int PROF_EVENTS = 7;
 #ifndef RS_HEAVY_PF_DEFAULT
-#define RS_HEAVY_PF_DEFAULT 600   // contended PF chunks per step above which a unit of a SMALL batch goes to the warp-per-unit kernel; measured at
-                                  // 4096 envs: 2.13 ms/step without, 1.97 / 1.94 / 1.97 at 300 / 600 / 1000; at 16 384 and 65 536 envs any threshold below
-                                  // 2500 costs 5-15 % (a warp executes ~3x the instructions of a lane), so it is only enabled at lane dilution 2
+#define RS_HEAVY_PF_DEFAULT 1000  // predicted contended PF chunks per step (embb_fast.cu is_heavy) above which a unit of a SMALL batch goes to the
+#define RS_HEAVY_PF_DIL1 1500     // warp-per-unit kernel.  Measured (profiles/r02f_heavy_prediction.txt): 4096 envs (lane dilution 2) 2.13 ms/step
+                                  // without, 1.70 / 1.60 / 1.61 at 800 / 1000 / 1200; 16 384 envs (dilution 1) 2.51 without, 2.33 / 2.45 / 2.50 at
+                                  // 1500 / 2500 / 3500; 65 536 envs 4.02 without, 4.28 / 4.11 at 3000 / 4000 (a warp executes ~3x the instructions of
+                                  // a lane), so it is only enabled for diluted batches
 #endif
 #ifndef RS_WARP_AUTO_UNITS_DEFAULT
 #define RS_WARP_AUTO_UNITS_DEFAULT 16384   // batches of up to this many units run the warp-per-unit kernel: 2048 envs x 5 slices 1.18 vs 1.89 ms/step,
@@ -324,9 +326,8 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
     {   // per-step scheduling scratch (outside the checkpoint arena)
         Carver sc;
         const size_t U = (size_t)h->embb.U;
-        // lane dilution of the shared-memory kernel (ranslice_state.cuh): while the diluted list (with ~10 % of pair
-        // entries) stays within 2.5x the lanes the GPU keeps resident (4 blocks of 128 threads per SM).  Measured on B200:
-        // 4096 envs 3.20 -> 2.78 ms/step at dil 2, 16384 envs 3.69 -> 3.43 at dil 1 (and 4.15 at dil 2), no gain beyond.
+        // lane dilution of the shared-memory kernel (ranslice_state.cuh): every 2nd lane while the diluted list (with ~10 % of pair
+        // entries) stays within 2.5x the lanes the GPU keeps resident (4 blocks of 128 threads per SM), every 4th within 1.75x.
         // warp-per-unit kernel (embb_warp.cu): kernel_variant 3, or automatically while the batch leaves the GPU underfilled
         // (measured crossover; RS_WARP_AUTO_UNITS overrides)
         size_t warp_auto = RS_WARP_AUTO_UNITS_DEFAULT;
@@ -335,8 +336,11 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         int dil = 0;
         const bool smem_variant = h->cfg.kernel_variant == 0 || h->cfg.kernel_variant == 4;
         if (smem_variant && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux && !h->use_warp) {
-            const double lanes = 2.5 * 4.0 * 128.0 * (double)h->sm_count;
-            while (dil < 2 && 1.1 * (double)U * (double)(2 << dil) <= lanes) ++dil;
+            // (profiles/r02f_dilution_sweep.jsonl, ms/step at dilution 0 / 1 / 2: 4096 envs 2.38 / 1.88 / 1.57, 6144 envs 2.49 / 1.96 / 1.96,
+            //  8192 envs 2.64 / 2.00 / 2.47, 16 384 envs 2.60 / 2.29 / 4.21, 24 576 envs 2.80 / 3.09 / 5.94)
+            const double resident = 4.0 * 128.0 * (double)h->sm_count, list = 1.1 * (double)U;
+            if (2.0 * list <= 2.5 * resident) dil = 1;
+            if (4.0 * list <= 1.75 * resident) dil = 2;
             if (const char *e = std::getenv("RS_DILUTION")) dil = std::max(0, std::min(2, std::atoi(e)));
         }
         h->embb.dil = dil;
@@ -345,7 +349,7 @@ static int create_impl(rs_handle *h, const rs_config *cfg, const rs_tables *tabl
         // heavy list of the default route (ranslice_state.cuh): threshold on last step's contended PF chunks; RS_HEAVY_PF overrides (0 = off)
         h->embb.heavy_thr = 0;
         if (h->cfg.kernel_variant == 0 && !h->use_warp && h->embb.K <= 16 && U > 0 && !h->cfg.l1_mux) {   // (variant 4 is the pure shared-memory route)
-            h->embb.heavy_thr = dil == 2 ? RS_HEAVY_PF_DEFAULT : 0;      // only where the step is bound by its slowest lanes (smallest batches)
+            h->embb.heavy_thr = dil == 2 ? RS_HEAVY_PF_DEFAULT : dil == 1 ? RS_HEAVY_PF_DIL1 : 0;   // only where the step is bound by its slowest lanes (small batches)
             if (const char *e = std::getenv("RS_HEAVY_PF")) h->embb.heavy_thr = std::max(0, std::atoi(e));
         }
         h->embb.heavy_cap = (int)std::min<size_t>(U, (size_t)8 * 4 * (size_t)h->sm_count);   // at most four 8-warp blocks per SM

@@ -2,7 +2,7 @@
 # A/B of warp-kernel builds: parity of the default build, then variant 3 at small batches, the default route at 4096 envs,
 # the multiplexed L1 and the env step under the KBRL policy, per build tag (base = the default library)
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 900 2>&1 | tail -5 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
+[ -n "$SKIP_TESTS" ] || timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 900 2>&1 | tail -5 > gpurun_out/pytest_gpu.txt; cat gpurun_out/pytest_gpu.txt
 for tag in "$@"; do
   if [ "$tag" = base ]; then unset RS_B200_LIB; else export RS_B200_LIB=$PWD/network-slicing_b200/libranslice_b200_$tag.so; fi
   for envs in 2048 4096; do
