@@ -133,7 +133,8 @@ int rs_get_profile(rs_handle *h, double *ms6, uint64_t *steps);
  * expression next to every fast-path decision.  rs_get_diag: out[0] max |p64 - p32| / eps over
  * reception decisions, out[1] max |mean64 - mean_fast| / guard over SNR estimates (guard = 2.5 x the fixed-point representation error), out[2] decisions
  * that would have differed (must be 0), out[3] / out[4] fp64 re-evaluations taken in the last step
- * (SNR rounding guard / reception guard). */
+ * (SNR rounding guard / reception guard); with n >= 6, out[5] = PRB chunks of the last step that the multiplexed-L1 kernel
+ * handed out several at a time (its batched ProportionalFair step; the others went through the chunk-by-chunk argmax). */
 int rs_set_debug_check(rs_handle *h, int32_t enable);
 int rs_get_diag(rs_handle *h, double *out, int32_t n);
 

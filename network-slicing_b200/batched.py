@@ -227,10 +227,10 @@ class BatchedRanSlice:
 
     def diag(self):
         """Guard-band diagnostics of the default kernel (see rs_get_diag in include/ranslice_b200.h)."""
-        out = (C.c_double * 5)()
-        _lib.check(_lib.lib().rs_get_diag(self._h, out, 5))
+        out = (C.c_double * 6)()
+        _lib.check(_lib.lib().rs_get_diag(self._h, out, 6))
         return {"max_p_err_over_eps": out[0], "max_mean_err_over_guard": out[1], "decision_mismatches": int(out[2]),
-                "slow_snr_last_step": int(out[3]), "slow_rx_last_step": int(out[4])}
+                "slow_snr_last_step": int(out[3]), "slow_rx_last_step": int(out[4]), "pf_batched_chunks_last_step": int(out[5])}
 
     def get_state(self):
         n = C.c_size_t()

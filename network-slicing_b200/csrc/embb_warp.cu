@@ -155,6 +155,24 @@ __device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int
 #ifndef RS_WARP_HEAVY_WARPS
 #define RS_WARP_HEAVY_WARPS 16
 #endif
+// batched PF step (see the RB loop below): events speculated per UE and step, bisection rounds of the budget cut, and the
+// loop lengths it is tried for (full chunks left, backlogged UEs)
+#ifndef RS_PF_BATCH
+#define RS_PF_BATCH 1             // bit 0: in the multiplexed L1, bit 1: in the per-slice kernel.  Measured (profiles/r02f_pf_batch.txt): the
+#endif                            // multiplexed L1 (12 UEs on ~130 PRBs: ~65 chunks per TTI) 2.45 -> 3.54 M env-steps/s at 16 384 envs; the
+                                  // per-slice kernel (2.8 UEs per slice) loses 9 % to the 2 KB of shared memory (16 instead of 18 warps per
+                                  // SM) and gains nothing on its heavy units, so it stays off there
+#ifndef RS_PF_SPEC
+#define RS_PF_SPEC 8              // (6: 3.23 M, 8: 3.54 M, 12: 2.88 M)
+#endif
+#ifndef RS_PF_BATCH_NMIN
+#define RS_PF_BATCH_NMIN 6        // (full chunks left, backlogged UEs) >= (12, 3): 3.29 M, (6, 2): 3.54 M, (4, 2): 3.50 M, (2, 2): 3.44 M,
+#endif                            // (24, 4): 3.08 M, (16, 5): 2.94 M
+#ifndef RS_PF_BATCH_BMIN
+#define RS_PF_BATCH_BMIN 2
+#endif
+constexpr int PF_SPEC = RS_PF_SPEC, PF_BISECT = 16, PF_BATCH_NMIN = RS_PF_BATCH_NMIN, PF_BATCH_BMIN = RS_PF_BATCH_BMIN;
+
 template <bool MUX, int MIN_WARPS>
 __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step_warp(const __grid_constant__ StepParams p,
                                                                const __grid_constant__ EmbbState st,
@@ -163,6 +181,8 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
     constexpr int TK = MUX ? 32 : WP_K;                          // UE slots per unit (a multiplexed L1 holds the UEs of all its RAN slices)
     __shared__ __align__(16) UeRec s_tbl[WP_WARPS][TK];          // RAN-event scratch (8 / 16 KB)
     __shared__ WarpCtx s_ctx[WP_WARPS];
+    constexpr bool BATCH = MUX ? (RS_PF_BATCH & 1) != 0 : (RS_PF_BATCH & 2) != 0;
+    __shared__ double s_spec[WP_WARPS][BATCH ? PF_SPEC : 1][BATCH ? 32 : 1];   // speculated working throughputs of the batched PF step (2 KB per warp)
     __shared__ MuxPark s_mux[MUX ? WP_WARPS : 1][MAX_SLICES];
     __shared__ int s_racc[MUX ? WP_WARPS : 1][MAX_SLICES][2][5]; // per (RAN slice, UE type) sums of one TTI: traffic, bits, PRBs, e_snr, UEs
     __shared__ unsigned long long s_rq[MUX ? WP_WARPS : 1][MAX_SLICES][2];   // ... and queues
@@ -237,6 +257,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
     int a_traffic_all = 0, a_traffic_v = 0, a_th_all = 0, a_th_v = 0, a_prb_all = 0, a_prb_v = 0;
     double a_queue_c = 0.0, a_queue_v = 0.0, a_snr_c = 0.0, a_snr_v = 0.0;
     unsigned trace_elems = 0, slow_snr = 0, slow_rx = 0, pf_iters = 0;      // per lane, reduced at the end
+    unsigned pf_batched = 0;                                     // chunks handed out by batched PF steps (uniform; rs_get_diag)
     const float Af = (float)tb.A, Bf = (float)tb.B;
     const double inv_n = n_prbs > 0 ? tb.pre_inv / (double)n_prbs : 0.0;
 
@@ -355,6 +376,84 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
             // ---- ProportionalFair.allocate RB loop (schedulers.py:47-63), phase 1: contended chunks
             while (n_backlog >= 2 && rr < n_prbs) {
                 if (RS_EXP & 8) break;
+                // ---- several chunks per warp-wide step (long loops only).  Event (k, j) = "UE k takes its j-th chunk from here"; its key is
+                // the minimum of k's metric before each of its chunks 1..j.  The loop below hands the chunks out in the order of decreasing
+                // keys (a UE's metric only changes when it is served), and a UE's state depends on HOW MANY chunks it took, not on the
+                // interleaving -- so every event whose key is clearly above (a) every key any UE can still produce beyond the PF_SPEC
+                // events it speculates here and (b) every event left out, is applied at once.  "Clearly": fp32 keys carry 2.4e-7, the cut
+                // keeps a band of 1e-6 empty on both sides; ties, near-ties and the last (possibly 1-PRB) chunk go through the exact
+                // step below.  tools/pf_stats_oracle.py: 16 chunks per step instead of 1.6 in the multiplexed L1, 6.8 instead of 2.4 else.
+                if (BATCH && ((n_prbs - rr) >> 1) >= PF_BATCH_NMIN && n_backlog >= PF_BATCH_BMIN) {
+                    const int nrem = (n_prbs - rr) >> 1;                 // full 2-PRB chunks left
+                    const long long cap2 = 2ll * rate;
+                    float key[PF_SPEC];
+                    double t = thpf;
+                    int bb = bits_l;
+                    long long q = live ? r.queue - bits_l : 0ll;
+                    float kmin = metf;
+#pragma unroll
+                    for (int j = 0; j < PF_SPEC; ++j) {
+                        key[j] = q > 0 ? kmin : -1.0f;
+                        if (q > 0) {
+                            const int tx = (int)min(cap2, q);
+                            q -= tx; bb += tx;
+                            t = __dadd_rn(__dmul_rn(PF_A, t), b_bits_over_slot(bb));
+                            kmin = fminf(kmin, q > 0 ? (float)rate * rcp_approx((float)t) : 0.0f);
+                        }
+                        s_spec[w][j][lane] = t;                          // working throughput after j + 1 chunks
+                    }
+                    // (a) the largest key still to come from beyond a horizon
+                    const float T = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(q > 0 ? kmin : 0.0f)));
+                    constexpr float UP = 1.0f + 1e-6f, DN = 1.0f - 1e-6f;
+                    auto count = [&](float C) {                          // events clearly above C | events within the band around C
+                        const float hi = C * UP, lo = C * DN;
+                        int in = 0, near = 0;
+#pragma unroll
+                        for (int j = 0; j < PF_SPEC; ++j) { in += key[j] > hi; near += key[j] > lo; }
+                        return in | ((near - in) << 16);
+                    };
+                    float C = T * UP;
+                    int mine = count(C);
+                    int tot = __reduce_add_sync(FULL, mine);
+                    if ((tot & 0xFFFF) > nrem) {                         // more than the PRBs allow: raise the cut (bisection on the bit patterns)
+                        // (the search starts at most a factor 256 below the best key: 16 rounds resolve 1e-4 of it; a cut that ends up
+                        //  too high only leaves more chunks to the next step)
+                        const unsigned top_b = __reduce_max_sync(FULL, __float_as_uint(fmaxf(key[0], 0.0f)));
+                        unsigned lo_b = max(__float_as_uint(C), top_b > (8u << 23) ? top_b - (8u << 23) : 0u), hi_b = top_b + 1u;
+#pragma unroll 1
+                        for (int it = 0; it < PF_BISECT && hi_b - lo_b > 1u; ++it) {
+                            const unsigned mid = lo_b + ((hi_b - lo_b) >> 1);
+                            const int cnt = __reduce_add_sync(FULL, count(__uint_as_float(mid)) & 0xFFFF);
+                            if (cnt > nrem) lo_b = mid; else hi_b = mid;
+                        }
+                        C = __uint_as_float(hi_b);
+                        mine = count(C);
+                        tot = __reduce_add_sync(FULL, mine);
+                    }
+                    if (tot >> 16) {                                     // events inside the band: move the cut above them, once
+                        C *= 1.0f + 3e-6f;
+                        mine = count(C);
+                        tot = __reduce_add_sync(FULL, mine);
+                    }
+                    if ((tot >> 16) == 0 && (tot & 0xFFFF) > 0) {
+                        const int cnt = mine & 0xFFFF;                   // chunks of this lane's UE
+                        int drained = 0;
+                        if (cnt > 0) {
+                            const long long left_q = r.queue - bits_l;
+                            const long long tx = min((long long)cnt * cap2, left_q);
+                            bits_l += (int)tx;
+                            rbs_l += 2 * cnt;
+                            thpf = s_spec[w][cnt - 1][lane];
+                            drained = left_q - tx <= 0;
+                            metf = drained ? 0.0f : (float)rate * rcp_approx((float)thpf);
+                        }
+                        n_backlog -= __popc(__ballot_sync(FULL, drained));
+                        rr += 2 * (tot & 0xFFFF);
+                        pf_iters += (unsigned)(tot & 0xFFFF);
+                        pf_batched += (unsigned)(tot & 0xFFFF);
+                        continue;
+                    }
+                }
                 ++pf_iters;
                 const int c = min(n_prbs - rr, 2);
                 // argmax of rate * (queue > 0) / th, first maximum: metrics are >= 0, so their bit patterns order like the values
@@ -562,6 +661,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
         if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
         if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
         if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
+        if (pf_batched) atomicAdd(p.slow_paths + 2, (unsigned long long)pf_batched);
         return;
     }
     if (lane != 0) return;
@@ -577,6 +677,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
     if (trace_elems) atomicAdd(p.trace_elems, (unsigned long long)trace_elems);
     if (slow_snr) atomicAdd(p.slow_paths + 0, (unsigned long long)slow_snr);
     if (slow_rx) atomicAdd(p.slow_paths + 1, (unsigned long long)slow_rx);
+    if (pf_batched) atomicAdd(p.slow_paths + 2, (unsigned long long)pf_batched);
 }
 
 void launch_embb_sort(const StepParams &p, const EmbbState &st, int max_front_ues, int heavy_min_ues, cudaStream_t stream);

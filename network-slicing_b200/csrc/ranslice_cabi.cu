@@ -475,7 +475,7 @@ int rs_step_device(rs_handle *h, const int32_t *d_action, float *d_obs, float *d
     p.labels = d_labels ? d_labels : h->d_labels;
     p.violations = d_violations ? d_violations : h->d_violations;
     p.flags = d_flags ? d_flags : h->d_flags;
-    CU(cudaMemsetAsync(h->d_trace_elems, 0, 3 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(h->d_trace_elems, 0, 4 * sizeof(unsigned long long), st));
     // profiling events of one step: [0] start, [1] / [2] around the dominant eMBB kernel, [3] end of the eMBB kernels,
     // [4] end of the mMTC scan, [5] end of the mMTC kernels, [6] end of the step
     cudaEvent_t ev[PROF_EVENTS] = {};
@@ -719,6 +719,7 @@ int rs_get_diag(rs_handle *h, double *out, int32_t n) {
     unsigned mism;
     std::memcpy(&mism, &dbg[2], sizeof mism);
     out[0] = dbg[0]; out[1] = dbg[1]; out[2] = (double)mism; out[3] = (double)ctr[1]; out[4] = (double)ctr[2];
+    if (n >= 6) out[5] = (double)ctr[3];
     return RS_OK;
 }
 

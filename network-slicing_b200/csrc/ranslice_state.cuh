@@ -164,7 +164,7 @@ struct StepParams {
     uint32_t *flags;               // [N]
     uint32_t *flags_acc;           // [N] scratch OR-ed by the slice kernels
     unsigned long long *trace_elems; // [1] algorithmic trace elements touched (B_trace counter)
-    unsigned long long *slow_paths;  // [2] fp64 re-evaluations taken: [0] e_snr rounding guard, [1] reception guard
+    unsigned long long *slow_paths;  // [3] fp64 re-evaluations taken: [0] e_snr rounding guard, [1] reception guard; [2] PRB chunks handed out by batched PF steps
     int debug_check;                 // tests only: evaluate fp64 next to every fast decision and record error/guard ratios
 };
 

@@ -311,7 +311,7 @@ static void new_ue(ue_t *u, int type) {                                     /* s
 }
 
 #ifdef ORC_PF_STATS
-unsigned long long orc_pf_stat[8];
+unsigned long long orc_pf_stat[12];
 #endif
 static void pf_allocate(orc_env *e, embb_t *sl) {                           /* schedulers.py:21-76 */
     int n = sl->n_ues, n_prb = sl->n_prbs;
@@ -327,6 +327,82 @@ static void pf_allocate(orc_env *e, embb_t *sl) {                           /* s
     }
 #ifdef ORC_PF_STATS
     int prev = -1, prev2 = -1, prev3 = -1;                                  /* winner / runner-up / third at the start of the current run */
+    {   /* What-if: chunks handed out in BATCHES.  Every backlogged UE speculates its next R chunks on its own; event (k, j) = "UE k gets
+         * its j-th chunk" has key min(head metrics before it); the greedy order of the RB loop is the order of decreasing keys, so every
+         * event whose key is above the largest key any UE could still produce beyond its horizon can be applied at once (counts only:
+         * a UE's state depends on how many chunks it got, not on the interleaving).  No such event: one run of the current loop.
+         * stat[6] = warp-wide steps of that scheme, stat[7] = steps that needed a selection of the top-N events (budget cut). */
+        extern unsigned long long orc_pf_stat[12];
+        enum { R = ORC_PF_SPEC };
+        double th2[MAX_UE]; int64_t q2[MAX_UE], b2[MAX_UE];
+        for (int i = 0; i < n; ++i) { th2[i] = th[i]; q2[i] = queue[i]; b2[i] = 0; }
+        int nrem = n_prb / 2;
+        for (;;) {
+            int nb = 0;
+            for (int i = 0; i < n; ++i) nb += q2[i] > 0;
+            if (nrem <= 0 || nb < 2) break;
+            double key[MAX_UE][R], T = 0.0; int nev[MAX_UE];
+#ifndef ORC_PF_NMIN
+#define ORC_PF_NMIN 0
+#define ORC_PF_BMIN 2
+#endif
+            const int use_batch = nrem >= ORC_PF_NMIN && nb >= ORC_PF_BMIN;
+            for (int i = 0; i < n; ++i) {
+                nev[i] = 0;
+                if (q2[i] <= 0) continue;
+                double t = th2[i], head = (double)rate[i] / t, kmin = head; int64_t q = q2[i], bb = b2[i];
+                int j = 0;
+#ifdef ORC_PF_NOCUT
+                const int depth = nrem / nb < R ? nrem / nb : R;            /* nb * depth <= nrem: a batch never exceeds the budget */
+#else
+                const int depth = R;
+#endif
+                for (; j < depth; ++j) {
+                    key[i][j] = kmin;
+                    int64_t tx = 2 * rate[i] < q ? 2 * rate[i] : q;
+                    q -= tx; bb += tx; t = a * t + b * (double)bb / slot;
+                    head = q > 0 ? (double)rate[i] / t : 0.0;
+                    if (head < kmin) kmin = head;
+                    if (q <= 0) { ++j; break; }
+                }
+                nev[i] = j;
+                if (q > 0 && kmin > T) T = kmin;                            /* more events beyond the horizon: all with key <= kmin */
+            }
+            int count = 0;
+            for (int i = 0; i < n; ++i) for (int j = 0; j < nev[i]; ++j) count += key[i][j] > T;
+            if (!use_batch) count = 0;
+            orc_pf_stat[6] += 1;
+            if (use_batch) orc_pf_stat[8] += 1;                             /* batch attempts */
+            if (use_batch && count == 0) orc_pf_stat[9] += 1;               /* ... that found nothing to apply */
+            if (count > nrem) {                                             /* budget cut: the nrem largest keys */
+                orc_pf_stat[7] += 1;
+                double all[MAX_UE * R]; int m = 0;
+                for (int i = 0; i < n; ++i) for (int j = 0; j < nev[i]; ++j) if (key[i][j] > T) all[m++] = key[i][j];
+                for (int x = 0; x < m; ++x) for (int y = x + 1; y < m; ++y) if (all[y] > all[x]) { double z = all[x]; all[x] = all[y]; all[y] = z; }
+                T = all[nrem];                                              /* events with key > the (nrem+1)-th largest (ties: fewer) */
+                count = 0;
+                for (int i = 0; i < n; ++i) for (int j = 0; j < nev[i]; ++j) count += key[i][j] > T;
+            }
+            if (count == 0) {                                               /* one run of the current loop */
+                int idx = 0; double best = -1.0, second = -1.0;
+                for (int i = 0; i < n; ++i) { double m = q2[i] > 0 ? (double)rate[i] / th2[i] : 0.0; if (m > best) { second = best; best = m; idx = i; } else if (m > second) second = m; }
+                do {
+                    int64_t tx = 2 * rate[idx] < q2[idx] ? 2 * rate[idx] : q2[idx];
+                    q2[idx] -= tx; b2[idx] += tx; th2[idx] = a * th2[idx] + b * (double)b2[idx] / slot; --nrem;
+                } while (nrem > 0 && q2[idx] > 0 && (double)rate[idx] / th2[idx] > second);
+                continue;
+            }
+            for (int i = 0; i < n; ++i) {
+                int c = 0;
+                for (int j = 0; j < nev[i]; ++j) c += key[i][j] > T;
+                for (int j = 0; j < c; ++j) {
+                    int64_t tx = 2 * rate[i] < q2[i] ? 2 * rate[i] : q2[i];
+                    q2[i] -= tx; b2[i] += tx; th2[i] = a * th2[i] + b * (double)b2[i] / slot;
+                }
+                nrem -= c;
+            }
+        }
+    }
 #endif
     for (int r = 0; r < n_prb; r += 2) {
         int prbs = n_prb - r < 2 ? n_prb - r : 2;
@@ -338,7 +414,7 @@ static void pf_allocate(orc_env *e, embb_t *sl) {                           /* s
 #ifdef ORC_PF_STATS
         {   /* statistics for the design of the warp kernel's PF loop: how often could the next winner
              * and runner-up be told from the top three of the previous warp-wide argmax alone? */
-            extern unsigned long long orc_pf_stat[8];
+            extern unsigned long long orc_pf_stat[12];
             int nb = 0;
             for (int i = 0; i < n; ++i) nb += queue[i] > 0;
             orc_pf_stat[0] += 1;                                            /* chunks */

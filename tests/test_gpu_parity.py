@@ -320,6 +320,33 @@ def test_multiplexed_l1_vs_oracle_and_facade(tables):
     assert len(info["SLA_labels"]) == 1 and info["n_prbs"] == [150]
 
 
+def test_multiplexed_l1_batched_pf_step_is_taken_and_exact(tables):
+    """The multiplexed-L1 kernel hands out several PRB chunks per warp-wide step when the RB loop is long (embb_warp.cu: events
+    speculated per UE, cut by a threshold on the prefix minima of the metrics).  256 envs x 300 steps with allocations that keep
+    the loop long (60..199 PRBs for ~10 UEs) against the oracle, bit for bit, and the diagnostics counter shows that most chunks
+    of a step do go through the batched step."""
+    scn, N, T, seed = 0, 256, 300, 9090
+    env = make_env(scn, N, seed, L1_level=False)
+    orc = ol.OracleBatch(tables, scn, N, seed, n_threads=8, l1_mux=True)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(11)
+    ok = np.ones(N, bool)
+    batched = 0
+    for t in range(T):
+        a = rng.integers(60, 200, (N, 1)).astype(np.int32)
+        obs, rew, _, info = env.step(a)
+        ok &= (info["flags"] & 1) == 0                      # UE cap (32 here, 64 in the oracle)
+        oo, orr, olab, ovio, _ = orc.step(a)
+        assert np.array_equal(obs[ok], oo[ok]) and np.array_equal(rew[ok].astype(np.float64), orr[ok]), t
+        assert np.array_equal(info["SLA_labels"][ok], olab[ok]) and np.array_equal(info["violations"][ok], ovio[ok]), t
+        if t >= T - 20:
+            batched += env.diag()["pf_batched_chunks_last_step"]
+    assert ok.mean() > 0.95 and env.n_ues().mean() > 8
+    chunks = 20 * N * 50 * 65                               # ~65 chunks per TTI at 130 PRBs on average
+    assert batched > 0.3 * chunks, (batched, chunks)
+    env.close()
+
+
 # ------------------------------------------------------------------------------------------------ round 2: routes, steady state, config surface
 def test_every_route_of_the_default_kernel_is_taken_and_exact(tables):
     """The default kernel routes a unit by its live-UE count: one lane, a pair of lanes (slots 8.. live in the neighbour

@@ -28,11 +28,11 @@ tables = load_tables()
 b = ol.OracleBatch(tables, 0, a.envs, 20260000, n_threads=1, l1_mux=a.mux)
 b.reset()
 rng = np.random.default_rng(5)
-stat = (C.c_ulonglong * 8).in_dll(ol.lib(), "orc_pf_stat")
+stat = (C.c_ulonglong * 12).in_dll(ol.lib(), "orc_pf_stat")
 S, n = b.S, b.envs[0].n_prbs
 for i in range(a.burn + a.steps):
     if i == a.burn:
-        for k in range(8):
+        for k in range(12):
             stat[k] = 0
     if a.mux:
         act = rng.integers(60, 200, (a.envs, S))
@@ -40,6 +40,11 @@ for i in range(a.burn + a.steps):
         w = rng.random((a.envs, S + 1))
         act = np.floor(n * w[:, :S] / w.sum(1, keepdims=True)).astype(np.int64)
     b.step(act)
-chunks, cont, runs, changes, to2, keep3 = [int(stat[k]) for k in range(6)]
+chunks, cont, runs, changes, to2, keep3, bsteps, bcuts = [int(stat[k]) for k in range(8)]
 print("chunks %d  contended %d (%.1f%%)  runs %d (%.2f chunks/run)  winner changes %d: to old runner-up %.1f%%, top-3 set kept %.1f%%"
       % (chunks, cont, 100.0 * cont / chunks, runs, cont / max(runs, 1), changes, 100.0 * to2 / max(changes, 1), 100.0 * keep3 / max(changes, 1)))
+print("batched what-if: %d warp-wide steps (%.2f contended chunks per step; the current loop takes %d), %d of them with a budget cut"
+      % (bsteps, cont / max(bsteps, 1), runs, bcuts))
+att, empty = int(stat[8]), int(stat[9])
+print("   batch attempts %d (%d empty), plain runs %d; cost model (run 1, batch 3, cut +1.5, empty batch +2): %.0f vs %d now"
+      % (att, empty, bsteps - att + empty, (bsteps - att + empty) + 3.0 * (att - empty) + 1.5 * bcuts + 2.0 * empty, runs))
