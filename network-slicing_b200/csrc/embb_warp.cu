@@ -158,10 +158,11 @@ __device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int
 // batched PF step (see the RB loop below): events speculated per UE and step, bisection rounds of the budget cut, and the
 // loop lengths it is tried for (full chunks left, backlogged UEs)
 #ifndef RS_PF_BATCH
-#define RS_PF_BATCH 1             // bit 0: in the multiplexed L1, bit 1: in the per-slice kernel.  Measured (profiles/r02f_pf_batch.txt): the
-#endif                            // multiplexed L1 (12 UEs on ~130 PRBs: ~65 chunks per TTI) 2.45 -> 3.54 M env-steps/s at 16 384 envs; the
-                                  // per-slice kernel (2.8 UEs per slice) loses 9 % to the 2 KB of shared memory (16 instead of 18 warps per
-                                  // SM) and gains nothing on its heavy units, so it stays off there
+#define RS_PF_BATCH 5             // bit 0: in the multiplexed L1, bit 1: in the per-slice kernel (whole batches), bit 2: (heavy list).
+#endif                            // Measured (profiles/r02f_pf_batch.txt): multiplexed L1 (12 UEs on ~130 PRBs: ~65 chunks per TTI) 2.45 -> 3.54 M
+                                  // env-steps/s at 16 384 envs; heavy list: 4096 envs 1.565 -> 1.50 ms/step, env step under KBRL 3.10 -> 2.80 ms;
+                                  // whole per-slice batches (2.8 UEs per slice) lose 9 % to the 2 KB of shared memory (16 instead of 18 warps
+                                  // per SM): off there
 #ifndef RS_PF_SPEC
 #define RS_PF_SPEC 8              // (6: 3.23 M, 8: 3.54 M, 12: 2.88 M)
 #endif
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(WP_WARPS * 32, MIN_WARPS / WP_WARPS) embb_step
     constexpr int TK = MUX ? 32 : WP_K;                          // UE slots per unit (a multiplexed L1 holds the UEs of all its RAN slices)
     __shared__ __align__(16) UeRec s_tbl[WP_WARPS][TK];          // RAN-event scratch (8 / 16 KB)
     __shared__ WarpCtx s_ctx[WP_WARPS];
-    constexpr bool BATCH = MUX ? (RS_PF_BATCH & 1) != 0 : (RS_PF_BATCH & 2) != 0;
+    constexpr bool BATCH = MUX ? (RS_PF_BATCH & 1) != 0 : (RS_PF_BATCH & (MIN_WARPS == RS_WARP_HEAVY_WARPS ? 4 : 2)) != 0;
     __shared__ double s_spec[WP_WARPS][BATCH ? PF_SPEC : 1][BATCH ? 32 : 1];   // speculated working throughputs of the batched PF step (2 KB per warp)
     __shared__ MuxPark s_mux[MUX ? WP_WARPS : 1][MAX_SLICES];
     __shared__ int s_racc[MUX ? WP_WARPS : 1][MAX_SLICES][2][5]; // per (RAN slice, UE type) sums of one TTI: traffic, bits, PRBs, e_snr, UEs

@@ -17,7 +17,7 @@ from . import _lib
 from .scenario_creator import scenarios, state_variables_embb, state_variables_mmtc
 
 alfa = 0.05                 # scenario_creator.py:187
-KBRL_HEAVY_THRESHOLD = 2500   # env routing under a KBRL policy (BatchedRanSlice.set_heavy_threshold; measured)
+KBRL_HEAVY_THRESHOLD = 1800   # env routing under a KBRL policy (BatchedRanSlice.set_heavy_threshold; measured)
 embb_sec, embb_a = (2, 8), (4, 20)        # :190-191
 mmtc_sec, mmtc_a = (1, 4), (2, 10)        # :192-193
 

@@ -28,7 +28,7 @@ ap.add_argument("--warm", type=int, default=20)
 ap.add_argument("--dict-cap", type=int, default=1024)
 ap.add_argument("--pool-mb", type=int, default=0)
 ap.add_argument("--resident", action="store_true")
-ap.add_argument("--heavy", type=int, default=2500, help="heavy-list threshold of the env under the KBRL policy (ranslice_b200.kbrl.KBRL_HEAVY_THRESHOLD); -1: library default")
+ap.add_argument("--heavy", type=int, default=1800, help="heavy-list threshold of the env under the KBRL policy (ranslice_b200.kbrl.KBRL_HEAVY_THRESHOLD); -1: library default")
 ap.add_argument("--report", default="", help="comma-separated step counts at which per-phase times and dictionary statistics are sampled")
 ap.add_argument("--window", type=int, default=20, help="steps averaged ahead of each checkpoint")
 a = ap.parse_args()
