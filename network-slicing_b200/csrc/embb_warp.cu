@@ -161,8 +161,8 @@ __device__ __forceinline__ void tma_load_column(void *dst, const void *tmap, int
 #define RS_PF_BATCH 5             // bit 0: in the multiplexed L1, bit 1: in the per-slice kernel (whole batches), bit 2: (heavy list).
 #endif                            // Measured (profiles/r02f_pf_batch.txt): multiplexed L1 (12 UEs on ~130 PRBs: ~65 chunks per TTI) 2.45 -> 3.54 M
                                   // env-steps/s at 16 384 envs; heavy list: 4096 envs 1.565 -> 1.50 ms/step, env step under KBRL 3.10 -> 2.80 ms;
-                                  // whole per-slice batches (2.8 UEs per slice) lose 9 % to the 2 KB of shared memory (16 instead of 18 warps
-                                  // per SM): off there
+                                  // whole per-slice batches (2.8 UEs per slice, short loops) lose 9-15 % to the attempts that find nothing to
+                                  // hand out: off there
 #ifndef RS_PF_SPEC
 #define RS_PF_SPEC 8              // (6: 3.23 M, 8: 3.54 M, 12: 2.88 M)
 #endif
