@@ -7,7 +7,8 @@
 //   * lane k owns UE k (<= 16 live UEs): traffic source, trace walk, window mean (prefix table), MCS lookup, reception,
 //     transmission_step all run in parallel over the UEs; the UE record stays in the lane's registers for the whole step;
 //   * the PF argmax over the UEs of a chunk (schedulers.py:52) is two warp REDUX instructions on the fp32 metric bits
-//     (+ the exact fp64 comparison when the runner-up is within 1e-6, as in the other kernels);
+//     (+ the exact fp64 comparison when the runner-up is within 1e-6, as in the other kernels); long RB loops hand out
+//     several chunks per warp-wide step (every lane speculates its own UE's next chunks; see the RB loop);
 //   * the per-PRB mutual-information sum of a served UE (channel_models.py:304-310) is spread over all 32 lanes, a quad
 //     of PRBs each, and tree-reduced;
 //   * the end-of-slot accumulators (slice_ran.py:278-305) are integer warp reductions.
